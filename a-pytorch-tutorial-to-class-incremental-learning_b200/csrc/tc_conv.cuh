@@ -1,0 +1,560 @@
+// tc_conv.cuh — tcgen05/TMEM implicit-GEMM kernels for the 3x3 (and 1x1) convolutions of the
+// CIFAR ResNet (reference: resnet.py:29-34,71-72 conv layers; autograd of template.py:270).
+//
+// Data layout in HBM: activations NHWC bf16 (channels 16/32/64, the 3-channel input is zero-padded
+// to 16), weights tap-major bf16 ([tap][n][k], K contiguous), accumulators fp32 in TMEM.
+//
+//   conv_gemm_kernel  : out[pix][n] = sum_tap sum_k A_tap[pix][k] * Wt[tap][n][k]
+//                       fprop  : A = x,  k = cin,  n = cout
+//                       dgrad  : A = dy, k = cout, n = cin, taps flipped (host builds that weight copy)
+//                       M tile = 128 output pixels (full-width rows of one or two images); every tap is one
+//                       TMA box load of the shifted window (out-of-bounds rows/cols zero-filled = padding 1)
+//                       into a K-major swizzled tile; tcgen05.mma M=128, N=n, K=16 steps.
+//   wgrad_gemm_kernel : dW[tap*cin + ci][co] += sum_pix X_tap[pix][ci] * dY[pix][co]
+//                       both operands MN-major straight from the NHWC tiles; the 9 taps are stacked along M
+//                       (LBO = tap-slot stride), K = pixels, accumulators live in TMEM across all of a CTA's
+//                       pixel tiles and are flushed once with vector fp32 reductions.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_idx % 4).
+#pragma once
+#include "tc_prims.cuh"
+
+namespace wacil {
+
+enum ConvEpilogue : int {
+  EPI_RAW = 0,    // bf16 store of the accumulator
+  EPI_STATS = 1,  // bf16 store + per-channel sum / sum-of-squares of the stored (rounded) values
+  EPI_INFER = 2,  // + bias[c] (+ residual) -> ReLU -> bf16 store   (BatchNorm folded into weights/bias)
+};
+
+struct ConvGemmParams {
+  int kc;         // K per tap (input channels of this GEMM): 16 / 32 / 64
+  int nc;         // N (output channels of this GEMM): 16 .. 128, multiple of 16
+  int taps;       // 9 (3x3, pad 1) or 1 (1x1)
+  int stride;     // 1 or 2 (2: A map is the parity-plane view, see make_act_map)
+  int Ht, Nt;     // tile = Nt images x Ht rows x full width; Nt*Ht*Wo == 128
+  int tiles_h;    // tiles per image along H (1 when Nt > 1)
+  int num_tiles;  // ceil(N*Ho*Wo / 128)
+  int num_pixels; // N*Ho*Wo (store guard)
+  int Ho, Wo;     // output spatial size
+  int stages;     // A ring depth
+  int epi;
+  __nv_bfloat16* out;        // [num_pixels][nc]
+  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics)
+  const float* bias;         // [nc] (EPI_INFER)
+  const __nv_bfloat16* res;  // residual (EPI_INFER) or nullptr
+  int res_stride;            // 1: same geometry as out; 2: residual is [N][2Ho][2Wo][res_c] sampled at even pixels
+  int res_c;                 // residual channels (<= nc); channels >= res_c get no residual (zero pad)
+};
+
+__device__ __forceinline__ void tap_coords(int taps, int stride, int tap, int kc, int h0, int n0, int& c0, int& c1,
+                                           int& c2, int& c3, int& c4) {
+  int r = 1, s = 1;
+  if (taps == 9) {
+    r = tap / 3;
+    s = tap - 3 * r;
+  }
+  if (stride == 1) {
+    // dims {C, W, H, N, 1}
+    c0 = 0;
+    c1 = s - 1;
+    c2 = h0 + r - 1;
+    c3 = n0;
+    c4 = 0;
+  } else {
+    // dims {2C, W/2, 2, H/2, N}: input row 2*ho + r - 1 = 2*(ho + dh) + p
+    const int pp = (r == 1) ? 0 : 1, dh = (r == 0) ? -1 : 0;
+    const int qq = (s == 1) ? 0 : 1, dw = (s == 0) ? -1 : 0;
+    c0 = qq * kc;
+    c1 = dw;
+    c2 = pp;
+    c3 = h0 + dh;
+    c4 = n0;
+  }
+}
+
+// Column sums over the 32 lanes of a warp for 16 per-lane values (recursive halving, 16 shuffles).
+// On return lane L holds in v0 the total of column  8*b4 + 4*b3 + 2*b2 + b1  (b_i = bit i of L).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < half) {
+        const float send = upper ? v[i] : v[i + half];
+        const float keep = upper ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int warp_colsum16_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+constexpr int kConvThreads = 192;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+    conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                     const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
+  const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
+  const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
+  const uint32_t w_bytes = p.taps * w_tap_bytes;
+
+  uint8_t* smem_w = smem;
+  uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * a_bytes);
+  uint64_t* full = bars;                  // [stages]
+  uint64_t* empty = bars + p.stages;      // [stages]
+  uint64_t* wfull = bars + 2 * p.stages;  // [1]
+  uint64_t* accfull = wfull + 1;          // [2]
+  uint64_t* accempty = accfull + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2*nc]
+
+  const uint32_t tmem_cols = next_pow2_cols(2u * p.nc);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&accfull[i], 1);
+      mbar_init(&accempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (p.epi == EPI_STATS)
+    for (int i = threadIdx.x; i < 2 * p.nc; i += blockDim.x) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(wfull, w_bytes);
+      for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n0 = (tile / p.tiles_h) * p.Nt;
+        const int h0 = (tile % p.tiles_h) * p.Ht;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], a_bytes);
+          int c0, c1, c2, c3, c4;
+          tap_coords(p.taps, p.stride, tap, p.kc, h0, n0, c0, c1, c2, c3, c4);
+          tma_load_5d(smem_a + stage * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t layout = umma_layout_for_rowbytes(rowbytes);
+      const uint32_t sbo = 8u * rowbytes;
+      const uint32_t idesc = umma_idesc_bf16(128, p.nc, 0, 0);
+      const int ksteps = p.kc / 16;
+      mbar_wait(wfull, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&accempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.nc;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * a_bytes);
+          const uint32_t w_addr = smem_u32(smem_w + tap * w_tap_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
+            const uint64_t bdesc = umma_smem_desc(w_addr + k * 32, 16, sbo, layout);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&accfull[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&accfull[as], aphase);
+      tc_fence_after();
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const __nv_bfloat16* res_ptr = nullptr;
+      if (p.epi == EPI_INFER && p.res != nullptr && valid) {
+        if (p.res_stride == 1) {
+          res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
+        } else {
+          const int w = pix % p.Wo;
+          const int h = (pix / p.Wo) % p.Ho;
+          const int n = pix / (p.Wo * p.Ho);
+          res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+        }
+      }
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * p.nc + c0, v);
+        if (p.epi == EPI_INFER) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
+          if (res_ptr != nullptr && c0 < p.res_c) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res_ptr + c0);
+            uint4 r4[2] = {__ldg(rp), __ldg(rp + 1)};
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(r4);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(rb[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        __align__(16) __nv_bfloat16 ob[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(pix) * p.nc + c0);
+          op[0] = reinterpret_cast<const uint4*>(ob)[0];
+          op[1] = reinterpret_cast<const uint4*>(ob)[1];
+        }
+        if (p.epi == EPI_STATS) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r = valid ? __bfloat162float(ob[i]) : 0.f;
+            s1[i] = r;
+            s2[i] = r * r;
+          }
+          const float t1 = warp_colsum16(s1, lane);
+          const float t2 = warp_colsum16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int c = c0 + warp_colsum16_col(lane);
+            atomicAdd(&s_stats[c], t1);
+            atomicAdd(&s_stats[p.nc + c], t2);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&accempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (p.epi == EPI_STATS) {
+      // the four epilogue warps only: named barrier 1, 128 threads
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      if (blockIdx.x < p.num_tiles)
+        for (int i = e; i < 2 * p.nc; i += 128) atomicAdd(&p.stats[i], s_stats[i]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int cin;            // channels of X (M rows per tap): 16/32/64
+  int cout;           // channels of dY (N): 16/32/64
+  int taps;           // 9 or 1
+  int stride;         // conv stride (selects the X map / tap coordinates)
+  int Ht, Nt;         // tile over OUTPUT pixels: Nt*Ht*Wo == 128
+  int tiles_h;
+  int num_tiles;      // pixel tiles in total
+  int ring;           // group ring depth (32 KB each)
+  float* dw;          // [taps*cin][cout] fp32, accumulated with red.global.add
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+    wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
+                      const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int xrow = p.cin * 2;                 // bytes per pixel row of an X tap tile
+  const int yrow = p.cout * 2;                // bytes per pixel row of the dY tile
+  const uint32_t slot_bytes = 128u * xrow;    // one tap tile
+  const int tpg = 128 / p.cin;                // taps stacked per 128-row M group
+  const int groups = (p.taps + tpg - 1) / tpg;
+  const uint32_t group_bytes = 128u * 128u * 2u;  // tpg * slot_bytes == 32 KB always
+  const uint32_t y_bytes = 128u * yrow;
+
+  uint8_t* smem_g = smem;
+  uint8_t* smem_y = smem + p.ring * group_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_y + 2 * ((y_bytes + 1023) & ~1023u));
+  uint64_t* gfull = bars;              // [ring]
+  uint64_t* gempty = bars + p.ring;    // [ring]
+  uint64_t* yfull = bars + 2 * p.ring; // [2]
+  uint64_t* yempty = yfull + 2;        // [2]
+  uint64_t* accfull = yempty + 2;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+  const uint32_t y_stride = (y_bytes + 1023) & ~1023u;
+
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(groups * p.cout));
+
+  // contiguous chunk of pixel tiles for this CTA
+  const int per = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(p.num_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapDY);
+    for (int i = 0; i < p.ring; ++i) {
+      mbar_init(&gfull[i], 1);
+      mbar_init(&gempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&yfull[i], 1);
+      mbar_init(&yempty[i], 1);
+    }
+    mbar_init(accfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gs = 0, ys = 0;
+      uint32_t gphase = 0, yphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int n0 = (tile / p.tiles_h) * p.Nt;
+        const int h0 = (tile % p.tiles_h) * p.Ht;
+        mbar_wait(&yempty[ys], yphase ^ 1);
+        mbar_expect_tx(&yfull[ys], y_bytes);
+        tma_load_2d(smem_y + ys * y_stride, &mapDY, &yfull[ys], 0, tile * 128);
+        if (++ys == 2) {
+          ys = 0;
+          yphase ^= 1;
+        }
+        for (int g = 0; g < groups; ++g) {
+          const int tap_lo = g * tpg;
+          const int ntap = min(tpg, p.taps - tap_lo);
+          mbar_wait(&gempty[gs], gphase ^ 1);
+          mbar_expect_tx(&gfull[gs], ntap * slot_bytes);
+          for (int j = 0; j < ntap; ++j) {
+            int c0, c1, c2, c3, c4;
+            tap_coords(p.taps, p.stride, tap_lo + j, p.cin, h0, n0, c0, c1, c2, c3, c4);
+            tma_load_5d(smem_g + gs * group_bytes + j * slot_bytes, &mapX, &gfull[gs], c0, c1, c2, c3, c4);
+          }
+          if (++gs == p.ring) {
+            gs = 0;
+            gphase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && t_begin < t_end) {
+      const uint32_t xlayout = umma_layout_for_rowbytes(xrow);
+      const uint32_t ylayout = umma_layout_for_rowbytes(yrow);
+      const uint32_t idesc = umma_idesc_bf16(128, p.cout, 1, 1);
+      int gs = 0, ys = 0;
+      uint32_t gphase = 0, yphase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&yfull[ys], yphase);
+        tc_fence_after();
+        const uint32_t y_addr = smem_u32(smem_y + ys * y_stride);
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&gfull[gs], gphase);
+          tc_fence_after();
+          const uint32_t g_addr = smem_u32(smem_g + gs * group_bytes);
+          const uint32_t d_tmem = tmem_base + g * p.cout;
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {  // 8 K-steps of 16 pixels
+            // MN-major: LBO = stride between MN atoms (tap slots), SBO = stride between 8-pixel K groups
+            const uint64_t adesc = umma_smem_desc(g_addr + j * 16 * xrow, slot_bytes, 8u * xrow, xlayout);
+            const uint64_t bdesc = umma_smem_desc(y_addr + j * 16 * yrow, y_bytes, 8u * yrow, ylayout);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (tile != t_begin) || (j != 0));
+          }
+          umma_commit(&gempty[gs]);
+          if (++gs == p.ring) {
+            gs = 0;
+            gphase ^= 1;
+          }
+        }
+        umma_commit(&yempty[ys]);
+        if (++ys == 2) {
+          ys = 0;
+          yphase ^= 1;
+        }
+      }
+      umma_commit(accfull);
+    }
+  } else if (t_begin < t_end) {
+    const int quarter = warp & 3;
+    mbar_wait(accfull, 0);
+    tc_fence_after();
+    const int rows = p.taps * p.cin;
+    for (int g = 0; g < groups; ++g) {
+      const int row = g * 128 + quarter * 32 + lane;
+      for (int c0 = 0; c0 < p.cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * p.cout + c0, v);
+        if (row < rows) {
+          float* dst = p.dw + static_cast<size_t>(row) * p.cout + c0;
+          red_add_v4(dst + 0, v[0], v[1], v[2], v[3]);
+          red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+          red_add_v4(dst + 8, v[8], v[9], v[10], v[11]);
+          red_add_v4(dst + 12, v[12], v[13], v[14], v[15]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor-map construction and launch helpers (no torch, no allocation).
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_tmap_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for_rowbytes(int rowbytes) {
+  return rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                         : (rowbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// Activation map for a conv whose INPUT is x[N][H][W][C] (bf16) and whose output tile is
+// Nt images x Ht rows x (full output width).  stride 1: dims {C, W, H, N, 1}; stride 2: the parity-plane
+// view {2C, W/2, 2, H/2, N} so that every tap is a unit-stride box.  Returns 0 on success.
+inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int stride, int Ht,
+                        int Nt) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return -100;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t e = 2;
+  if (stride == 1) {
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 1;
+    strides[0] = C * e; strides[1] = W * C * e; strides[2] = (cuuint64_t)H * W * C * e;
+    strides[3] = (cuuint64_t)N * H * W * C * e;
+    box[0] = C; box[1] = W; box[2] = Ht; box[3] = Nt; box[4] = 1;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+    strides[0] = 2 * C * e; strides[1] = W * C * e; strides[2] = 2 * (cuuint64_t)W * C * e;
+    strides[3] = (cuuint64_t)H * W * C * e;
+    box[0] = C; box[1] = W / 2; box[2] = 1; box[3] = Ht; box[4] = Nt;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_rowbytes(C * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1000 - static_cast<int>(r);
+}
+
+// Row-major 2D bf16 matrix [rows][cols] with a {cols, box_rows} box (cols*2 bytes must be 32/64/128).
+inline int make_mat_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows) {
+  PFN_tmapEncodeTiled enc = get_tmap_encode();
+  if (!enc) return -100;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_rowbytes(cols * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1000 - static_cast<int>(r);
+}
+
+inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
+  // 128 output pixels per tile, full-width rows.
+  const int rows = 128 / Wo;  // rows of width Wo per tile
+  if (rows <= Ho) {
+    Ht = rows; Nt = 1; tiles_h = Ho / rows;
+  } else {
+    Ht = Ho; Nt = rows / Ho; tiles_h = 1;
+  }
+}
+
+inline size_t conv_smem_bytes(const ConvGemmParams& p) {
+  const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
+  return 1024 + w + (size_t)p.stages * 128 * p.kc * 2 + (2 * p.stages + 5) * 8 + 16 + 2 * p.nc * 4 + 64;
+}
+inline int conv_pick_stages(int kc, int nc, int taps) {
+  const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
+  const size_t budget = 200 * 1024 - w;
+  int s = (int)(budget / (128 * kc * 2));
+  if (s > 9) s = 9;
+  if (s < 2) s = 2;
+  return s;
+}
+inline size_t wgrad_smem_bytes(const WgradParams& p) {
+  const size_t y = (((size_t)128 * p.cout * 2) + 1023) & ~size_t(1023);
+  return 1024 + (size_t)p.ring * 32768 + 2 * y + (2 * p.ring + 5) * 8 + 64;
+}
+
+}  // namespace wacil
