@@ -1,0 +1,581 @@
+// ew_kernels.cuh — the memory-bound kernels around the tcgen05 convolutions:
+//   pack_input        fp32 NCHW image batch -> bf16 NHWC, 3 channels zero-padded to 16      (template.py:256)
+//   cast_weights      fp32 master weights [9][cin][cout] -> bf16 fprop ([9][cout][cin]) and dgrad
+//                     ([9 flipped][cin][cout]) operand copies, all layers in one launch
+//   fold_bn           eval-mode BatchNorm folded into bf16 weights + fp32 bias (teacher / feature extraction)
+//   bn_apply_fwd      train-mode BatchNorm normalise + affine (+ residual, option-A shortcut) + ReLU,
+//                     running-statistics update                                            (resnet.py:43-53,15-17)
+//   bn_bwd_reduce / bn_bwd_apply   ReLU mask + BatchNorm backward (+ shortcut gradient gather)
+//   pool_fc_fwd / fc_bwd           8x8 average pool + classifier heads                      (resnet.py:114-115,
+//                                                                                          template.py:99-101)
+//   sgd_step          momentum SGD with weight decay on the flat arena                      (template.py:246-247,271)
+//   weight_align      fused row-norm + two-group mean + scale                               (template.py:156-166)
+//   herd_barycenter   iCaRL herding, one CTA per class, float32 order of oracle/herding.c   (template.py:300-302)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wacil {
+
+struct LayerDesc {
+  int cin, cin_pad, cout, stride, H_in, H_out;
+  long long w_off, gamma_off, beta_off;  // params arena (fp32 elements)
+  long long rmean_off, rvar_off;         // bn_running arena
+  long long wf_off, wd_off;              // bf16 weight buffer (elements)
+  long long bias_off;                    // folded bias buffer (fp32 elements)
+};
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& q, float (&v)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __low2float(p[i]);
+    v[2 * i + 1] = __high2float(p[i]);
+  }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float (&v)[8]) {
+  uint4 q;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------ pack
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int HW) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // pixel index
+  if (i >= static_cast<long long>(N) * HW) return;
+  const long long n = i / HW, p = i - n * HW;
+  const float* xp = x + n * 3 * HW + p;
+  float v[8] = {xp[0], xp[HW], xp[2 * HW], 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4* op = reinterpret_cast<uint4*>(out + i * 16);
+  op[0] = float_to_bf16x8(v);
+  op[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+__global__ void cast_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wbuf,
+                                    const LayerDesc* __restrict__ layers) {
+  const LayerDesc L = layers[blockIdx.y];
+  const int n = 9 * L.cin_pad * L.cout;
+  const float* w = params + L.w_off;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int co = e % L.cout;
+    const int ci = (e / L.cout) % L.cin_pad;
+    const int t = e / (L.cout * L.cin_pad);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[e]);
+    wbuf[L.wf_off + (static_cast<long long>(t) * L.cout + co) * L.cin_pad + ci] = v;
+    wbuf[L.wd_off + (static_cast<long long>(8 - t) * L.cin_pad + ci) * L.cout + co] = v;
+  }
+}
+
+__global__ void fold_bn_kernel(const float* __restrict__ params, const float* __restrict__ bn_running,
+                               __nv_bfloat16* __restrict__ wbuf, float* __restrict__ bias,
+                               const LayerDesc* __restrict__ layers, float eps) {
+  const LayerDesc L = layers[blockIdx.y];
+  const int n = 9 * L.cin_pad * L.cout;
+  const float* w = params + L.w_off;
+  const float* g = params + L.gamma_off;
+  const float* b = params + L.beta_off;
+  const float* rm = bn_running + L.rmean_off;
+  const float* rv = bn_running + L.rvar_off;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int co = e % L.cout;
+    const int ci = (e / L.cout) % L.cin_pad;
+    const int t = e / (L.cout * L.cin_pad);
+    const float sc = g[co] * rsqrtf(rv[co] + eps);
+    wbuf[L.wf_off + (static_cast<long long>(t) * L.cout + co) * L.cin_pad + ci] = __float2bfloat16_rn(w[e] * sc);
+    if (e < L.cout) {
+      const float s2 = g[e] * rsqrtf(rv[e] + eps);
+      bias[L.bias_off + e] = b[e] - rm[e] * s2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN forward
+struct BnApplyParams {
+  const __nv_bfloat16* y;    // raw conv output [pix][C]
+  __nv_bfloat16* out;        // [pix][C]
+  const __nv_bfloat16* res;  // residual source or nullptr
+  int res_mode;              // 0 none, 1 same shape, 2 option-A shortcut: res is [N][2Ho][2Wo][C/2]
+  const float* stats;        // [2C] sum, sumsq over the batch
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* saved;              // [2C] mean, rstd (for the backward)
+  int C, Ho, Wo;
+  long long num_pixels;
+  float eps, momentum;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const BnApplyParams p) {
+  __shared__ float s_scale[64], s_shift[64];
+  const float cnt = static_cast<float>(p.num_pixels);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float mean = p.stats[c] / cnt;
+    float var = p.stats[p.C + c] / cnt - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    const float sc = p.gamma[c] * rstd;
+    s_scale[c] = sc;
+    s_shift[c] = p.beta[c] - mean * sc;
+    if (blockIdx.x == 0) {
+      p.saved[c] = mean;
+      p.saved[p.C + c] = rstd;
+      p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (cnt / (cnt - 1.f));
+    }
+  }
+  __syncthreads();
+  const int cv = p.C / 8;
+  const long long total = p.num_pixels * cv;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = v / cv;
+    const int c0 = static_cast<int>(v - pix * cv) * 8;
+    float f[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] * s_scale[c0 + i] + s_shift[c0 + i];
+    if (p.res_mode == 1) {
+      float r[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.res) + v), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    } else if (p.res_mode == 2 && c0 < p.C / 2) {
+      const int w = static_cast<int>(pix % p.Wo);
+      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
+      const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+      const long long rp = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * (p.C / 2) + c0;
+      float r[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.res + rp)), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    reinterpret_cast<uint4*>(p.out)[v] = float_to_bf16x8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+struct BnBwdParams {
+  const __nv_bfloat16* g_main;  // gradient wrt this layer's post-ReLU output [pix][C], or nullptr
+  const float* g_pool;          // or: gradient wrt the pooled features [N][C] (last layer), scaled by inv_hw
+  float inv_hw;
+  const __nv_bfloat16* g_res;   // shortcut gradient from the following block, or nullptr
+  int gres_mode;                // 1: same shape; 2: source is [N][Ho/2][Wo/2][2C], lands on even pixels, channels < C
+  const __nv_bfloat16* act;     // post-ReLU output of this layer (mask)
+  const __nv_bfloat16* y;       // raw conv output
+  const float* saved;           // mean, rstd
+  const float* gamma;
+  float* dgamma;                // grads arena (accumulated by the reduce kernel, read by the apply kernel)
+  float* dbeta;
+  __nv_bfloat16* gy;            // out: gradient wrt the conv output [pix][C]
+  __nv_bfloat16* gy_up;         // optional: same, scattered to even pixels of [N][2Ho][2Wo][C] (stride-2 dgrad input)
+  __nv_bfloat16* gz;            // optional: masked gradient (before BN backward) for the previous block's shortcut
+  int C, Ho, Wo;
+  long long num_pixels;
+};
+
+__device__ __forceinline__ void bn_bwd_load_gz(const BnBwdParams& p, long long pix, int c0, long long v,
+                                               float (&g)[8]) {
+  if (p.g_main) {
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_main) + v), g);
+  } else {
+    const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+    const float4* gp = reinterpret_cast<const float4*>(p.g_pool + n * p.C + c0);
+    const float4 a = __ldg(gp), b = __ldg(gp + 1);
+    g[0] = a.x * p.inv_hw; g[1] = a.y * p.inv_hw; g[2] = a.z * p.inv_hw; g[3] = a.w * p.inv_hw;
+    g[4] = b.x * p.inv_hw; g[5] = b.y * p.inv_hw; g[6] = b.z * p.inv_hw; g[7] = b.w * p.inv_hw;
+  }
+  if (p.g_res) {
+    if (p.gres_mode == 1) {
+      float r[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_res) + v), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += r[i];
+    } else {
+      const int w = static_cast<int>(pix % p.Wo);
+      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
+      if (((w | h) & 1) == 0) {
+        const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+        const long long rp = ((n * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.C) + c0;
+        float r[8];
+        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_res + rp)), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += r[i];
+      }
+    }
+  }
+  float a[8];
+  bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.act) + v), a);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = (a[i] > 0.f) ? g[i] : 0.f;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  __shared__ float s_acc[128];
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int cv = p.C / 8;                 // channel vectors per pixel (2 / 4 / 8)
+  const int lanes = blockDim.x / cv;      // pixels per block pass
+  const int myc = threadIdx.x % cv;
+  const int c0 = myc * 8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = p.saved[c0 + i];
+    rstd[i] = p.saved[p.C + c0 + i];
+  }
+  float sg[8], sx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
+  for (long long pix = blockIdx.x * static_cast<long long>(lanes) + threadIdx.x / cv; pix < p.num_pixels;
+       pix += static_cast<long long>(gridDim.x) * lanes) {
+    const long long v = pix * cv + myc;
+    float g[8], yv[8];
+    bn_bwd_load_gz(p, pix, c0, v, g);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sg[i] += g[i];
+      sx[i] += g[i] * (yv[i] - mean[i]) * rstd[i];
+    }
+  }
+  // combine the threads of a warp that own the same channel vector (lane ids congruent mod cv)
+  for (int o = 16; o >= cv; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sg[i] += __shfl_xor_sync(0xffffffffu, sg[i], o);
+      sx[i] += __shfl_xor_sync(0xffffffffu, sx[i], o);
+    }
+  }
+  if ((threadIdx.x & 31) < cv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[c0 + i], sg[i]);
+      atomicAdd(&s_acc[p.C + c0 + i], sx[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+    atomicAdd(p.dbeta + i, s_acc[i]);
+    atomicAdd(p.dgamma + i, s_acc[p.C + i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  __shared__ float s_k[64], s_a[64], s_b[64], s_mean[64], s_rstd[64];
+  const float inv_m = 1.f / static_cast<float>(p.num_pixels);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float rstd = p.saved[p.C + c];
+    s_mean[c] = p.saved[c];
+    s_rstd[c] = rstd;
+    s_k[c] = p.gamma[c] * rstd;          // dL/dy = k * (gz - a - xhat * b)
+    s_a[c] = p.dbeta[c] * inv_m;
+    s_b[c] = p.dgamma[c] * inv_m;
+  }
+  __syncthreads();
+  const int cv = p.C / 8;
+  const long long total = p.num_pixels * cv;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = v / cv;
+    const int c0 = static_cast<int>(v - pix * cv) * 8;
+    float g[8], yv[8], o[8];
+    bn_bwd_load_gz(p, pix, c0, v, g);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), yv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+      o[i] = s_k[c0 + i] * (g[i] - s_a[c0 + i] - xhat * s_b[c0 + i]);
+    }
+    const uint4 q = float_to_bf16x8(o);
+    reinterpret_cast<uint4*>(p.gy)[v] = q;
+    if (p.gy_up) {
+      const int w = static_cast<int>(pix % p.Wo);
+      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
+      const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+      const long long up = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.C + c0;
+      *reinterpret_cast<uint4*>(p.gy_up + up) = q;
+    }
+    if (p.gz) reinterpret_cast<uint4*>(p.gz)[v] = float_to_bf16x8(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pool + FC
+// One CTA (64 threads) per image: feats = mean over the 8x8 map; logits = feats . W^T + b over C_seen rows.
+__global__ void __launch_bounds__(64) pool_fc_fwd_kernel(const __nv_bfloat16* __restrict__ act, int HW, int D,
+                                                         const float* __restrict__ W, const float* __restrict__ b,
+                                                         int C_seen, float* __restrict__ feats,
+                                                         float* __restrict__ logits) {
+  __shared__ float s_f[64];
+  const int n = blockIdx.x, c = threadIdx.x;
+  const __nv_bfloat16* ap = act + static_cast<long long>(n) * HW * D + c;
+  float s = 0.f;
+  for (int i = 0; i < HW; ++i) s += __bfloat162float(ap[static_cast<long long>(i) * D]);
+  s *= 1.f / static_cast<float>(HW);
+  s_f[c] = s;
+  feats[static_cast<long long>(n) * D + c] = s;
+  __syncthreads();
+  if (logits == nullptr) return;
+  for (int j = c; j < C_seen; j += blockDim.x) {
+    const float4* wp = reinterpret_cast<const float4*>(W + static_cast<long long>(j) * D);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const float4 q = __ldg(wp + k);
+      acc += q.x * s_f[4 * k] + q.y * s_f[4 * k + 1] + q.z * s_f[4 * k + 2] + q.w * s_f[4 * k + 3];
+    }
+    logits[static_cast<long long>(n) * C_seen + j] = acc + __ldg(b + j);
+  }
+}
+
+// blocks [0, C_seen): dW[j][:] and db[j];  blocks [C_seen, C_seen + B): dfeats[b][:].  64 threads, no atomics.
+__global__ void __launch_bounds__(64) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ feats,
+                                                    const float* __restrict__ W, int B, int C_seen, int D,
+                                                    float* __restrict__ dW, float* __restrict__ db,
+                                                    float* __restrict__ dfeats) {
+  const int c = threadIdx.x;
+  if (static_cast<int>(blockIdx.x) < C_seen) {
+    const int j = blockIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (int n = 0; n < B; ++n) {
+      const float g = __ldg(dlogits + static_cast<long long>(n) * C_seen + j);
+      acc += g * __ldg(feats + static_cast<long long>(n) * D + c);
+      accb += g;
+    }
+    dW[static_cast<long long>(j) * D + c] = acc;
+    if (c == 0) db[j] = accb;
+  } else {
+    const int n = blockIdx.x - C_seen;
+    float acc = 0.f;
+    for (int j = 0; j < C_seen; ++j)
+      acc += __ldg(dlogits + static_cast<long long>(n) * C_seen + j) * __ldg(W + static_cast<long long>(j) * D + c);
+    dfeats[static_cast<long long>(n) * D + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SGD
+__global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ v, long long n,
+                                                       const float* __restrict__ lr_dev, float mom, float wd,
+                                                       float gscale) {
+  const float lr = __ldg(lr_dev);
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    vv.x = mom * vv.x + (gg.x * gscale + wd * pp.x); pp.x -= lr * vv.x;
+    vv.y = mom * vv.y + (gg.y * gscale + wd * pp.y); pp.y -= lr * vv.y;
+    vv.z = mom * vv.z + (gg.z * gscale + wd * pp.z); pp.z -= lr * vv.z;
+    vv.w = mom * vv.w + (gg.w * gscale + wd * pp.w); pp.w -= lr * vv.w;
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float vv = mom * v[i] + (g[i] * gscale + wd * p[i]);
+      v[i] = vv;
+      p[i] -= lr * vv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight align
+// Cooperative launch (all CTAs co-resident).  bar[0], bar[1]: grid barrier counters, left at zero.
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (atomicAdd(bar, 0u) < gridDim.x) __nanosleep(64);
+    __threadfence();
+    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+      bar[1] = 0u;
+      __threadfence();
+      bar[0] = 0u;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T> __device__ __forceinline__ float wa_ld(const T* p);
+template <> __device__ __forceinline__ float wa_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float wa_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void wa_st(T* p, float v);
+template <> __device__ __forceinline__ void wa_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void wa_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) weight_align_kernel(T* __restrict__ W, int C_total, int D, int n_new,
+                                                           float* __restrict__ norms, unsigned* bar,
+                                                           float* __restrict__ gamma_out) {
+  __shared__ float s_red[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * 8;
+  constexpr int VW = 16 / sizeof(T);  // elements per 16-byte vector
+  const bool vec = (D % VW) == 0;
+  // phase 1: row norms, one warp per row
+  for (int r = blockIdx.x * 8 + warp; r < C_total; r += warps_total) {
+    const T* row = W + static_cast<long long>(r) * D;
+    float ss = 0.f;
+    if (vec) {
+      for (int k = lane * VW; k < D; k += 32 * VW) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + k);
+        const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int i = 0; i < VW; ++i) {
+          const float f = wa_ld<T>(e + i);
+          ss += f * f;
+        }
+      }
+    } else {
+      for (int k = lane; k < D; k += 32) {
+        const float f = wa_ld<T>(row + k);
+        ss += f * f;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) norms[r] = sqrtf(ss);
+  }
+  grid_barrier(bar);
+  // phase 2: every CTA forms gamma with the same fixed summation order
+  const int C_old = C_total - n_new;
+  float so = 0.f, sn = 0.f;
+  for (int r = threadIdx.x; r < C_total; r += blockDim.x) {
+    const float v = __ldcg(norms + r);
+    if (r < C_old) so += v; else sn += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    so += __shfl_xor_sync(0xffffffffu, so, o);
+    sn += __shfl_xor_sync(0xffffffffu, sn, o);
+  }
+  if (lane == 0) { s_red[0][warp] = so; s_red[1][warp] = sn; }
+  __syncthreads();
+  so = 0.f; sn = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { so += s_red[0][i]; sn += s_red[1][i]; }
+  const float gamma = (so / static_cast<float>(C_old)) / (sn / static_cast<float>(n_new));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gamma_out = gamma;
+  // phase 3: scale the new rows (they are still L2 resident from phase 1)
+  for (int r = C_old + blockIdx.x * 8 + warp; r < C_total; r += warps_total) {
+    T* row = W + static_cast<long long>(r) * D;
+    if (vec) {
+      for (int k = lane * VW; k < D; k += 32 * VW) {
+        uint4 q = *reinterpret_cast<const uint4*>(row + k);
+        T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+        for (int i = 0; i < VW; ++i) wa_st<T>(e + i, gamma * wa_ld<T>(e + i));
+        *reinterpret_cast<uint4*>(row + k) = q;
+      }
+    } else {
+      for (int k = lane; k < D; k += 32) wa_st<T>(row + k, gamma * wa_ld<T>(row + k));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ herding
+// One CTA per class.  Every float32 operation is an explicit round-to-nearest intrinsic in the order of
+// oracle/herding.c, so the selected indices are bit-identical.  dnT: workspace [D][n] (feature-major) so that
+// thread i streams sample i's coordinates with coalesced loads.
+__global__ void __launch_bounds__(256) herd_barycenter_kernel(const float* __restrict__ features,
+                                                              const int* __restrict__ class_offsets, int D, int quota,
+                                                              long long n_total, float* __restrict__ dnT,
+                                                              int* __restrict__ rank, int* __restrict__ out_idx,
+                                                              int* __restrict__ out_count) {
+  extern __shared__ float s_mem[];  // mu[D], w[D]
+  float* s_mu = s_mem;
+  float* s_w = s_mem + D;
+  __shared__ float s_best[8];
+  __shared__ int s_bidx[8];
+  __shared__ int s_pick, s_it, s_eff;
+  const int k_class = blockIdx.x;
+  const int lo = class_offsets[k_class], hi = class_offsets[k_class + 1];
+  const int m = hi - lo;
+  const int take = quota < m ? quota : m;
+  int* oidx = out_idx + static_cast<long long>(k_class) * quota;
+  for (int i = threadIdx.x; i < quota; i += blockDim.x) oidx[i] = -1;
+  if (m <= 0) {
+    if (threadIdx.x == 0) out_count[k_class] = 0;
+    return;
+  }
+  // 1. normalise each sample (sequential over the feature dimension)
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const float* f = features + static_cast<long long>(lo + i) * D;
+    float ss = 0.f;
+    for (int k = 0; k < D; ++k) ss = __fadd_rn(ss, __fmul_rn(f[k], f[k]));
+    const float nrm = __fadd_rn(__fsqrt_rn(ss), 1e-8f);
+    for (int k = 0; k < D; ++k) dnT[static_cast<long long>(k) * n_total + lo + i] = __fdiv_rn(f[k], nrm);
+    rank[lo + i] = 0;
+  }
+  __syncthreads();
+  // 2. mean (sequential over samples)
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    const float* col = dnT + static_cast<long long>(k) * n_total + lo;
+    float s = 0.f;
+    for (int i = 0; i < m; ++i) s = __fadd_rn(s, col[i]);
+    const float mu = __fdiv_rn(s, static_cast<float>(m));
+    s_mu[k] = mu;
+    s_w[k] = mu;
+  }
+  if (threadIdx.x == 0) { s_it = 0; s_eff = 0; }
+  __syncthreads();
+  // 3. greedy selection
+  while (s_it != take && s_eff < 1000) {
+    float best = 0.f;
+    int bi = -1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const float* col = dnT + lo + i;
+      float s = 0.f;
+      for (int k = 0; k < D; ++k) s = __fadd_rn(s, __fmul_rn(s_w[k], col[static_cast<long long>(k) * n_total]));
+      if (bi < 0 || s > best) { best = s; bi = i; }
+    }
+    // first maximum wins: order by (value desc, index asc)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_bidx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = s_best[0];
+      int bidx = s_bidx[0];
+      for (int wv = 1; wv < static_cast<int>(blockDim.x >> 5); ++wv) {
+        const float ob = s_best[wv];
+        const int oi = s_bidx[wv];
+        if (oi >= 0 && (bidx < 0 || ob > b || (ob == b && oi < bidx))) { b = ob; bidx = oi; }
+      }
+      s_pick = bidx;
+      s_eff = s_eff + 1;
+      if (rank[lo + bidx] == 0) {
+        rank[lo + bidx] = 1 + s_it;
+        oidx[s_it] = bidx;
+        s_it = s_it + 1;
+      }
+    }
+    __syncthreads();
+    const int pick = s_pick;
+    for (int k = threadIdx.x; k < D; k += blockDim.x)
+      s_w[k] = __fsub_rn(__fadd_rn(s_w[k], s_mu[k]), dnT[static_cast<long long>(k) * n_total + lo + pick]);
+    __syncthreads();
+  }
+  // 4. iteration cap hit before the quota was filled: unpicked samples follow in index order
+  if (threadIdx.x == 0) {
+    int got = s_it;
+    for (int i = 0; i < m && got < take; ++i)
+      if (rank[lo + i] == 0) oidx[got++] = i;
+    out_count[k_class] = got;
+  }
+}
+
+}  // namespace wacil

@@ -1,0 +1,756 @@
+// wacil_api.cu — implementation of include/wacil.h: C ABI, launch plans, argument checking.
+// Host code only sequences kernels; it never allocates device memory and never synchronises.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wacil.h"
+#include "ew_kernels.cuh"
+#include "loss_kernels.cuh"
+#include "tc_conv.cuh"
+
+using namespace wacil;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e) > 0 ? static_cast<int>(e) : 1;
+}
+#define WACIL_LAUNCH_CHECK(what)                           \
+  do {                                                     \
+    cudaError_t e_ = cudaGetLastError();                   \
+    if (e_ != cudaSuccess) return cuda_fail(e_, what);     \
+  } while (0)
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline int ew_grid(long long work_items, int threads = 256) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr int kFeatDim = 64;
+
+// ---------------------------------------------------------------------------------------- layer geometry
+int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_net_layout_t* lay) {
+  if (depth < 8 || (depth - 2) % 6 != 0) return fail(WACIL_E_SHAPE, "depth %d is not 6n+2", depth);
+  if (max_classes < 0) return fail(WACIL_E_SHAPE, "max_classes %d", max_classes);
+  const int n = (depth - 2) / 6;
+  L.clear();
+  auto add = [&](int cin, int cout, int stride, int H_in) {
+    LayerDesc d{};
+    d.cin = cin;
+    d.cin_pad = cin < 16 ? 16 : cin;
+    d.cout = cout;
+    d.stride = stride;
+    d.H_in = H_in;
+    d.H_out = H_in / stride;
+    L.push_back(d);
+  };
+  add(3, 16, 1, 32);
+  int inpl = 16, H = 32;
+  const int planes[3] = {16, 32, 64};
+  for (int s = 0; s < 3; ++s)
+    for (int b = 0; b < n; ++b) {
+      const int stride = (s > 0 && b == 0) ? 2 : 1;
+      add(inpl, planes[s], stride, H);
+      H /= stride;
+      add(planes[s], planes[s], 1, H);
+      inpl = planes[s];
+    }
+  long long off = 0, boff = 0, woff = 0, bioff = 0;
+  for (auto& d : L) {
+    d.w_off = off;
+    off += 9LL * d.cin_pad * d.cout;
+  }
+  for (auto& d : L) {
+    d.gamma_off = off;
+    off += d.cout;
+    d.beta_off = off;
+    off += d.cout;
+    d.rmean_off = boff;
+    boff += d.cout;
+    d.rvar_off = boff;
+    boff += d.cout;
+    d.wf_off = woff;
+    woff += 9LL * d.cin_pad * d.cout;
+    d.wd_off = woff;
+    woff += 9LL * d.cin_pad * d.cout;
+    d.bias_off = bioff;
+    bioff += d.cout;
+  }
+  if (lay) {
+    lay->depth = depth;
+    lay->n_layers = static_cast<int>(L.size());
+    lay->feat_dim = kFeatDim;
+    off = static_cast<long long>(align_up(off, 4));
+    lay->fc_weight_off = off;
+    off += static_cast<long long>(max_classes) * kFeatDim;
+    lay->fc_bias_off = off;
+    off += max_classes;
+    lay->param_elems = static_cast<long long>(align_up(off, 4));
+    lay->bn_elems = boff;
+  }
+  return 0;
+}
+
+struct Carve {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  }
+};
+
+struct Offsets {
+  size_t table, wbuf, bias, stats, saved, a0, dfeats, gd, gy, gz[2], tmp[3];
+  std::vector<size_t> y, a, gyup;
+  size_t stat_elems = 0, wbuf_elems = 0, total = 0;
+};
+
+void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offsets& o) {
+  Carve c;
+  const size_t nl = L.size();
+  o.table = c.take(nl * sizeof(LayerDesc));
+  size_t wel = 0, sel = 0;
+  for (auto& d : L) {
+    wel += 18ull * d.cin_pad * d.cout;
+    sel += 2ull * d.cout;
+  }
+  o.wbuf_elems = wel;
+  o.stat_elems = sel;
+  o.wbuf = c.take(wel * 2);
+  o.bias = c.take(sel * 2);  // cout floats per layer (<= sel*2 bytes... sized generously: sel*4/2)
+  o.stats = c.take(sel * 4);
+  o.saved = c.take(sel * 4);
+  o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
+  o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
+  size_t max_act = 0;
+  for (auto& d : L) {
+    const size_t in_b = static_cast<size_t>(batch) * d.H_in * d.H_in * d.cin_pad * 2;
+    const size_t out_b = static_cast<size_t>(batch) * d.H_out * d.H_out * d.cout * 2;
+    if (in_b > max_act) max_act = in_b;
+    if (out_b > max_act) max_act = out_b;
+  }
+  o.y.assign(nl, 0);
+  o.a.assign(nl, 0);
+  o.gyup.assign(nl, 0);
+  if (mode == WACIL_NET_TRAIN) {
+    for (size_t l = 0; l < nl; ++l) {
+      const size_t out_b = static_cast<size_t>(batch) * L[l].H_out * L[l].H_out * L[l].cout * 2;
+      o.y[l] = c.take(out_b);
+      o.a[l] = c.take(out_b);
+      if (L[l].stride == 2) o.gyup[l] = c.take(out_b * 4);
+    }
+    o.gd = c.take(max_act);
+    o.gy = c.take(max_act);
+    o.gz[0] = c.take(max_act);
+    o.gz[1] = c.take(max_act);
+    o.tmp[0] = o.tmp[1] = o.tmp[2] = 0;
+  } else {
+    for (int i = 0; i < 3; ++i) o.tmp[i] = c.take(max_act);
+    o.gd = o.gy = o.gz[0] = o.gz[1] = 0;
+  }
+  o.total = c.off;
+}
+
+struct ConvLaunch {
+  CUtensorMap mapA, mapW;
+  ConvGemmParams p;
+  int grid;
+  size_t smem;
+};
+struct WgradLaunch {
+  CUtensorMap mapX, mapDY;
+  WgradParams p;
+  int grid;
+  size_t smem;
+};
+
+int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int nc, int stride, int taps,
+               const void* wts, int epi) {
+  ConvGemmParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = H / stride, Wo = W / stride;
+  p.kc = kc;
+  p.nc = nc;
+  p.taps = taps;
+  p.stride = stride;
+  conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
+  p.num_pixels = N * Ho * Wo;
+  p.num_tiles = (p.num_pixels + 127) / 128;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.stages = conv_pick_stages(kc, nc, taps);
+  p.epi = epi;
+  p.res_stride = 1;
+  p.res_c = nc;
+  int e = make_act_map(&c.mapA, in, N, H, W, kc, stride, p.Ht, p.Nt);
+  if (e) return fail(WACIL_E_DRIVER, "activation tensor map (N=%d H=%d C=%d s=%d): %d", N, H, kc, stride, e);
+  e = make_mat_map(&c.mapW, wts, static_cast<long long>(taps) * nc, kc, nc);
+  if (e) return fail(WACIL_E_DRIVER, "weight tensor map (%dx%d): %d", nc, kc, e);
+  c.grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  c.smem = conv_smem_bytes(p);
+  return 0;
+}
+
+int launch_conv(const ConvLaunch& c, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (c.smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(220 * 1024));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
+    smem_set = 220 * 1024;
+  }
+  conv_gemm_kernel<<<c.grid, kConvThreads, c.smem, st>>>(c.mapA, c.mapW, c.p);
+  WACIL_LAUNCH_CHECK("conv_gemm_kernel");
+  return 0;
+}
+
+int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout,
+                int stride, int taps) {
+  WgradParams& p = w.p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = H / stride, Wo = W / stride;
+  p.cin = cin;
+  p.cout = cout;
+  p.taps = taps;
+  p.stride = stride;
+  conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
+  const long long npix = static_cast<long long>(N) * Ho * Wo;
+  p.num_tiles = static_cast<int>((npix + 127) / 128);
+  p.ring = 4;
+  p.dw = dw;
+  int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
+  if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
+  e = make_mat_map(&w.mapDY, dy, npix, cout, 128);
+  if (e) return fail(WACIL_E_DRIVER, "wgrad dY tensor map: %d", e);
+  int g = (p.num_tiles + 1) / 2;
+  if (g > num_sms()) g = num_sms();
+  if (g < 1) g = 1;
+  w.grid = g;
+  w.smem = wgrad_smem_bytes(p);
+  return 0;
+}
+
+int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(220 * 1024));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad_gemm_kernel)");
+    set = true;
+  }
+  wgrad_gemm_kernel<<<w.grid, kConvThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
+  WACIL_LAUNCH_CHECK("wgrad_gemm_kernel");
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================================ the engine
+struct wacil_net {
+  int depth, batch, max_classes, mode;
+  std::vector<LayerDesc> L;
+  wacil_net_layout_t lay;
+  Offsets off;
+  float *params, *grads, *bn;
+  uint8_t* ws;
+  std::vector<ConvLaunch> fprop, dgrad;
+  std::vector<WgradLaunch> wgrad;
+  bool fwd_done = false;
+  const float* last_feats = nullptr;
+  bool folded = false;
+  int launches = 0;
+
+  template <typename T> T* at(size_t o) const { return reinterpret_cast<T*>(ws + o); }
+  __nv_bfloat16* act_in(int l) const { return l == 0 ? at<__nv_bfloat16>(off.a0) : at<__nv_bfloat16>(off.a[l - 1]); }
+};
+
+extern "C" {
+
+int wacil_version(void) { return 100; }
+const char* wacil_last_error(void) { return g_err.c_str(); }
+
+int wacil_net_layout(int depth, int max_classes, wacil_net_layout_t* out) {
+  if (!out) return fail(WACIL_E_NULL, "out is NULL");
+  std::vector<LayerDesc> L;
+  return build_layers(depth, max_classes, L, out);
+}
+
+int wacil_net_layer_layout(int depth, int max_classes, int layer, wacil_layer_layout_t* out) {
+  if (!out) return fail(WACIL_E_NULL, "out is NULL");
+  std::vector<LayerDesc> L;
+  wacil_net_layout_t lay;
+  int e = build_layers(depth, max_classes, L, &lay);
+  if (e) return e;
+  if (layer < 0 || layer >= static_cast<int>(L.size())) return fail(WACIL_E_SHAPE, "layer %d out of range", layer);
+  const LayerDesc& d = L[layer];
+  out->cin = d.cin; out->cin_pad = d.cin_pad; out->cout = d.cout; out->stride = d.stride;
+  out->H_in = d.H_in; out->H_out = d.H_out;
+  out->w_off = d.w_off; out->gamma_off = d.gamma_off; out->beta_off = d.beta_off;
+  out->rmean_off = d.rmean_off; out->rvar_off = d.rvar_off;
+  return 0;
+}
+
+size_t wacil_net_workspace_bytes(int depth, int batch, int max_classes, int mode) {
+  std::vector<LayerDesc> L;
+  wacil_net_layout_t lay;
+  if (build_layers(depth, max_classes, L, &lay)) return 0;
+  Offsets o;
+  carve_workspace(L, batch, mode, o);
+  return o.total;
+}
+
+int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, int mode, float* params,
+                     float* grads, float* bn_running, void* workspace, size_t workspace_bytes) {
+  if (!out || !params || !bn_running || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (mode != WACIL_NET_TRAIN && mode != WACIL_NET_INFER) return fail(WACIL_E_SHAPE, "mode %d", mode);
+  if (mode == WACIL_NET_TRAIN && !grads) return fail(WACIL_E_NULL, "grads is NULL in TRAIN mode");
+  if (batch < 1) return fail(WACIL_E_SHAPE, "batch %d", batch);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(params) & 15) ||
+      (grads && (reinterpret_cast<uintptr_t>(grads) & 15)))
+    return fail(WACIL_E_ALIGN, "workspace must be 1024-byte aligned, arenas 16-byte aligned");
+  wacil_net* n = new wacil_net();
+  n->depth = depth; n->batch = batch; n->max_classes = max_classes; n->mode = mode;
+  int e = build_layers(depth, max_classes, n->L, &n->lay);
+  if (e) { delete n; return e; }
+  carve_workspace(n->L, batch, mode, n->off);
+  if (workspace_bytes < n->off.total) {
+    delete n;
+    return fail(WACIL_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, n->off.total);
+  }
+  n->params = params; n->grads = grads; n->bn = bn_running; n->ws = static_cast<uint8_t*>(workspace);
+  const size_t nl = n->L.size();
+  cudaError_t ce = cudaMemcpy(n->ws + n->off.table, n->L.data(), nl * sizeof(LayerDesc), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "layer table upload"); }
+  __nv_bfloat16* wbuf = n->at<__nv_bfloat16>(n->off.wbuf);
+  n->fprop.resize(nl);
+  if (mode == WACIL_NET_TRAIN) {
+    n->dgrad.resize(nl);
+    n->wgrad.resize(nl);
+    float* stats = n->at<float>(n->off.stats);
+    size_t soff = 0;
+    for (size_t l = 0; l < nl; ++l) {
+      const LayerDesc& d = n->L[l];
+      ConvLaunch& c = n->fprop[l];
+      e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
+                     wbuf + d.wf_off, EPI_STATS);
+      if (e) { delete n; return e; }
+      c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
+      c.p.stats = stats + soff;
+      soff += 2 * d.cout;
+      // wgrad: X = layer input, dY = GY
+      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy), n->grads + d.w_off, batch,
+                      d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
+      if (e) { delete n; return e; }
+      if (l > 0) {
+        // dgrad: stride-1 conv over GY (or its zero-upsampled copy) with the flipped [cin][cout] weights
+        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy);
+        ConvLaunch& g = n->dgrad[l];
+        e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
+        if (e) { delete n; return e; }
+        g.p.out = n->at<__nv_bfloat16>(n->off.gd);
+        if (d.stride == 2) {
+          ce = cudaMemset(n->ws + n->off.gyup[l], 0,
+                          static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
+          if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "gy_up clear"); }
+        }
+      }
+    }
+  } else {
+    // INFER: block input in tmp[cur], conv_a -> tmp[mid], conv_b (+shortcut from tmp[cur]) -> tmp[nxt]
+    float* bias = n->at<float>(n->off.bias);
+    int cur = 0;
+    for (size_t l = 0; l < nl; ++l) {
+      const LayerDesc& d = n->L[l];
+      ConvLaunch& c = n->fprop[l];
+      const void* in;
+      __nv_bfloat16* outp;
+      const __nv_bfloat16* res = nullptr;
+      int res_stride = 1, res_c = d.cout;
+      if (l == 0) {
+        in = n->at<void>(n->off.a0);
+        outp = n->at<__nv_bfloat16>(n->off.tmp[cur]);
+      } else if (l % 2 == 1) {  // conv_a
+        in = n->at<void>(n->off.tmp[cur]);
+        outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 1) % 3]);
+      } else {  // conv_b
+        in = n->at<void>(n->off.tmp[(cur + 1) % 3]);
+        outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 2) % 3]);
+        res = n->at<__nv_bfloat16>(n->off.tmp[cur]);
+        const LayerDesc& da = n->L[l - 1];
+        if (da.stride == 2 || da.cin != da.cout) { res_stride = 2; res_c = da.cin; }
+        cur = (cur + 2) % 3;
+      }
+      e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
+      if (e) { delete n; return e; }
+      c.p.out = outp;
+      c.p.bias = bias + d.bias_off;
+      c.p.res = res;
+      c.p.res_stride = res_stride;
+      c.p.res_c = res_c;
+    }
+  }
+  *out = n;
+  return 0;
+}
+
+void wacil_net_destroy(wacil_net_t* net) { delete net; }
+
+int wacil_net_last_launches(const wacil_net_t* net) { return net ? net->launches : 0; }
+
+int wacil_net_fold(wacil_net_t* n, void* stream) {
+  if (!n) return fail(WACIL_E_NULL, "net is NULL");
+  if (n->mode != WACIL_NET_INFER) return fail(WACIL_E_STATE, "fold is for INFER plans");
+  dim3 grid(8, static_cast<unsigned>(n->L.size()));
+  fold_bn_kernel<<<grid, 256, 0, S(stream)>>>(n->params, n->bn, n->at<__nv_bfloat16>(n->off.wbuf),
+                                              n->at<float>(n->off.bias), n->at<LayerDesc>(n->off.table), kBnEps);
+  WACIL_LAUNCH_CHECK("fold_bn_kernel");
+  n->folded = true;
+  return 0;
+}
+
+int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, float* logits, void* stream) {
+  if (!n || !x || !feats) return fail(WACIL_E_NULL, "NULL argument");
+  if (C_seen < 0 || C_seen > n->max_classes) return fail(WACIL_E_SHAPE, "C_seen %d > max_classes %d", C_seen, n->max_classes);
+  if (logits == nullptr && C_seen != 0) return fail(WACIL_E_NULL, "logits is NULL but C_seen = %d", C_seen);
+  cudaStream_t st = S(stream);
+  const size_t nl = n->L.size();
+  int launches = 0;
+  int e;
+  const long long npix0 = static_cast<long long>(n->batch) * 32 * 32;
+  pack_input_kernel<<<static_cast<int>((npix0 + 255) / 256), 256, 0, st>>>(x, n->at<__nv_bfloat16>(n->off.a0),
+                                                                         n->batch, 32 * 32);
+  WACIL_LAUNCH_CHECK("pack_input_kernel");
+  ++launches;
+  const __nv_bfloat16* last = nullptr;
+  if (n->mode == WACIL_NET_TRAIN) {
+    cudaError_t ce = cudaMemsetAsync(n->ws + n->off.stats, 0, n->off.stat_elems * 4, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
+    dim3 grid(8, static_cast<unsigned>(nl));
+    cast_weights_kernel<<<grid, 256, 0, st>>>(n->params, n->at<__nv_bfloat16>(n->off.wbuf),
+                                              n->at<LayerDesc>(n->off.table));
+    WACIL_LAUNCH_CHECK("cast_weights_kernel");
+    ++launches;
+    float* saved = n->at<float>(n->off.saved);
+    size_t soff = 0;
+    for (size_t l = 0; l < nl; ++l) {
+      const LayerDesc& d = n->L[l];
+      if ((e = launch_conv(n->fprop[l], st))) return e;
+      BnApplyParams bp{};
+      bp.y = n->at<__nv_bfloat16>(n->off.y[l]);
+      bp.out = n->at<__nv_bfloat16>(n->off.a[l]);
+      bp.res = nullptr;
+      bp.res_mode = 0;
+      if (l >= 2 && l % 2 == 0) {  // conv_b: add the block input through the shortcut
+        const LayerDesc& da = n->L[l - 1];
+        bp.res = n->act_in(static_cast<int>(l) - 1);
+        bp.res_mode = (da.stride == 2 || da.cin != da.cout) ? 2 : 1;
+      }
+      bp.stats = n->fprop[l].p.stats;
+      bp.gamma = n->params + d.gamma_off;
+      bp.beta = n->params + d.beta_off;
+      bp.running_mean = n->bn + d.rmean_off;
+      bp.running_var = n->bn + d.rvar_off;
+      bp.saved = saved + soff;
+      soff += 2 * d.cout;
+      bp.C = d.cout;
+      bp.Ho = d.H_out;
+      bp.Wo = d.H_out;
+      bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
+      bp.eps = kBnEps;
+      bp.momentum = kBnMomentum;
+      bn_apply_fwd_kernel<<<ew_grid(bp.num_pixels * d.cout / 8), 256, 0, st>>>(bp);
+      WACIL_LAUNCH_CHECK("bn_apply_fwd_kernel");
+      launches += 2;
+    }
+    last = n->at<__nv_bfloat16>(n->off.a[nl - 1]);
+  } else {
+    if (!n->folded) return fail(WACIL_E_STATE, "INFER plan used before wacil_net_fold");
+    for (size_t l = 0; l < nl; ++l) {
+      if ((e = launch_conv(n->fprop[l], st))) return e;
+      ++launches;
+    }
+    last = n->fprop[nl - 1].p.out;
+  }
+  pool_fc_fwd_kernel<<<n->batch, 64, 0, st>>>(last, 64, kFeatDim, n->params + n->lay.fc_weight_off,
+                                              n->params + n->lay.fc_bias_off, C_seen, feats, logits);
+  WACIL_LAUNCH_CHECK("pool_fc_fwd_kernel");
+  ++launches;
+  n->launches = launches;
+  n->fwd_done = true;
+  n->last_feats = feats;  // the backward reads them (fc weight gradient)
+  return 0;
+}
+
+int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* stream) {
+  if (!n || !dlogits) return fail(WACIL_E_NULL, "NULL argument");
+  if (n->mode != WACIL_NET_TRAIN) return fail(WACIL_E_STATE, "backward needs a TRAIN plan");
+  if (!n->fwd_done || !n->last_feats) return fail(WACIL_E_STATE, "backward before forward");
+  if (C_seen <= 0 || C_seen > n->max_classes) return fail(WACIL_E_SHAPE, "C_seen %d", C_seen);
+  cudaStream_t st = S(stream);
+  const int nl = static_cast<int>(n->L.size());
+  int launches = 0, e;
+  cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
+  float* dfeats = n->at<float>(n->off.dfeats);
+  fc_bwd_kernel<<<C_seen + n->batch, 64, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
+                                                  C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
+                                                  n->grads + n->lay.fc_bias_off, dfeats);
+  WACIL_LAUNCH_CHECK("fc_bwd_kernel");
+  ++launches;
+  const float* saved = n->at<float>(n->off.saved);
+  std::vector<size_t> soff(nl);
+  {
+    size_t o = 0;
+    for (int l = 0; l < nl; ++l) { soff[l] = o; o += 2 * n->L[l].cout; }
+  }
+  for (int l = nl - 1; l >= 0; --l) {
+    const LayerDesc& d = n->L[l];
+    BnBwdParams bp{};
+    if (l == nl - 1) {
+      bp.g_pool = dfeats;
+      bp.inv_hw = 1.f / static_cast<float>(d.H_out * d.H_out);
+    } else {
+      bp.g_main = n->at<__nv_bfloat16>(n->off.gd);
+    }
+    const bool block_output = (l == 0) || (l % 2 == 0);
+    if (block_output && l + 2 < nl) {
+      const LayerDesc& na = n->L[l + 1];
+      bp.g_res = n->at<__nv_bfloat16>(n->off.gz[(l / 2) % 2]);
+      bp.gres_mode = (na.stride == 2 || na.cin != na.cout) ? 2 : 1;
+    }
+    bp.act = n->at<__nv_bfloat16>(n->off.a[l]);
+    bp.y = n->at<__nv_bfloat16>(n->off.y[l]);
+    bp.saved = saved + soff[l];
+    bp.gamma = n->params + d.gamma_off;
+    bp.dgamma = n->grads + d.gamma_off;
+    bp.dbeta = n->grads + d.beta_off;
+    bp.gy = n->at<__nv_bfloat16>(n->off.gy);
+    bp.gy_up = d.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[l]) : nullptr;
+    bp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
+    bp.C = d.cout;
+    bp.Ho = d.H_out;
+    bp.Wo = d.H_out;
+    bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
+    const int lanes = 256 / (d.cout / 8);
+    int rgrid = static_cast<int>((bp.num_pixels + lanes - 1) / lanes);
+    if (rgrid > num_sms() * 2) rgrid = num_sms() * 2;
+    bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
+    WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8), 256, 0, st>>>(bp);
+    WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    if ((e = launch_wgrad(n->wgrad[l], st))) return e;
+    launches += 3;
+    if (l > 0) {
+      if ((e = launch_conv(n->dgrad[l], st))) return e;
+      ++launches;
+    }
+  }
+  n->launches = launches;
+  return 0;
+}
+
+// ============================================================================================ single ops
+size_t wacil_kd_workspace_bytes(int B) { return 64 + static_cast<size_t>(B > 0 ? B : 0) * 3 * 4; }
+
+extern "C++" {
+namespace {
+template <typename T>
+int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B, int C, float T_, float scale,
+                float* loss_out, void* g, int64_t g_ld, int accumulate, void* ws, cudaStream_t st) {
+  const T* sp = static_cast<const T*>(s);
+  const T* tp = static_cast<const T*>(t);
+  T* gp = static_cast<T*>(g);
+  unsigned* counter = static_cast<unsigned*>(ws);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
+  const float invT = 1.f / T_;
+  const float gscale = scale * T_ / static_cast<float>(B);
+  const float lscale = scale * T_ * T_ / static_cast<float>(B);
+  const size_t vb = 4 * sizeof(T);
+  const bool vec = (C % 4 == 0) && (s_ld % 4 == 0) && (t_ld % 4 == 0) && (!g || g_ld % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(s) % vb == 0) && (reinterpret_cast<uintptr_t>(t) % vb == 0) &&
+                   (!g || reinterpret_cast<uintptr_t>(g) % vb == 0);
+#define KD_LAUNCH(TPR, CACHE, VEC)                                                                              \
+  kd_rows_kernel<T, TPR, CACHE, VEC><<<(B + (256 / TPR) - 1) / (256 / TPR), 256, 0, st>>>(                      \
+      sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp, g_ld, accumulate, part, counter)
+  if (C <= 128) {
+    if (vec) KD_LAUNCH(32, 4, true); else KD_LAUNCH(32, 4, false);
+  } else if (C <= 1024) {
+    if (vec) KD_LAUNCH(32, 32, true); else KD_LAUNCH(32, 32, false);
+  } else if (C <= 2048) {
+    if (vec) KD_LAUNCH(256, 8, true); else KD_LAUNCH(256, 8, false);
+  } else if (C <= 8192) {
+    if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);
+  } else {
+    return fail(WACIL_E_SHAPE, "C = %d > 8192 columns is not supported", C);
+  }
+#undef KD_LAUNCH
+  WACIL_LAUNCH_CHECK("kd_rows_kernel");
+  return 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int wacil_kd_fwd_bwd(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B, int C, float T, float scale,
+                     float* loss_out, void* grad_s, int64_t g_ld, int accumulate, int dtype, void* workspace,
+                     void* stream) {
+  if (!s || !t || !loss_out || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || C <= 0 || s_ld < C || t_ld < C || (grad_s && g_ld < C)) return fail(WACIL_E_SHAPE, "B=%d C=%d", B, C);
+  if (!(T > 0.f)) return fail(WACIL_E_SHAPE, "temperature must be positive");
+  if (dtype == WACIL_F32)
+    return kd_dispatch<float>(s, s_ld, t, t_ld, B, C, T, scale, loss_out, grad_s, g_ld, accumulate, workspace, S(stream));
+  if (dtype == WACIL_BF16)
+    return kd_dispatch<__nv_bfloat16>(s, s_ld, t, t_ld, B, C, T, scale, loss_out, grad_s, g_ld, accumulate, workspace,
+                                      S(stream));
+  return fail(WACIL_E_DTYPE, "dtype %d", dtype);
+}
+
+int wacil_ce_kd_fwd_bwd(const float* logits, int64_t l_ld, const int64_t* targets, const float* t_logits,
+                        int64_t t_ld, int B, int C_seen, int C_known, float T, float lambda_kd, float smooth,
+                        float* losses_out, float* dlogits, int64_t d_ld, void* workspace, void* stream) {
+  if (!logits || !targets || !losses_out || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || C_seen <= 0 || l_ld < C_seen || (dlogits && d_ld < C_seen)) return fail(WACIL_E_SHAPE, "B=%d C=%d", B, C_seen);
+  if (t_logits && (C_known <= 0 || C_known > C_seen || t_ld < C_known)) return fail(WACIL_E_SHAPE, "C_known=%d", C_known);
+  if (!(T > 0.f)) return fail(WACIL_E_SHAPE, "temperature must be positive");
+  if (!t_logits) C_known = 0;
+  unsigned* counter = static_cast<unsigned*>(workspace);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 64);
+  const float invT = 1.f / T;
+  const float gsc = lambda_kd * T / static_cast<float>(B);
+  const float lsc = lambda_kd * T * T / static_cast<float>(B);
+  cudaStream_t st = S(stream);
+#define CK_LAUNCH(TPR, CACHE)                                                                                 \
+  ce_kd_rows_kernel<TPR, CACHE><<<(B + (256 / TPR) - 1) / (256 / TPR), 256, 0, st>>>(                         \
+      logits, l_ld, targets, t_logits, t_ld, B, C_seen, C_known, invT, gsc, lsc, smooth, losses_out, dlogits, \
+      d_ld, part, counter)
+  if (C_seen <= 128) CK_LAUNCH(32, 4);
+  else if (C_seen <= 1024) CK_LAUNCH(32, 32);
+  else if (C_seen <= 8192) CK_LAUNCH(256, 32);
+  else return fail(WACIL_E_SHAPE, "C_seen = %d > 8192", C_seen);
+#undef CK_LAUNCH
+  WACIL_LAUNCH_CHECK("ce_kd_rows_kernel");
+  return 0;
+}
+
+size_t wacil_weight_align_workspace_bytes(int C_total) { return 64 + static_cast<size_t>(C_total > 0 ? C_total : 0) * 4; }
+
+extern "C++" {
+namespace {
+template <typename T>
+int wa_launch(void* W, int C_total, int D, int n_new, float* gamma_out, void* ws, cudaStream_t st) {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weight_align_kernel<T>, 256, 0);
+  if (e != cudaSuccess || occ < 1) return cuda_fail(e, "occupancy(weight_align_kernel)");
+  int grid = (C_total + 7) / 8;
+  const int cap = occ * num_sms();
+  if (grid > cap) grid = cap;
+  T* Wp = static_cast<T*>(W);
+  unsigned* bar = static_cast<unsigned*>(ws);
+  float* norms = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
+  void* args[] = {&Wp, &C_total, &D, &n_new, &norms, &bar, &gamma_out};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(weight_align_kernel<T>), dim3(grid), dim3(256), args, 0, st);
+  if (e != cudaSuccess) return cuda_fail(e, "weight_align_kernel");
+  return 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int wacil_weight_align(void* W, int C_total, int D, int n_new, float* gamma_out, int dtype, void* workspace,
+                       void* stream) {
+  if (!W || !gamma_out || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (C_total <= 1 || D <= 0 || n_new <= 0 || n_new >= C_total)
+    return fail(WACIL_E_SHAPE, "C_total=%d D=%d n_new=%d (need 0 < n_new < C_total)", C_total, D, n_new);
+  if (reinterpret_cast<uintptr_t>(W) & 15) return fail(WACIL_E_ALIGN, "W must be 16-byte aligned");
+  if (dtype == WACIL_F32) return wa_launch<float>(W, C_total, D, n_new, gamma_out, workspace, S(stream));
+  if (dtype == WACIL_BF16) return wa_launch<__nv_bfloat16>(W, C_total, D, n_new, gamma_out, workspace, S(stream));
+  return fail(WACIL_E_DTYPE, "dtype %d", dtype);
+}
+
+int wacil_sgd_step(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
+                   float weight_decay, float grad_scale, void* stream) {
+  if (!p || !g || !v || !lr_dev) return fail(WACIL_E_NULL, "NULL argument");
+  if (n <= 0) return fail(WACIL_E_SHAPE, "n=%lld", static_cast<long long>(n));
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(WACIL_E_ALIGN, "arenas must be 16-byte aligned");
+  sgd_step_kernel<<<ew_grid(n / 4 + 1), 256, 0, S(stream)>>>(p, g, v, n, lr_dev, momentum, weight_decay, grad_scale);
+  WACIL_LAUNCH_CHECK("sgd_step_kernel");
+  return 0;
+}
+
+size_t wacil_herd_workspace_bytes(int64_t n, int D) {
+  if (n <= 0 || D <= 0) return 0;
+  return align_up(static_cast<size_t>(n) * D * 4, 256) + static_cast<size_t>(n) * 4;
+}
+
+int wacil_herd_barycenter(const float* features, int64_t n, const int32_t* class_offsets, int n_classes, int D,
+                          int quota, int32_t* out_idx, int32_t* out_count, void* workspace, void* stream) {
+  if (!features || !class_offsets || !out_idx || !out_count || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (n <= 0 || n_classes <= 0 || D <= 0 || D > 2048 || quota <= 0)
+    return fail(WACIL_E_SHAPE, "n=%lld classes=%d D=%d quota=%d", static_cast<long long>(n), n_classes, D, quota);
+  float* dnT = static_cast<float*>(workspace);
+  int* rank = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + align_up(static_cast<size_t>(n) * D * 4, 256));
+  herd_barycenter_kernel<<<n_classes, 256, 2 * D * sizeof(float), S(stream)>>>(features, class_offsets, D, quota, n, dnT,
+                                                                              rank, out_idx, out_count);
+  WACIL_LAUNCH_CHECK("herd_barycenter_kernel");
+  return 0;
+}
+
+int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int N, int H, int W, int cin, int cout,
+                        int stride, void* stream) {
+  if (!x || !w || !y) return fail(WACIL_E_NULL, "NULL argument");
+  if ((cin != 16 && cin != 32 && cin != 64) || cout % 16 || cout < 16 || cout > 128 || (stride != 1 && stride != 2) ||
+      H != W || (H != 32 && H != 16 && H != 8) || (H / stride) < 8 || N < 1)
+    return fail(WACIL_E_SHAPE, "conv3x3 N=%d H=%d W=%d cin=%d cout=%d stride=%d", N, H, W, cin, cout, stride);
+  ConvLaunch c;
+  int e = setup_conv(c, x, N, H, W, cin, cout, stride, 9, w, stats ? EPI_STATS : EPI_RAW);
+  if (e) return e;
+  c.p.out = static_cast<__nv_bfloat16*>(y);
+  c.p.stats = stats;
+  return launch_conv(c, S(stream));
+}
+
+int wacil_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
+                        void* stream) {
+  if (!x || !dy || !dw) return fail(WACIL_E_NULL, "NULL argument");
+  if ((cin != 16 && cin != 32 && cin != 64) || (cout != 16 && cout != 32 && cout != 64) ||
+      (stride != 1 && stride != 2) || H != W || (H != 32 && H != 16 && H != 8) || (H / stride) < 8 || N < 1)
+    return fail(WACIL_E_SHAPE, "wgrad N=%d H=%d cin=%d cout=%d stride=%d", N, H, cin, cout, stride);
+  WgradLaunch wl;
+  int e = setup_wgrad(wl, x, dy, dw, N, H, W, cin, cout, stride, 9);
+  if (e) return e;
+  return launch_wgrad(wl, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+"""Tensor-level wrappers over the C ABI: each passes data_ptr()s and the current CUDA stream, nothing else.
+Every function raises if its tensors are not CUDA tensors — there is no CPU path."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_ws_cache = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.WacilError("wacil ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _workspace(key, nbytes, device):
+    """Zero-initialised scratch, cached per (kind, size, device); kernels leave their counters re-armed."""
+    k = (key, device)
+    ws = _ws_cache.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[k] = ws
+    return ws
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise _lib.WacilError(f"unsupported dtype {t.dtype}")
+
+
+def kd_fwd_bwd(out_s, out_t, T, scale=1.0, grad_out=None, accumulate=False, need_grad=True, workspace=None):
+    """SoftTarget (utils.py:127-132) forward + backward in one kernel.
+    out_s [B,C] (any row stride, unit column stride), out_t [B,C].  Returns (loss 0-dim fp32, grad or None)."""
+    _need_cuda(out_s, out_t)
+    if out_s.dim() != 2 or out_s.shape != out_t.shape or out_s.dtype != out_t.dtype:
+        raise _lib.WacilError("kd: out_s/out_t must be 2-D with equal shape and dtype")
+    if out_s.stride(1) != 1:
+        out_s = out_s.contiguous()
+    if out_t.stride(1) != 1:
+        out_t = out_t.contiguous()
+    B, Cn = out_s.shape
+    loss = torch.empty((), dtype=torch.float32, device=out_s.device)
+    g = None
+    if need_grad:
+        g = grad_out if grad_out is not None else torch.empty((B, Cn), dtype=out_s.dtype, device=out_s.device)
+        if g.stride(1) != 1:
+            raise _lib.WacilError("kd: grad_out needs unit column stride")
+    ws = workspace if workspace is not None else _workspace("kd", lib().wacil_kd_workspace_bytes(B), out_s.device)
+    check(lib().wacil_kd_fwd_bwd(out_s.data_ptr(), out_s.stride(0), out_t.data_ptr(), out_t.stride(0), B, Cn, float(T),
+                                 float(scale), loss.data_ptr(), g.data_ptr() if g is not None else None,
+                                 g.stride(0) if g is not None else 0, int(bool(accumulate)), _dtype_code(out_s),
+                                 ws.data_ptr(), _stream()), "wacil_kd_fwd_bwd")
+    return loss, g
+
+
+def ce_kd_fwd_bwd(logits, targets, t_logits, known, T=2.0, lambda_kd=0.5, smooth=0.0, losses=None, dlogits=None,
+                  workspace=None):
+    """CE + lambda*KD (template.py:259-266), forward and backward.  Returns (losses[4], dlogits[B,C_seen])."""
+    _need_cuda(logits, targets, t_logits)
+    B, Cs = logits.shape
+    if logits.dtype != torch.float32 or logits.stride(1) != 1 or targets.dtype != torch.int64:
+        raise _lib.WacilError("ce_kd: logits fp32 with unit column stride, targets int64")
+    if losses is None:
+        losses = torch.empty(4, dtype=torch.float32, device=logits.device)
+    if dlogits is None:
+        dlogits = torch.empty((B, Cs), dtype=torch.float32, device=logits.device)
+    ws = workspace if workspace is not None else _workspace("cekd", lib().wacil_kd_workspace_bytes(B), logits.device)
+    tl = None if t_logits is None else t_logits
+    check(lib().wacil_ce_kd_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(),
+                                    tl.data_ptr() if tl is not None else None, tl.stride(0) if tl is not None else 0,
+                                    B, Cs, int(known) if tl is not None else 0, float(T), float(lambda_kd),
+                                    float(smooth), losses.data_ptr(), dlogits.data_ptr(), dlogits.stride(0),
+                                    ws.data_ptr(), _stream()), "wacil_ce_kd_fwd_bwd")
+    return losses, dlogits
+
+
+def weight_align_(W, n_new, gamma_out=None):
+    """In-place WA on the contiguous classifier matrix W [C_total, D] (template.py:156-166); returns gamma (0-dim)."""
+    _need_cuda(W)
+    if W.dim() != 2 or not W.is_contiguous():
+        raise _lib.WacilError("weight_align: W must be a contiguous [C_total, D] matrix")
+    if gamma_out is None:
+        gamma_out = torch.empty((), dtype=torch.float32, device=W.device)
+    ws = _workspace("wa", lib().wacil_weight_align_workspace_bytes(W.shape[0]), W.device)
+    check(lib().wacil_weight_align(W.data_ptr(), W.shape[0], W.shape[1], int(n_new), gamma_out.data_ptr(),
+                                   _dtype_code(W), ws.data_ptr(), _stream()), "wacil_weight_align")
+    return gamma_out
+
+
+def sgd_step_(p, g, v, lr_dev, momentum=0.9, weight_decay=5e-4, grad_scale=1.0):
+    _need_cuda(p, g, v, lr_dev)
+    for t in (p, g, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.WacilError("sgd: flat contiguous fp32 arenas")
+    check(lib().wacil_sgd_step(p.data_ptr(), g.data_ptr(), v.data_ptr(), p.numel(), lr_dev.data_ptr(), float(momentum),
+                               float(weight_decay), float(grad_scale), _stream()), "wacil_sgd_step")
+
+
+def herd_barycenter(features, class_offsets, quota):
+    """features [n,D] fp32 grouped by class; class_offsets int32 [n_classes+1].  Returns (idx [n_classes,quota]
+    int32 row-local, counts [n_classes] int32)."""
+    _need_cuda(features, class_offsets)
+    if features.dtype != torch.float32 or not features.is_contiguous() or class_offsets.dtype != torch.int32:
+        raise _lib.WacilError("herd: features fp32 contiguous, class_offsets int32")
+    n, D = features.shape
+    k = class_offsets.numel() - 1
+    idx = torch.empty((k, quota), dtype=torch.int32, device=features.device)
+    cnt = torch.empty((k,), dtype=torch.int32, device=features.device)
+    ws = _workspace("herd", lib().wacil_herd_workspace_bytes(n, D), features.device)
+    check(lib().wacil_herd_barycenter(features.data_ptr(), n, class_offsets.data_ptr(), k, D, int(quota), idx.data_ptr(),
+                                      cnt.data_ptr(), ws.data_ptr(), _stream()), "wacil_herd_barycenter")
+    return idx, cnt
+
+
+def conv3x3_fprop(x, w, stride=1, want_stats=False):
+    """x [N,H,W,cin] bf16 NHWC, w [9,cout,cin] bf16 -> y [N,H/s,W/s,cout] bf16 (+ stats [2*cout] fp32)."""
+    _need_cuda(x, w)
+    N, H, W_, cin = x.shape
+    cout = w.shape[1]
+    y = torch.empty((N, H // stride, W_ // stride, cout), dtype=torch.bfloat16, device=x.device)
+    stats = torch.zeros(2 * cout, dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib().wacil_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(),
+                                    stats.data_ptr() if stats is not None else None, N, H, W_, cin, cout, stride,
+                                    _stream()), "wacil_conv3x3_fprop")
+    return (y, stats) if want_stats else y
+
+
+def conv3x3_wgrad(x, dy, stride=1):
+    """x [N,H,W,cin] bf16, dy [N,H/s,W/s,cout] bf16 -> dW [9,cin,cout] fp32."""
+    _need_cuda(x, dy)
+    N, H, W_, cin = x.shape
+    cout = dy.shape[3]
+    dw = torch.zeros((9, cin, cout), dtype=torch.float32, device=x.device)
+    check(lib().wacil_conv3x3_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W_, cin, cout, stride, _stream()),
+          "wacil_conv3x3_wgrad")
+    return dw

@@ -1,0 +1,122 @@
+"""Rehearsal memory + barycenter herding with the selection loop on the GPU.
+
+Mirrors `continuum.rehearsal.RehearsalMemory` / `herd_closest_to_barycenter` as the reference uses them
+(template.py:9,212-216,231,300-302; continuum==1.2.2 is a third-party dependency that is not vendored in the
+reference, so the semantics follow its published behaviour — see oracle/wa_oracle.py and DESIGN.md)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+def herd_indices(features, y, nb_per_class, device=None):
+    """Indices (into the rows of `features`) of the exemplars: classes in ascending id order, herding-rank order
+    inside a class.  `features`: [n, D] float32 numpy array or torch tensor; `y`: [n] integer labels."""
+    if isinstance(features, np.ndarray):
+        if features.ndim != 2:
+            raise ValueError(f"Expected features to have 2 dimensions, not {features.ndim}d.")
+        feats = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+    else:
+        if features.dim() != 2:
+            raise ValueError(f"Expected features to have 2 dimensions, not {features.dim()}d.")
+        feats = features.detach().float()
+    if device is None:
+        device = feats.device if feats.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if not torch.cuda.is_available():
+        raise _lib.WacilError("herding runs on the GPU (no CPU fallback)")
+    feats = feats.to(device)
+    y_t = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(device).long()
+    order = torch.argsort(y_t, stable=True)             # group rows by ascending class id, original order inside
+    classes, counts = torch.unique_consecutive(y_t[order], return_counts=True)
+    offsets = torch.zeros(classes.numel() + 1, dtype=torch.int32, device=device)
+    offsets[1:] = torch.cumsum(counts, 0).int()
+    grouped = feats.index_select(0, order).contiguous()
+    idx, cnt = ops.herd_barycenter(grouped, offsets, int(nb_per_class))
+    # row-local -> original indices, trimmed to the per-class counts
+    k, q = idx.shape
+    valid = torch.arange(q, device=device)[None, :] < cnt[:, None]
+    glob = order[(idx.clamp_min(0).long() + offsets[:-1, None].long())]
+    return glob[valid]
+
+
+def herd_closest_to_barycenter(x, y, t, features, nb_per_class):
+    """continuum's function signature: returns (x[idx], y[idx], t[idx])."""
+    idx = herd_indices(features, y, nb_per_class).cpu().numpy()
+    return x[idx], y[idx], t[idx]
+
+
+class RehearsalMemory:
+    """`rehearsal.RehearsalMemory(memory_size, herding_method, fixed_memory)` (template.py:212-216).
+
+    add(x, y, t, features) herds on the GPU; get() returns numpy arrays like upstream.  `dedup_old=False` (default)
+    reproduces the upstream behaviour the reference relies on: the task set passed at template.py:300-302 already
+    contains the old exemplars, they are herded again and appended, so old classes appear twice.  `dedup_old=True`
+    keeps each class once (the 2000-exemplar budget of BASELINE.md)."""
+
+    def __init__(self, memory_size, herding_method="barycenter", fixed_memory=False, nb_total_classes=None,
+                 dedup_old=False):
+        if isinstance(herding_method, str):
+            if herding_method != "barycenter":
+                raise NotImplementedError(f"Unknown rehearsal method {herding_method}.")
+            herding_method = herd_closest_to_barycenter
+        elif not callable(herding_method):
+            raise NotImplementedError("herding_method must be 'barycenter' or a callable")
+        if fixed_memory and nb_total_classes is None:
+            raise ValueError("When memory is fixed, precise the `nb_total_classes` argument.")
+        self.memory_size, self.herding_method = memory_size, herding_method
+        self.fixed_memory, self.nb_total_classes, self.dedup_old = fixed_memory, nb_total_classes, dedup_old
+        self.seen_classes = set()
+        self._x = self._y = self._t = None
+
+    @property
+    def nb_classes(self):
+        return len(self.seen_classes)
+
+    @property
+    def memory_per_class(self):
+        if self.fixed_memory:
+            return self.memory_size // self.nb_total_classes
+        elif self.nb_classes > 0:
+            return self.memory_size // self.nb_classes
+        return self.memory_size
+
+    def __len__(self):
+        return 0 if self._x is None else len(self._x)
+
+    def get(self):
+        return self._x, self._y, self._t
+
+    def save(self, path="memory.npz"):
+        np.savez(path, x=self._x, y=self._y, t=self._t)
+
+    def load(self, path="memory.npz"):
+        data = np.load(path)
+        self._x, self._y, self._t = data["x"], data["y"], data["t"]
+        assert len(self) <= self.memory_size, len(self)
+        self.seen_classes = set(int(c) for c in np.unique(self._y))
+
+    def _reduce(self):
+        xs, ys, ts = [], [], []
+        for class_id in np.unique(self._y):
+            indexes = np.where(self._y == class_id)[0][: self.memory_per_class]
+            xs.append(self._x[indexes]); ys.append(self._y[indexes]); ts.append(self._t[indexes])
+        self._x, self._y, self._t = np.concatenate(xs), np.concatenate(ys), np.concatenate(ts)
+
+    def add(self, x, y, t, z):
+        """z = features of (x, y, t) (template.py:300-302)."""
+        for c in np.unique(y):
+            self.seen_classes.add(int(c))
+        mem_x, mem_y, mem_t = self.herding_method(x, y, t, z, nb_per_class=self.memory_per_class)
+        if self._x is None:
+            self._x, self._y, self._t = mem_x, mem_y, mem_t
+        else:
+            if not self.fixed_memory:
+                self._reduce()
+            if self.dedup_old:
+                keep = ~np.isin(mem_y, np.unique(self._y))
+                mem_x, mem_y, mem_t = mem_x[keep], mem_y[keep], mem_t[keep]
+            self._x = np.concatenate((self._x, mem_x))
+            self._y = np.concatenate((self._y, mem_y))
+            self._t = np.concatenate((self._t, mem_t))

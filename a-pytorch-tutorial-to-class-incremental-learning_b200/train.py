@@ -1,0 +1,338 @@
+"""The WA task loop of the reference's script body (template.py:191-303) as functions.
+
+The reference has no train()/update_model() functions — its loop is inline under `if __name__ == "__main__"`.
+This module provides them as thin wrappers with the same call order and hyper-parameter names:
+
+    update_model(model, args, nb_new, "before")   template.py:241          (add a head)
+    train_task(model, teacher, (x, y), args)      template.py:246-283      (epochs of CE + lambda*KD, SGD, cosine LR)
+    update_model(model, args, nb_new, "after")    template.py:285-290      (weight align, teacher snapshot)
+    TaskTrainer.step(x, y)                        template.py:255-271      (one optimisation step, CUDA-graph replay)
+
+Per-step host synchronisations of the reference (4x .item(), barrier; template.py:272-276) are gone: losses are
+accumulated on the device and read once per epoch."""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .model import CilModel
+
+
+def get_args_parser():
+    """The reference's flags with the same names and defaults (template.py:13-49)."""
+    p = argparse.ArgumentParser("Class-Incremental Learning training and evaluation script", add_help=False)
+    p.add_argument("--seed", default=0, type=int)
+    p.add_argument("--num_bases", default=50, type=int)
+    p.add_argument("--increment", default=10, type=int)
+    p.add_argument("--backbone", default="resnet32", type=str)
+    p.add_argument("--batch_size", default=128, type=int)
+    p.add_argument("--input_size", default=32, type=int)
+    p.add_argument("--color_jitter", default=0.4, type=float)
+    p.add_argument("--aa", type=str, default="rand-m9-mstd0.5-inc1", metavar="NAME")
+    p.add_argument("--reprob", type=float, default=0.0, metavar="PCT")
+    p.add_argument("--remode", type=str, default="pixel")
+    p.add_argument("--recount", type=int, default=1)
+    p.add_argument("--resplit", action="store_true", default=False)
+    p.add_argument("--herding_method", default="barycenter", type=str)
+    p.add_argument("--memory_size", default=2000, type=int)
+    p.add_argument("--fixed_memory", default=False, action="store_true")
+    p.add_argument("--lr", default=0.1, type=float)
+    p.add_argument("--momentum", default=0.9, type=float)
+    p.add_argument("--weight_decay", default=5e-4, type=float)
+    p.add_argument("--num_epochs", default=140, type=int)
+    p.add_argument("--smooth", default=0.0, type=float)
+    p.add_argument("--eval_every_epoch", default=5, type=float)
+    p.add_argument("--dist_url", default="env://")
+    p.add_argument("--data_set", default="cifar")
+    p.add_argument("--data_path", default="/data/data/data/cifar100")
+    p.add_argument("--lambda_kd", default=0.5, type=float)
+    p.add_argument("--dynamic_lambda_kd", action="store_true")
+    return p
+
+
+def init_seed(args):
+    """template.py:52-58."""
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(args.seed)
+
+
+def init_distributed_mode(args):
+    """utils.py:135-153: one process per GPU from torchrun's env; NCCL on GPUs (gloo only for CPU-side tests).
+    Unlike the reference, a plain single-process launch is accepted (world_size 1)."""
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        args.rank = int(os.environ["RANK"])
+        args.world_size = int(os.environ["WORLD_SIZE"])
+        args.gpu = int(os.environ.get("LOCAL_RANK", 0))
+        args.distributed = True
+        cuda = torch.cuda.is_available()
+        if cuda:
+            torch.cuda.set_device(args.gpu)
+        args.dist_backend = "nccl" if cuda else "gloo"
+        if not dist.is_initialized():
+            kw = {"device_id": torch.device("cuda", args.gpu)} if cuda else {}
+            dist.init_process_group(backend=args.dist_backend, init_method=getattr(args, "dist_url", "env://"),
+                                    world_size=args.world_size, rank=args.rank, **kw)
+        dist.barrier()
+    else:
+        args.rank, args.world_size, args.gpu, args.distributed = 0, 1, 0, False
+        if torch.cuda.is_available():
+            torch.cuda.set_device(0)
+
+
+def accuracy(output, target, topk=(1,)):
+    """timm.utils.accuracy as used at template.py:179,267."""
+    maxk = min(max(topk), output.size(1))
+    _, pred = output.topk(maxk, 1, True, True)
+    pred = pred.t()
+    correct = pred.eq(target.reshape(1, -1).expand_as(pred))
+    return [correct[: min(k, maxk)].reshape(-1).float().sum(0) * 100.0 / target.size(0) for k in topk]
+
+
+def cosine_lr(base_lr, epoch, t_max):
+    """CosineAnnealingLR(T_max=num_epochs) stepped once per epoch (template.py:248-249,278)."""
+    return 0.5 * base_lr * (1.0 + math.cos(math.pi * epoch / t_max))
+
+
+def sampler_indices(n, epoch, rank, world_size, seed=0, shuffle=True):
+    """torch.utils.data.DistributedSampler(shuffle=True, drop_last=False) index arithmetic (template.py:232-233,253)."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        idx = torch.randperm(n, generator=g)
+    else:
+        idx = torch.arange(n)
+    total = int(math.ceil(n / world_size)) * world_size
+    if total > n:
+        pad = total - n
+        idx = torch.cat([idx, idx[:pad]]) if pad <= n else torch.cat([idx, idx.repeat(math.ceil(pad / n))[:pad]])
+    return idx[rank:total:world_size]
+
+
+# ------------------------------------------------------------------------------------------------------------
+class _StepState:
+    """Static buffers + captured graph for one batch size."""
+
+    def __init__(self, tr, batch):
+        dev = tr.device
+        self.batch = batch
+        self.x = torch.zeros((batch, 3, 32, 32), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((batch,), dtype=torch.int64, device=dev)
+        self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.dlogits = torch.zeros((batch, tr.c_seen), dtype=torch.float32, device=dev)
+        self.ws = torch.zeros(_lib.lib().wacil_kd_workspace_bytes(batch), dtype=torch.uint8, device=dev)
+        self.plan_s = tr.model._plan(_lib.NET_TRAIN, batch)
+        self.plan_t = None
+        if tr.teacher is not None:
+            self.plan_t = tr.teacher._plan(_lib.NET_INFER, batch)
+            self.plan_t.fold()
+            self.plan_t._folded_version = tr.teacher._fold_version()
+        self.graph_fb = None   # forward + loss + backward (+ SGD when world_size == 1)
+        self.graph_opt = None  # SGD after the all-reduce (world_size > 1)
+        self.warm = 0
+
+
+class TaskTrainer:
+    """One task's optimiser state and step executor (a new one per task, like the reference's per-task SGD and
+    schedule, template.py:246-249)."""
+
+    def __init__(self, model: CilModel, teacher, known_classes, lr=0.1, momentum=0.9, weight_decay=5e-4,
+                 lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None):
+        if not model.arena.is_cuda:
+            raise _lib.WacilError("TaskTrainer needs the model on a CUDA device (no CPU path)")
+        self.model, self.teacher = model, teacher
+        self.device = model.arena.device
+        self.c_seen, self.known = model.num_classes, int(known_classes)
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.lambda_kd, self.T, self.smooth = lambda_kd, T, smooth
+        self.world_size, self.pg = world_size, process_group
+        self.use_graph = use_graph
+        self.mom = torch.zeros_like(model._arena.params)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+        self.acc = torch.zeros(4, dtype=torch.float32, device=self.device)  # running sums of [ce, kd, loss, top1]
+        self.steps_done = 0
+        self._states = {}
+        self.launches_per_step = 0
+        if teacher is not None and teacher.num_classes != self.known:
+            raise _lib.WacilError(f"teacher has {teacher.num_classes} classes, known_classes = {self.known}")
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr))
+
+    # -- pieces -------------------------------------------------------------------------------------------------
+    def _fwd_bwd(self, st):
+        logits, _ = st.plan_s.forward(st.x, self.c_seen)
+        n = st.plan_s.launches
+        t_logits = None
+        if st.plan_t is not None:
+            t_logits, _ = st.plan_t.forward(st.x, self.known)
+            n += st.plan_t.launches
+        ops.ce_kd_fwd_bwd(logits, st.y, t_logits, self.known, self.T, self.lambda_kd, self.smooth, st.losses,
+                          st.dlogits, st.ws)
+        st.plan_s.backward(st.dlogits)
+        n += st.plan_s.launches + 1
+        self.acc.add_(st.losses)
+        return n
+
+    def _opt(self):
+        a = self.model._arena
+        ops.sgd_step_(a.params, a.grads, self.mom, self.lr_dev, self.momentum, self.weight_decay,
+                      1.0 / self.world_size)
+        return 1
+
+    def _run(self, st):
+        single = self.world_size == 1
+        if not self.use_graph or st.warm < 2:
+            n = self._fwd_bwd(st)
+            if not single:
+                dist.all_reduce(self.model._arena.grads, group=self.pg)
+            n += self._opt()
+            st.warm += 1
+            self.launches_per_step = n
+            return
+        if st.graph_fb is None:
+            torch.cuda.synchronize()
+            st.graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.graph_fb):
+                self._fwd_bwd(st)
+                if single:
+                    self._opt()
+            if not single:
+                st.graph_opt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st.graph_opt):
+                    self._opt()
+                dist.all_reduce(self.model._arena.grads, group=self.pg)
+                st.graph_opt.replay()
+            return  # capture executed nothing for forward/backward: the caller's step counts from the next replay
+        st.graph_fb.replay()
+        if not single:
+            dist.all_reduce(self.model._arena.grads, group=self.pg)
+            st.graph_opt.replay()
+
+    def step(self, x, y):
+        """One optimisation step (template.py:255-271) on a [B,3,32,32] fp32 batch and int64 targets; `x`/`y` may live
+        in pinned host memory (copied asynchronously) or on the device.  Returns the device tensor [ce, kd, loss, top1
+        count] of this step (no host sync)."""
+        b = x.shape[0]
+        st = self._states.get(b)
+        if st is None:
+            st = self._states[b] = _StepState(self, b)
+        st.x.copy_(x, non_blocking=True)
+        st.y.copy_(y, non_blocking=True)
+        captured_now = self.use_graph and st.warm >= 2 and st.graph_fb is None
+        self._run(st)
+        if captured_now:
+            self._run(st)  # the capture itself did not execute the step
+        self.steps_done += 1
+        self.model._num_batches_tracked += 1
+        self.model._touch()
+        return st.losses
+
+    def epoch_stats(self, n_samples):
+        """Means of ce / kd / loss and top-1 % since the last call (one host sync per epoch)."""
+        acc = self.acc.clone()
+        if self.world_size > 1:
+            dist.all_reduce(acc, group=self.pg)
+        steps = max(self.steps_done, 1)
+        ce, kd, loss, top1 = acc.tolist()
+        self.acc.zero_()
+        out = {"ce": ce / (steps * self.world_size), "kd": kd / (steps * self.world_size),
+               "loss": loss / (steps * self.world_size), "acc1": 100.0 * top1 / max(n_samples, 1)}
+        self.steps_done = 0
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+def train_task(model, teacher_model, data, args, rank=None, world_size=None, num_epochs=None, use_graph=True,
+               on_epoch_end=None, log=print):
+    """Train `model` on one task (template.py:246-283).  `data` = (x [N,3,32,32] fp32, y [N] int64) for this task
+    (new samples U rehearsal memory), device-resident or pinned host tensors.  Returns the per-epoch stats."""
+    x_all, y_all = data
+    rank = getattr(args, "rank", 0) if rank is None else rank
+    world_size = getattr(args, "world_size", 1) if world_size is None else world_size
+    epochs = args.num_epochs if num_epochs is None else num_epochs
+    bs = args.batch_size
+    known = getattr(args, "known_classes", 0)
+    if teacher_model is None:
+        known = 0
+    tr = TaskTrainer(model, teacher_model, known, lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay,
+                     lambda_kd=args.lambda_kd, T=2.0, smooth=getattr(args, "smooth", 0.0), world_size=world_size,
+                     use_graph=use_graph)
+    n = x_all.shape[0]
+    history = []
+    on_dev = x_all.is_cuda
+    for epoch in range(epochs):
+        model.train()
+        tr.set_lr(cosine_lr(args.lr, epoch, epochs))
+        idx = sampler_indices(n, epoch, rank, world_size, seed=0, shuffle=True)
+        if on_dev:
+            idx = idx.to(x_all.device)
+        seen = 0
+        for s in range(0, idx.numel(), bs):
+            bi = idx[s: s + bs]
+            tr.step(x_all.index_select(0, bi), y_all.index_select(0, bi))
+            seen += bi.numel()
+        stats = tr.epoch_stats(seen * world_size)
+        stats["epoch"], stats["lr"] = epoch + 1, cosine_lr(args.lr, epoch, epochs)
+        history.append(stats)
+        if log is not None and rank == 0:
+            log(f"train states: epoch :[{epoch + 1}/{epochs}] ce: {stats['ce']:.4f}  kd: {stats['kd']:.4f}  "
+                f"loss: {stats['loss']:.4f}  acc1: {stats['acc1']:.4f}")
+        if on_epoch_end is not None:
+            on_epoch_end(epoch, stats)
+    return history
+
+
+def update_model(model, args, nb_new_classes, stage):
+    """stage "before": grow the classifier by one head (template.py:241).
+    stage "after": weight-align when task_id > 0 and snapshot the frozen teacher (template.py:285-290); returns it."""
+    if stage == "before":
+        model.prev_model_adaption(nb_new_classes)
+        return model
+    if stage == "after":
+        model.after_model_adaption(nb_new_classes, args)
+        return model.copy().freeze()
+    raise ValueError(stage)
+
+
+@torch.no_grad()
+def extract_features(model, x_all, batch_size=128):
+    """Features of every sample for herding (template.py:292-299), eval-mode BN, kept on the device."""
+    was_training = model.training
+    model.eval()
+    outs = []
+    for s in range(0, x_all.shape[0], batch_size):
+        xb = x_all[s: s + batch_size]
+        if not xb.is_cuda:
+            xb = xb.to(model.arena.device, non_blocking=True)
+        outs.append(model.extract_vector(xb.contiguous()))
+    model.train(was_training)
+    return torch.cat(outs, 0)
+
+
+@torch.no_grad()
+def eval(model, val_loader):  # noqa: A001  (the reference's name, template.py:169-188)
+    """Top-1 accuracy (%) over an iterable of (images, target, task_ids); cross-rank mean when distributed."""
+    model.eval()
+    dev = model.arena.device
+    tot = torch.zeros(4, dtype=torch.float64, device=dev)  # n, loss*n, top1*n, top5*n
+    for images, target, *_ in val_loader:
+        images, target = images.to(dev, non_blocking=True), target.to(dev, non_blocking=True)
+        logits, _ = model(images.contiguous().float())
+        loss = torch.nn.functional.cross_entropy(logits, target)
+        a1, a5 = accuracy(logits, target, topk=(1, min(5, logits.shape[1])))
+        b = images.shape[0]
+        tot += torch.stack([torch.tensor(float(b), device=dev, dtype=torch.float64), loss.double() * b,
+                            a1.double() * b, a5.double() * b])
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(tot)
+    n = max(tot[0].item(), 1.0)
+    print(" Acc@1 {:.3f}  loss {:.3f}".format(tot[2].item() / n, tot[1].item() / n))
+    return tot[2].item() / n
