@@ -153,3 +153,27 @@ def test_rehearsal_memory_quota_and_reduce():
     x, y, t = mem.get()
     assert mem.memory_per_class == 10 and len(x) == 40
     assert all((y == c).sum() == 10 for c in range(4))
+
+
+# ------------------------------------------------------------------------- mixed-precision model of the same step
+@pytest.mark.parametrize("depth,heads", [(20, [10, 10]), (32, [10])])
+def test_manual_backward_model_equals_autograd_oracle_when_rounding_is_off(depth, heads):
+    """oracle/wa_oracle_bf16.py with rounding disabled must reproduce the fp32 oracle (which is pinned to the
+    reference): that ties the bf16 model used for GPU gradient parity back to the reference."""
+    import wa_oracle_bf16 as wb
+    sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in wo.make_state(depth, heads, 7).items()}
+    tsd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in wo.make_state(depth, heads[:1], 8).items()}
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(6, 3, 32, 32, generator=gen).double()
+    y = torch.randint(0, sum(heads), (6,), generator=gen)
+    known = 10 if len(heads) > 1 else 0
+    r = wo.train_step(dict(sd), tsd if known else None, x, y, depth, known, 0.1, {}, apply_update=False)
+    t_logits = r["t_logits"]
+    m = wb.forward_backward(sd, x, depth, wb.ce_kd_dlogits(y, t_logits, known), rnd=wb.identity)
+    np.testing.assert_allclose(m["logits"].numpy(), r["logits"].numpy(), rtol=1e-9, atol=1e-10)
+    for k, g in r["grads"].items():
+        np.testing.assert_allclose(m["grads"][k].numpy(), g.numpy(), rtol=1e-7, atol=1e-10 * (1 + g.abs().max().item()),
+                                   err_msg=k)
+    for k, v in r["new_buffers"].items():
+        if v.dtype.is_floating_point:
+            np.testing.assert_allclose(m["new_buffers"][k].numpy(), v.numpy(), rtol=1e-9, atol=1e-12)
