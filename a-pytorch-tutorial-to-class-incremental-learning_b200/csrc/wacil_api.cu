@@ -430,6 +430,30 @@ void wacil_net_destroy(wacil_net_t* net) { delete net; }
 
 int wacil_net_last_launches(const wacil_net_t* net) { return net ? net->launches : 0; }
 
+int wacil_net_tensor(const wacil_net_t* n, int what, int layer, void** ptr, size_t* bytes) {
+  if (!n || !ptr || !bytes) return fail(WACIL_E_NULL, "NULL argument");
+  if (n->mode != WACIL_NET_TRAIN) return fail(WACIL_E_STATE, "only TRAIN plans keep their activations");
+  const int nl = static_cast<int>(n->L.size());
+  if (what != WACIL_T_INPUT && (layer < 0 || layer >= nl)) return fail(WACIL_E_SHAPE, "layer %d", layer);
+  if (what == WACIL_T_INPUT) {
+    *ptr = n->ws + n->off.a0;
+    *bytes = static_cast<size_t>(n->batch) * 32 * 32 * 16 * 2;
+    return 0;
+  }
+  const LayerDesc& d = n->L[layer];
+  const size_t act = static_cast<size_t>(n->batch) * d.H_out * d.H_out * d.cout * 2;
+  if (what == WACIL_T_CONV_OUT) { *ptr = n->ws + n->off.y[layer]; *bytes = act; return 0; }
+  if (what == WACIL_T_ACT) { *ptr = n->ws + n->off.a[layer]; *bytes = act; return 0; }
+  if (what == WACIL_T_BN_SAVED) {
+    size_t o = 0;
+    for (int l = 0; l < layer; ++l) o += 2 * n->L[l].cout;
+    *ptr = n->ws + n->off.saved + o * 4;
+    *bytes = 2 * d.cout * 4;
+    return 0;
+  }
+  return fail(WACIL_E_SHAPE, "what %d", what);
+}
+
 int wacil_net_fold(wacil_net_t* n, void* stream) {
   if (!n) return fail(WACIL_E_NULL, "net is NULL");
   if (n->mode != WACIL_NET_INFER) return fail(WACIL_E_STATE, "fold is for INFER plans");

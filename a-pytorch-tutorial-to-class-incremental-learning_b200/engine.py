@@ -140,6 +140,20 @@ class Plan:
         check(lib().wacil_net_backward(self.handle, dlogits.data_ptr(), dlogits.shape[1],
                                        torch.cuda.current_stream().cuda_stream), "wacil_net_backward")
 
+    def tensor(self, what, layer=0):
+        """A view of a tensor the TRAIN plan keeps after a forward (parity tests): 0 packed input, 1 conv output,
+        2 activation (all bf16 NHWC), 3 BatchNorm batch mean / rstd (fp32 [2, C])."""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        check(lib().wacil_net_tensor(self.handle, what, layer, C.byref(ptr), C.byref(nbytes)), "wacil_net_tensor")
+        off = ptr.value - self.workspace.data_ptr()
+        raw = self.workspace[off: off + nbytes.value]
+        if what == 3:
+            return raw.view(torch.float32).view(2, -1)
+        if what == 0:
+            return raw.view(torch.bfloat16).view(self.batch, 32, 32, 16)
+        ll = self.arena.layers[layer]
+        return raw.view(torch.bfloat16).view(self.batch, ll.H_out, ll.H_out, ll.cout)
+
     @property
     def launches(self):
         return lib().wacil_net_last_launches(self.handle)

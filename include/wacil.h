@@ -158,6 +158,16 @@ int wacil_net_forward(wacil_net_t* net, const float* x, int C_seen, float* feats
  * accumulated: the arena is zeroed inside).  feats/logits of that forward must still be intact. */
 int wacil_net_backward(wacil_net_t* net, const float* dlogits, int C_seen, void* stream);
 
+/* Introspection for the parity tests: device pointer + size of a tensor the TRAIN plan keeps in its workspace
+ * after a forward: WACIL_T_INPUT packed input bf16 [B][32][32][16] (layer ignored); WACIL_T_CONV_OUT raw conv
+ * output y_l bf16 [B][H][W][C]; WACIL_T_ACT post-BN/ReLU activation a_l bf16; WACIL_T_BN_SAVED fp32 [2C] batch mean
+ * and 1/sqrt(var+eps) of layer l. */
+#define WACIL_T_INPUT 0
+#define WACIL_T_CONV_OUT 1
+#define WACIL_T_ACT 2
+#define WACIL_T_BN_SAVED 3
+int wacil_net_tensor(const wacil_net_t* net, int what, int layer, void** ptr, size_t* bytes);
+
 /* Number of kernels the last forward / backward call launched (for bench.py's gpu_launches). */
 int wacil_net_last_launches(const wacil_net_t* net);
 
