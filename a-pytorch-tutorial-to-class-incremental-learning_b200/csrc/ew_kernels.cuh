@@ -129,34 +129,50 @@ __global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const BnApplyParams p
     }
   }
   __syncthreads();
+  // Each thread owns one 8-channel group (grid stride is a multiple of C/8) and streams kU vectors per pass with
+  // all loads issued before the first use.
+  constexpr int kU = 4;
   const int cv = p.C / 8;
   const long long total = p.num_pixels * cv;
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pix = v / cv;
-    const int c0 = static_cast<int>(v - pix * cv) * 8;
-    float f[8];
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), f);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int c0 = static_cast<int>(v0 % cv) * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = f[i] * s_scale[c0 + i] + s_shift[c0 + i];
-    if (p.res_mode == 1) {
-      float r[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.res) + v), r);
+  for (int i = 0; i < 8; ++i) { sc[i] = s_scale[c0 + i]; sh[i] = s_shift[c0 + i]; }
+  const bool res_a = p.res_mode == 2 && c0 < p.C / 2;
+  for (long long vb = v0; vb < total; vb += stride * kU) {
+    uint4 qy[kU], qr[kU];
+    bool ok[kU];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
-    } else if (p.res_mode == 2 && c0 < p.C / 2) {
-      const int w = static_cast<int>(pix % p.Wo);
-      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
-      const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-      const long long rp = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * (p.C / 2) + c0;
-      float r[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.res + rp)), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    for (int j = 0; j < kU; ++j) {
+      const long long v = vb + j * stride;
+      ok[j] = v < total;
+      qr[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[j]) {
+        qy[j] = __ldg(reinterpret_cast<const uint4*>(p.y) + v);
+        if (p.res_mode == 1) {
+          qr[j] = __ldg(reinterpret_cast<const uint4*>(p.res) + v);
+        } else if (res_a) {
+          const long long pix = v / cv;
+          const int w = static_cast<int>(pix % p.Wo);
+          const int h = static_cast<int>((pix / p.Wo) % p.Ho);
+          const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+          const long long rp = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * (p.C / 2) + c0;
+          qr[j] = __ldg(reinterpret_cast<const uint4*>(p.res + rp));
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    reinterpret_cast<uint4*>(p.out)[v] = float_to_bf16x8(f);
+    for (int j = 0; j < kU; ++j) {
+      if (!ok[j]) continue;
+      float f[8], r[8];
+      bf16x8_to_float(qy[j], f);
+      bf16x8_to_float(qr[j], r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i] * sc[i] + sh[i] + r[i], 0.f);
+      reinterpret_cast<uint4*>(p.out)[vb + j * stride] = float_to_bf16x8(f);
+    }
   }
 }
 
@@ -180,38 +196,62 @@ struct BnBwdParams {
   long long num_pixels;
 };
 
-__device__ __forceinline__ void bn_bwd_load_gz(const BnBwdParams& p, long long pix, int c0, long long v,
-                                               float (&g)[8]) {
+// Raw 16-byte loads of everything one output vector needs, issued together; decode happens later.
+struct BnBwdRaw {
+  uint4 g, r, a, y;
+  float gp[8];
+  bool has_r;
+};
+
+__device__ __forceinline__ void bn_bwd_issue_loads(const BnBwdParams& p, long long pix, int c0, long long v,
+                                                   BnBwdRaw& raw) {
+  raw.has_r = false;
   if (p.g_main) {
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_main) + v), g);
+    raw.g = __ldg(reinterpret_cast<const uint4*>(p.g_main) + v);
   } else {
     const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
     const float4* gp = reinterpret_cast<const float4*>(p.g_pool + n * p.C + c0);
     const float4 a = __ldg(gp), b = __ldg(gp + 1);
-    g[0] = a.x * p.inv_hw; g[1] = a.y * p.inv_hw; g[2] = a.z * p.inv_hw; g[3] = a.w * p.inv_hw;
-    g[4] = b.x * p.inv_hw; g[5] = b.y * p.inv_hw; g[6] = b.z * p.inv_hw; g[7] = b.w * p.inv_hw;
+    raw.gp[0] = a.x; raw.gp[1] = a.y; raw.gp[2] = a.z; raw.gp[3] = a.w;
+    raw.gp[4] = b.x; raw.gp[5] = b.y; raw.gp[6] = b.z; raw.gp[7] = b.w;
   }
   if (p.g_res) {
     if (p.gres_mode == 1) {
-      float r[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_res) + v), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] += r[i];
+      raw.r = __ldg(reinterpret_cast<const uint4*>(p.g_res) + v);
+      raw.has_r = true;
     } else {
       const int w = static_cast<int>(pix % p.Wo);
       const int h = static_cast<int>((pix / p.Wo) % p.Ho);
       if (((w | h) & 1) == 0) {
         const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
         const long long rp = ((n * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.C) + c0;
-        float r[8];
-        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.g_res + rp)), r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] += r[i];
+        raw.r = __ldg(reinterpret_cast<const uint4*>(p.g_res + rp));
+        raw.has_r = true;
       }
     }
   }
+  raw.a = __ldg(reinterpret_cast<const uint4*>(p.act) + v);
+  raw.y = __ldg(reinterpret_cast<const uint4*>(p.y) + v);
+}
+
+// masked gradient gz (fp32) and raw conv output y (fp32) of one vector
+__device__ __forceinline__ void bn_bwd_decode(const BnBwdParams& p, const BnBwdRaw& raw, float (&g)[8],
+                                              float (&yv)[8]) {
+  if (p.g_main) {
+    bf16x8_to_float(raw.g, g);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = raw.gp[i] * p.inv_hw;
+  }
+  if (raw.has_r) {
+    float r[8];
+    bf16x8_to_float(raw.r, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += r[i];
+  }
   float a[8];
-  bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.act) + v), a);
+  bf16x8_to_float(raw.a, a);
+  bf16x8_to_float(raw.y, yv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = (a[i] > 0.f) ? g[i] : 0.f;
 }
@@ -220,6 +260,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   __shared__ float s_acc[128];
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
+  constexpr int kU = 2;
   const int cv = p.C / 8;                 // channel vectors per pixel (2 / 4 / 8)
   const int lanes = blockDim.x / cv;      // pixels per block pass
   const int myc = threadIdx.x % cv;
@@ -233,16 +274,27 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
   float sg[8], sx[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
-  for (long long pix = blockIdx.x * static_cast<long long>(lanes) + threadIdx.x / cv; pix < p.num_pixels;
-       pix += static_cast<long long>(gridDim.x) * lanes) {
-    const long long v = pix * cv + myc;
-    float g[8], yv[8];
-    bn_bwd_load_gz(p, pix, c0, v, g);
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), yv);
+  const long long pstride = static_cast<long long>(gridDim.x) * lanes;
+  for (long long pb = blockIdx.x * static_cast<long long>(lanes) + threadIdx.x / cv; pb < p.num_pixels;
+       pb += pstride * kU) {
+    BnBwdRaw raw[kU];
+    bool ok[kU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sg[i] += g[i];
-      sx[i] += g[i] * (yv[i] - mean[i]) * rstd[i];
+    for (int j = 0; j < kU; ++j) {
+      const long long pix = pb + j * pstride;
+      ok[j] = pix < p.num_pixels;
+      if (ok[j]) bn_bwd_issue_loads(p, pix, c0, pix * cv + myc, raw[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      if (!ok[j]) continue;
+      float g[8], yv[8];
+      bn_bwd_decode(p, raw[j], g, yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] += g[i];
+        sx[i] += g[i] * (yv[i] - mean[i]) * rstd[i];
+      }
     }
   }
   // combine the threads of a warp that own the same channel vector (lane ids congruent mod cv)
@@ -279,30 +331,49 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     s_b[c] = p.dgamma[c] * inv_m;
   }
   __syncthreads();
+  constexpr int kU = 2;
   const int cv = p.C / 8;
   const long long total = p.num_pixels * cv;
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pix = v / cv;
-    const int c0 = static_cast<int>(v - pix * cv) * 8;
-    float g[8], yv[8], o[8];
-    bn_bwd_load_gz(p, pix, c0, v, g);
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(p.y) + v), yv);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int c0 = static_cast<int>(v0 % cv) * 8;
+  float kk[8], aa[8], bb[8], mm[8], rr[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
-      o[i] = s_k[c0 + i] * (g[i] - s_a[c0 + i] - xhat * s_b[c0 + i]);
+  for (int i = 0; i < 8; ++i) {
+    kk[i] = s_k[c0 + i]; aa[i] = s_a[c0 + i]; bb[i] = s_b[c0 + i]; mm[i] = s_mean[c0 + i]; rr[i] = s_rstd[c0 + i];
+  }
+  for (long long vb = v0; vb < total; vb += stride * kU) {
+    BnBwdRaw raw[kU];
+    bool ok[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const long long v = vb + j * stride;
+      ok[j] = v < total;
+      if (ok[j]) bn_bwd_issue_loads(p, v / cv, c0, v, raw[j]);
     }
-    const uint4 q = float_to_bf16x8(o);
-    reinterpret_cast<uint4*>(p.gy)[v] = q;
-    if (p.gy_up) {
-      const int w = static_cast<int>(pix % p.Wo);
-      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
-      const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-      const long long up = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.C + c0;
-      *reinterpret_cast<uint4*>(p.gy_up + up) = q;
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      if (!ok[j]) continue;
+      const long long v = vb + j * stride;
+      float g[8], yv[8], o[8];
+      bn_bwd_decode(p, raw[j], g, yv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xhat = (yv[i] - mm[i]) * rr[i];
+        o[i] = kk[i] * (g[i] - aa[i] - xhat * bb[i]);
+      }
+      const uint4 q = float_to_bf16x8(o);
+      reinterpret_cast<uint4*>(p.gy)[v] = q;
+      if (p.gy_up) {
+        const long long pix = v / cv;
+        const int w = static_cast<int>(pix % p.Wo);
+        const int h = static_cast<int>((pix / p.Wo) % p.Ho);
+        const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
+        const long long up = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.C + c0;
+        *reinterpret_cast<uint4*>(p.gy_up + up) = q;
+      }
+      if (p.gz) reinterpret_cast<uint4*>(p.gz)[v] = float_to_bf16x8(g);
     }
-    if (p.gz) reinterpret_cast<uint4*>(p.gz)[v] = float_to_bf16x8(g);
   }
 }
 

@@ -38,7 +38,8 @@ struct ConvGemmParams {
   int num_tiles;  // ceil(N*Ho*Wo / 128)
   int num_pixels; // N*Ho*Wo (store guard)
   int Ho, Wo;     // output spatial size
-  int stages;     // A ring depth
+  int stages;     // A ring depth (in stages)
+  int tps;        // taps per pipeline stage (one mbarrier round trip per stage)
   int epi;
   __nv_bfloat16* out;        // [num_pixels][nc]
   float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics)
@@ -107,12 +108,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int lane = threadIdx.x & 31;
   const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
   const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
+  const uint32_t stage_bytes = p.tps * a_bytes;  // one pipeline stage = tps tap tiles
+  const int groups = (p.taps + p.tps - 1) / p.tps;
   const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
   const uint32_t w_bytes = p.taps * w_tap_bytes;
 
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * a_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * stage_bytes);
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + p.stages;      // [stages]
   uint64_t* wfull = bars + 2 * p.stages;  // [1]
@@ -155,12 +158,16 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n0 = (tile / p.tiles_h) * p.Nt;
         const int h0 = (tile % p.tiles_h) * p.Ht;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int g = 0; g < groups; ++g) {
+          const int tap_lo = g * p.tps;
+          const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], a_bytes);
-          int c0, c1, c2, c3, c4;
-          tap_coords(p.taps, p.stride, tap, p.kc, h0, n0, c0, c1, c2, c3, c4);
-          tma_load_5d(smem_a + stage * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+          mbar_expect_tx(&full[stage], ntap * a_bytes);
+          for (int j = 0; j < ntap; ++j) {
+            int c0, c1, c2, c3, c4;
+            tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
+            tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -185,15 +192,20 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         mbar_wait(&accempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.nc;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        for (int g = 0; g < groups; ++g) {
+          const int tap_lo = g * p.tps;
+          const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * a_bytes);
-          const uint32_t w_addr = smem_u32(smem_w + tap * w_tap_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
-            const uint64_t bdesc = umma_smem_desc(w_addr + k * 32, 16, sbo, layout);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | k) != 0);
+          const uint32_t s_addr = smem_u32(smem_a + stage * stage_bytes);
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t a_addr = s_addr + j * a_bytes;
+            const uint32_t w_addr = smem_u32(smem_w + (tap_lo + j) * w_tap_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
+              const uint64_t bdesc = umma_smem_desc(w_addr + k * 32, 16, sbo, layout);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (tap_lo + j + k) != 0);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == p.stages) {
@@ -542,15 +554,19 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
-  return 1024 + w + (size_t)p.stages * 128 * p.kc * 2 + (2 * p.stages + 5) * 8 + 16 + 2 * p.nc * 4 + 64;
+  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 5) * 8 + 16 + 2 * p.nc * 4 + 64;
 }
-inline int conv_pick_stages(int kc, int nc, int taps) {
+// Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
+// stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
+inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
-  const size_t budget = 200 * 1024 - w;
-  int s = (int)(budget / (128 * kc * 2));
-  if (s > 9) s = 9;
-  if (s < 2) s = 2;
-  return s;
+  const size_t budget = 208 * 1024 - w;
+  const size_t tap_bytes = (size_t)128 * kc * 2;
+  tps = taps;
+  if (taps == 9 && (size_t)2 * 9 * tap_bytes > budget) tps = 3;
+  stages = (int)(budget / (tps * tap_bytes));
+  if (stages > 6) stages = 6;
+  if (stages < 2) { tps = 1; stages = (int)(budget / tap_bytes); if (stages > 9) stages = 9; }
 }
 inline size_t wgrad_smem_bytes(const WgradParams& p) {
   const size_t y = (((size_t)128 * p.cout * 2) + 1023) & ~size_t(1023);

@@ -1,6 +1,7 @@
 // test_tc.cu — standalone self-test of the tcgen05 conv / wgrad kernels against a double-precision CPU
 // loop on the same bf16-rounded inputs.  Build: make -C csrc bin/test_tc ; run on a B200.
-// Usage: test_tc [case-index]   (no argument = all cases in one process)
+// Usage: test_tc [case-index|-1] [time [stages]]   (no argument = verify all cases in one process;
+//        "time" skips the CPU check and reports back-to-back launch time, optional A-ring depth override)
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -33,6 +34,9 @@ struct Case {
   int res_mode; // 0 none, 1 same, 2 downsample-A (only with EPI_INFER)
 };
 
+static bool g_timing = false;
+static int g_stages = 0;  // override of the A ring depth (experiments)
+
 static int run_conv(const Case& c) {
   const int Ho = c.H / c.stride, Wo = c.W / c.stride;
   const size_t nx = (size_t)c.N * c.H * c.W * c.kc, nw = (size_t)c.taps * c.nc * c.kc;
@@ -54,7 +58,7 @@ static int run_conv(const Case& c) {
 
   // CPU reference
   std::vector<double> yref(ny, 0.0);
-  for (int n = 0; n < c.N; ++n)
+  for (int n = 0; n < (g_timing ? 0 : c.N); ++n)
     for (int ho = 0; ho < Ho; ++ho)
       for (int wo = 0; wo < Wo; ++wo)
         for (int t = 0; t < c.taps; ++t) {
@@ -111,7 +115,8 @@ static int run_conv(const Case& c) {
   p.num_pixels = (int)npix;
   p.num_tiles = (int)((npix + 127) / 128);
   p.Ho = Ho; p.Wo = Wo;
-  p.stages = conv_pick_stages(c.kc, c.nc, c.taps);
+  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
+  if (g_stages > 0) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
   p.epi = c.epi;
   p.out = dy; p.stats = dstats; p.bias = dbias; p.res = dres; p.res_stride = rs; p.res_c = rC;
   CUtensorMap mapA, mapW;
@@ -124,6 +129,20 @@ static int run_conv(const Case& c) {
   conv_gemm_kernel<<<grid, kConvThreads, smem>>>(mapA, mapW, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
+  if (g_timing) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 50;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) conv_gemm_kernel<<<grid, kConvThreads, smem>>>(mapA, mapW, p);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-34s conv  tps %d stages %2d grid %3d smem %6zu : %7.2f us/launch (warm L2, back-to-back)\n", c.name, p.tps, p.stages, grid,
+           smem, 1e3 * ms / reps);
+    cudaFree(dx); cudaFree(dw); cudaFree(dy); cudaFree(dstats); cudaFree(dbias); if (dres) cudaFree(dres);
+    return 0;
+  }
 
   std::vector<__nv_bfloat16> yb(ny);
   std::vector<float> st(2 * c.nc);
@@ -165,7 +184,7 @@ static int run_wgrad(const Case& c) {
   for (size_t i = 0; i < nx; ++i) xb[i] = __float2bfloat16_rn(x[i]);
   for (size_t i = 0; i < ny; ++i) yb[i] = __float2bfloat16_rn(dy[i]);
   std::vector<double> ref(nw, 0.0);
-  for (int n = 0; n < c.N; ++n)
+  for (int n = 0; n < (g_timing ? 0 : c.N); ++n)
     for (int ho = 0; ho < Ho; ++ho)
       for (int wo = 0; wo < Wo; ++wo)
         for (int t = 0; t < c.taps; ++t) {
@@ -198,10 +217,24 @@ static int run_wgrad(const Case& c) {
   const size_t smem = wgrad_smem_bytes(p);
   CK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.num_tiles < 148 ? p.num_tiles : 148;
-  if (grid > 3) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
+  if (grid > 3 && !g_timing) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
+  if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 148) grid = 148; }
   wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
+  if (g_timing) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 50;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-34s wgrad grid %3d : %7.2f us/launch (warm L2, back-to-back)\n", c.name, grid, 1e3 * ms / reps);
+    cudaFree(dx); cudaFree(ddy); cudaFree(ddw);
+    return 0;
+  }
   std::vector<float> got(nw);
   CK(cudaMemcpy(got.data(), ddw, nw * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0, maxref = 0; size_t bad = 0, firstbad = 0;
@@ -239,6 +272,10 @@ int main(int argc, char** argv) {
       {"s1 16x16 32->32 infer+resA", 4, 16, 16, 32, 32, 1, 9, EPI_INFER, 2},
       {"1x1 8x8 64->128 raw", 8, 8, 8, 64, 128, 1, 1, EPI_RAW, 0},
       {"large s1 32x32 16->16 stats N=128", 128, 32, 32, 16, 16, 1, 9, EPI_STATS, 0},
+      {"large s1 16x16 32->32 stats N=128", 128, 16, 16, 32, 32, 1, 9, EPI_STATS, 0},
+      {"large s1 8x8 64->64 stats N=128", 128, 8, 8, 64, 64, 1, 9, EPI_STATS, 0},
+      {"large s1 32x32 16->16 raw N=128", 128, 32, 32, 16, 16, 1, 9, EPI_RAW, 0},
+      {"large s1 32x32 16->16 infer N=128", 128, 32, 32, 16, 16, 1, 9, EPI_INFER, 1},
   };
   const Case wcases[] = {
       {"s1 32x32 16x16", 4, 32, 32, 16, 16, 1, 9, 0, 0},
@@ -247,9 +284,13 @@ int main(int argc, char** argv) {
       {"s2 32x32 16x32", 4, 32, 32, 16, 32, 2, 9, 0, 0},
       {"s2 16x16 32x64", 6, 16, 16, 32, 64, 2, 9, 0, 0},
       {"s1 32x32 16x16 N=128", 128, 32, 32, 16, 16, 1, 9, 0, 0},
+      {"s1 16x16 32x32 N=128", 128, 16, 16, 32, 32, 1, 9, 0, 0},
+      {"s1 8x8 64x64 N=128", 128, 8, 8, 64, 64, 1, 9, 0, 0},
   };
   const int nc = sizeof(cases) / sizeof(cases[0]), nw = sizeof(wcases) / sizeof(wcases[0]);
   int only = argc > 1 ? atoi(argv[1]) : -1;
+  if (argc > 2 && std::string(argv[2]) == "time") g_timing = true;
+  if (argc > 3) g_stages = atoi(argv[3]);
   int fails = 0;
   for (int i = 0; i < nc + nw; ++i) {
     if (only >= 0 && i != only) continue;

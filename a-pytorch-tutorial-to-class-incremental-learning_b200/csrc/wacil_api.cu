@@ -211,7 +211,7 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.num_tiles = (p.num_pixels + 127) / 128;
   p.Ho = Ho;
   p.Wo = Wo;
-  p.stages = conv_pick_stages(kc, nc, taps);
+  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
   p.epi = epi;
   p.res_stride = 1;
   p.res_c = nc;
@@ -515,7 +515,7 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
       bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
       bp.eps = kBnEps;
       bp.momentum = kBnMomentum;
-      bn_apply_fwd_kernel<<<ew_grid(bp.num_pixels * d.cout / 8), 256, 0, st>>>(bp);
+      bn_apply_fwd_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 4), 256, 0, st>>>(bp);
       WACIL_LAUNCH_CHECK("bn_apply_fwd_kernel");
       launches += 2;
     }
@@ -593,7 +593,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     if (rgrid > num_sms() * 2) rgrid = num_sms() * 2;
     bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-    bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8), 256, 0, st>>>(bp);
+    bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 2), 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
     if ((e = launch_wgrad(n->wgrad[l], st))) return e;
     launches += 3;
