@@ -244,10 +244,16 @@ def run_ours(args, rank, local_rank, world):
         loss_host[i % loss_host.shape[0]].copy_(losses, non_blocking=True)
 
     warm = max(args.warmup, 3)
-    for i in range(warm + 3):  # +3: two eager steps and the graph capture happen before anything is timed
+    for i in range(3):  # two eager steps and the graph capture happen before anything is warmed up or timed
         step_dev(i)
     torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:  # clocks under load: warm-up, both timed regions and the soak in between
+        t_soak = time.perf_counter()
+        i = 0
+        while i < warm or time.perf_counter() - t_soak < 1.0:  # >= W warm-up steps and >= 1 s so the sampler sees load
+            step_dev(i)
+            i += 1
+        torch.cuda.synchronize()
         ms = timed(step_dev, args.steps, world)
         for i in range(3):
             step_e2e(i)
