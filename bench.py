@@ -248,11 +248,8 @@ def run_ours(args, rank, local_rank, world):
         step_dev(i)
     torch.cuda.synchronize()
     with ClockSampler(local_rank) as clk:  # clocks under load: warm-up, both timed regions and the soak in between
-        t_soak = time.perf_counter()
-        i = 0
-        while i < warm or time.perf_counter() - t_soak < 1.0:  # >= W warm-up steps and >= 1 s so the sampler sees load
-            step_dev(i)
-            i += 1
+        for i in range(max(warm, 400)):  # >= W warm-up steps; a fixed count (same on every rank) long enough
+            step_dev(i)                  # (~0.5 s) for the 200 ms sampler to see the clocks under load
         torch.cuda.synchronize()
         ms = timed(step_dev, args.steps, world)
         for i in range(3):
