@@ -26,6 +26,9 @@ enum ConvEpilogue : int {
   EPI_RAW = 0,    // bf16 store of the accumulator
   EPI_STATS = 1,  // bf16 store + per-channel sum / sum-of-squares of the stored (rounded) values
   EPI_INFER = 2,  // + bias[c] (+ residual) -> ReLU -> bf16 store   (BatchNorm folded into weights/bias)
+  // Fused modes: cooperative launch, every tile of the CTA keeps its accumulator in TMEM across a grid barrier.
+  EPI_BN_TRAIN = 3,  // fprop: store y, batch statistics -> grid barrier -> BatchNorm + shortcut + ReLU -> store a
+  EPI_BNBWD = 4,     // dgrad: gz = (acc + shortcut grad) * relu mask, d-gamma/d-beta -> grid barrier -> gy (BN backward)
 };
 
 struct ConvGemmParams {
@@ -47,7 +50,68 @@ struct ConvGemmParams {
   const __nv_bfloat16* res;  // residual (EPI_INFER) or nullptr
   int res_stride;            // 1: same geometry as out; 2: residual is [N][2Ho][2Wo][res_c] sampled at even pixels
   int res_c;                 // residual channels (<= nc); channels >= res_c get no residual (zero pad)
+  // ---- fused modes ----
+  int acc_stages;            // TMEM accumulator stages: 2 (ring) or >= tiles per CTA (fused modes)
+  unsigned* grid_bar;        // [2] self-resetting grid barrier counters (zero at rest)
+  // EPI_BN_TRAIN: out = y (raw), act_out = a; stats/gamma/beta/running/saved as in bn_apply_fwd
+  __nv_bfloat16* act_out;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* saved;              // [2*nc] batch mean, rstd (written in BN_TRAIN, read in BNBWD)
+  float eps, momentum;
+  // EPI_BNBWD (this launch is the dgrad producing the gradient wrt a_l; BN backward of layer l):
+  const __nv_bfloat16* g_res;   // shortcut gradient source or nullptr
+  int gres_mode;                // 1 same shape; 2 source [N][Ho/2][Wo/2][2*nc], lands on even pixels
+  const __nv_bfloat16* act_in;  // a_l (ReLU mask)
+  const __nv_bfloat16* y_in;    // y_l (x-hat)
+  float* dgamma;
+  float* dbeta;
+  __nv_bfloat16* gy;            // out: gradient wrt y_l
+  __nv_bfloat16* gy_up;         // optional zero-upsampled copy (stride-2 layer l)
+  __nv_bfloat16* gz;            // optional masked gradient (shortcut of the previous block)
 };
+
+// Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
+// cooperative launch (all CTAs co-resident).  bar[0], bar[1] are zero at rest; bounded spin (a bug must trap, not hang).
+__device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid128 == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (atomicAdd(bar, 0u) < gridDim.x) {
+      if (clock64() - t0 > 4000000000LL) {
+        printf("wacil: grid barrier timeout (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+      bar[1] = 0u;
+      __threadfence();
+      bar[0] = 0u;
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&v)[16]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 r4[2] = {__ldg(q), __ldg(q + 1)};
+  const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(r4);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __bfloat162float(rb[i]);
+}
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&v)[16]) {
+  __align__(16) __nv_bfloat16 ob[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+  uint4* op = reinterpret_cast<uint4*>(p);
+  op[0] = reinterpret_cast<const uint4*>(ob)[0];
+  op[1] = reinterpret_cast<const uint4*>(ob)[1];
+}
 
 __device__ __forceinline__ void tap_coords(int taps, int stride, int tap, int kc, int h0, int n0, int& c0, int& c1,
                                            int& c2, int& c3, int& c4) {
@@ -119,12 +183,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + p.stages;      // [stages]
   uint64_t* wfull = bars + 2 * p.stages;  // [1]
-  uint64_t* accfull = wfull + 1;          // [2]
-  uint64_t* accempty = accfull + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2*nc]
+  const int nacc = p.acc_stages;
+  uint64_t* accfull = wfull + 1;          // [nacc]
+  uint64_t* accempty = accfull + nacc;    // [nacc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [8*64] per-channel scratch
 
-  const uint32_t tmem_cols = next_pow2_cols(2u * p.nc);
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -134,15 +199,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       mbar_init(&empty[i], 1);
     }
     mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < nacc; ++i) {
       mbar_init(&accfull[i], 1);
       mbar_init(&accempty[i], 4);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  if (p.epi == EPI_STATS)
-    for (int i = threadIdx.x; i < 2 * p.nc; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * p.nc; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,9 +278,186 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           }
         }
         umma_commit(&accfull[as]);
-        if (++as == 2) {
+        if (++as == nacc) {
           as = 0;
           aphase ^= 1;
+        }
+      }
+    }
+  } else if (p.epi >= EPI_BN_TRAIN) {
+    // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    const int tid128 = threadIdx.x - 64;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    float* s_a0 = s_stats;            // [nc] sum      | d-beta partial
+    float* s_a1 = s_stats + 64;       // [nc] sumsq    | d-gamma partial
+    float* s_c0 = s_stats + 128;      // [nc] scale    | k = gamma * rstd
+    float* s_c1 = s_stats + 192;      // [nc] shift    | d-beta / M
+    float* s_c2 = s_stats + 256;      // [nc]          | d-gamma / M
+    float* s_mean = s_stats + 320;    // [nc]
+    float* s_rstd = s_stats + 384;    // [nc]
+    if (p.epi == EPI_BNBWD) {
+      for (int c = tid128; c < p.nc; c += 128) {
+        s_mean[c] = p.saved[c];
+        s_rstd[c] = p.saved[p.nc + c];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
+    int as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      mbar_wait(&accfull[as], 0);
+      tc_fence_after();
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      const __nv_bfloat16* gres_ptr = nullptr;
+      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
+        if (p.gres_mode == 1) {
+          gres_ptr = p.g_res + base;
+        } else {
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          if (((w | h) & 1) == 0)
+            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+        }
+      }
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        float v[16], s1[16], s2[16];
+        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
+        if (p.epi == EPI_BN_TRAIN) {
+          __align__(16) __nv_bfloat16 ob[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + base + c0);
+            op[0] = reinterpret_cast<const uint4*>(ob)[0];
+            op[1] = reinterpret_cast<const uint4*>(ob)[1];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float r = valid ? __bfloat162float(ob[i]) : 0.f;
+            s1[i] = r;
+            s2[i] = r * r;
+          }
+        } else {
+          float a[16], yv[16];
+          if (valid) {
+            load16_bf16(p.act_in + base + c0, a);
+            load16_bf16(p.y_in + base + c0, yv);
+            if (gres_ptr != nullptr) {
+              float r[16];
+              load16_bf16(gres_ptr + c0, r);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float gzv = (valid && a[i] > 0.f) ? v[i] : 0.f;
+            s1[i] = gzv;
+            s2[i] = valid ? gzv * (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;
+          }
+        }
+        const float t1 = warp_colsum16(s1, lane);
+        const float t2 = warp_colsum16(s2, lane);
+        if ((lane & 1) == 0) {
+          const int c = c0 + warp_colsum16_col(lane);
+          atomicAdd(&s_a0[c], t1);
+          atomicAdd(&s_a1[c], t2);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    {
+      float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
+      float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + p.nc : p.dgamma;
+      for (int c = tid128; c < p.nc; c += 128) {
+        atomicAdd(g0 + c, s_a0[c]);
+        atomicAdd(g1 + c, s_a1[c]);
+      }
+    }
+    grid_barrier_epi(p.grid_bar, tid128);
+    // ---------------- per-channel constants from the grid-wide sums
+    const float cnt = static_cast<float>(p.num_pixels);
+    for (int c = tid128; c < p.nc; c += 128) {
+      if (p.epi == EPI_BN_TRAIN) {
+        const float mean = __ldcg(p.stats + c) / cnt;
+        float var = __ldcg(p.stats + p.nc + c) / cnt - mean * mean;
+        var = fmaxf(var, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const float sc = p.gamma[c] * rstd;
+        s_c0[c] = sc;
+        s_c1[c] = p.beta[c] - mean * sc;
+        if (blockIdx.x == 0) {
+          p.saved[c] = mean;
+          p.saved[p.nc + c] = rstd;
+          p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (cnt / (cnt - 1.f));
+        }
+      } else {
+        s_c0[c] = p.gamma[c] * s_rstd[c];
+        s_c1[c] = __ldcg(p.dbeta + c) / cnt;
+        s_c2[c] = __ldcg(p.dgamma + c) / cnt;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---------------- phase 2: normalise (forward) / BN backward, from the accumulators still in TMEM
+    as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+      const __nv_bfloat16* res_ptr = nullptr;
+      const __nv_bfloat16* gres_ptr = nullptr;
+      if (valid && p.epi == EPI_BN_TRAIN && p.res != nullptr) {
+        res_ptr = p.res_stride == 1
+                      ? p.res + static_cast<size_t>(pix) * p.res_c
+                      : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+      }
+      if (valid && p.epi == EPI_BNBWD && p.g_res != nullptr) {
+        if (p.gres_mode == 1) gres_ptr = p.g_res + base;
+        else if (((w | h) & 1) == 0)
+          gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+      }
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
+        if (!valid) continue;
+        if (p.epi == EPI_BN_TRAIN) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
+          if (res_ptr != nullptr && c0 < p.res_c) {
+            float r[16];
+            load16_bf16(res_ptr + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          store16_bf16(p.act_out + base + c0, v);
+        } else {
+          float a[16], yv[16], o[16];
+          load16_bf16(p.act_in + base + c0, a);
+          load16_bf16(p.y_in + base + c0, yv);
+          if (gres_ptr != nullptr) {
+            float r[16];
+            load16_bf16(gres_ptr + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
+            const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+            o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
+          }
+          store16_bf16(p.gy + base + c0, o);
+          if (p.gy_up != nullptr)
+            store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
+          if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
         }
       }
     }
@@ -286,7 +527,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&accempty[as]);
-      if (++as == 2) {
+      if (++as == nacc) {
         as = 0;
         aphase ^= 1;
       }
@@ -554,7 +795,8 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
-  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 5) * 8 + 16 + 2 * p.nc * 4 + 64;
+  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
+         8 * 64 * 4 + 64;
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).

@@ -118,6 +118,7 @@ static int run_conv(const Case& c) {
   conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
   if (g_stages > 0) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
   p.epi = c.epi;
+  p.acc_stages = 2;
   p.out = dy; p.stats = dstats; p.bias = dbias; p.res = dres; p.res_stride = rs; p.res_c = rC;
   CUtensorMap mapA, mapW;
   int e1 = make_act_map(&mapA, dx, c.N, c.H, c.W, c.kc, c.stride, p.Ht, p.Nt);

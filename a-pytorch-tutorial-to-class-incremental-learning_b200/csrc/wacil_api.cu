@@ -133,7 +133,7 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, saved, a0, dfeats, gd, gy, gz[2], tmp[3];
+  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[2], gz[2], tmp[3];
   std::vector<size_t> y, a, gyup;
   size_t stat_elems = 0, wbuf_elems = 0, total = 0;
 };
@@ -155,6 +155,7 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
+  o.gbar = c.take(64);
   size_t max_act = 0;
   for (auto& d : L) {
     const size_t in_b = static_cast<size_t>(batch) * d.H_in * d.H_in * d.cin_pad * 2;
@@ -172,14 +173,14 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
       o.a[l] = c.take(out_b);
       if (L[l].stride == 2) o.gyup[l] = c.take(out_b * 4);
     }
-    o.gd = c.take(max_act);
-    o.gy = c.take(max_act);
+    o.gy[0] = c.take(max_act);
+    o.gy[1] = c.take(max_act);
     o.gz[0] = c.take(max_act);
     o.gz[1] = c.take(max_act);
     o.tmp[0] = o.tmp[1] = o.tmp[2] = 0;
   } else {
     for (int i = 0; i < 3; ++i) o.tmp[i] = c.take(max_act);
-    o.gd = o.gy = o.gz[0] = o.gz[1] = 0;
+    o.gy[0] = o.gy[1] = o.gz[0] = o.gz[1] = 0;
   }
   o.total = c.off;
 }
@@ -213,6 +214,7 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.Wo = Wo;
   conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
   p.epi = epi;
+  p.acc_stages = 2;
   p.res_stride = 1;
   p.res_c = nc;
   int e = make_act_map(&c.mapA, in, N, H, W, kc, stride, p.Ht, p.Nt);
@@ -232,8 +234,31 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
     smem_set = 220 * 1024;
   }
+  if (c.p.epi >= EPI_BN_TRAIN) {
+    // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
+    void* args[] = {const_cast<CUtensorMap*>(&c.mapA), const_cast<CUtensorMap*>(&c.mapW),
+                    const_cast<ConvGemmParams*>(&c.p)};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(conv_gemm_kernel), dim3(c.grid),
+                                                dim3(kConvThreads), args, c.smem, st);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel (cooperative)");
+    return 0;
+  }
   conv_gemm_kernel<<<c.grid, kConvThreads, c.smem, st>>>(c.mapA, c.mapW, c.p);
   WACIL_LAUNCH_CHECK("conv_gemm_kernel");
+  return 0;
+}
+
+// Switch a prepared launch to a fused mode: one TMEM accumulator stage per tile of a CTA.
+int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
+  c.p.epi = epi;
+  c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
+  if (c.p.acc_stages * c.p.nc > 512)
+    return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path: %d tiles x %d channels per CTA > 512 TMEM "
+                "columns", c.p.acc_stages, c.p.nc);
+  c.p.grid_bar = grid_bar;
+  c.p.eps = kBnEps;
+  c.p.momentum = kBnMomentum;
+  c.smem = conv_smem_bytes(c.p);
   return 0;
 }
 
@@ -360,30 +385,71 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     n->dgrad.resize(nl);
     n->wgrad.resize(nl);
     float* stats = n->at<float>(n->off.stats);
-    size_t soff = 0;
+    float* saved = n->at<float>(n->off.saved);
+    unsigned* gbar = n->at<unsigned>(n->off.gbar);
+    ce = cudaMemset(gbar, 0, 64);
+    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "grid barrier clear"); }
+    std::vector<size_t> so(nl);
+    {
+      size_t o = 0;
+      for (size_t l = 0; l < nl; ++l) { so[l] = o; o += 2 * n->L[l].cout; }
+    }
     for (size_t l = 0; l < nl; ++l) {
       const LayerDesc& d = n->L[l];
+      // ---- forward: conv + batch statistics + BatchNorm + shortcut + ReLU in one cooperative launch
       ConvLaunch& c = n->fprop[l];
       e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
                      wbuf + d.wf_off, EPI_STATS);
       if (e) { delete n; return e; }
+      if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) { delete n; return e; }
       c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
-      c.p.stats = stats + soff;
-      soff += 2 * d.cout;
-      // wgrad: X = layer input, dY = GY
-      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy), n->grads + d.w_off, batch,
-                      d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
+      c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
+      c.p.stats = stats + so[l];
+      c.p.saved = saved + so[l];
+      c.p.gamma = n->params + d.gamma_off;
+      c.p.beta = n->params + d.beta_off;
+      c.p.running_mean = n->bn + d.rmean_off;
+      c.p.running_var = n->bn + d.rvar_off;
+      c.p.res = nullptr;
+      if (l >= 2 && l % 2 == 0) {  // conv_b: add the block input through the shortcut
+        const LayerDesc& da = n->L[l - 1];
+        c.p.res = n->act_in(static_cast<int>(l) - 1);
+        const bool ds = (da.stride == 2 || da.cin != da.cout);
+        c.p.res_stride = ds ? 2 : 1;
+        c.p.res_c = ds ? da.cin : d.cout;
+      }
+      // ---- wgrad: X = layer input, dY = GY[l % 2]
+      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 2]),
+                      n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
       if (l > 0) {
-        // dgrad: stride-1 conv over GY (or its zero-upsampled copy) with the flipped [cin][cout] weights
-        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy);
+        // ---- dgrad of layer l (stride-1 conv over GY or its zero-upsampled copy, flipped [cin][cout] weights)
+        //      fused with the ReLU mask + BatchNorm backward of layer l-1
+        const LayerDesc& pd = n->L[l - 1];
+        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 2]);
         ConvLaunch& g = n->dgrad[l];
         e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
         if (e) { delete n; return e; }
-        g.p.out = n->at<__nv_bfloat16>(n->off.gd);
+        if ((e = make_fused(g, EPI_BNBWD, gbar))) { delete n; return e; }
+        const int pl = static_cast<int>(l) - 1;
+        g.p.g_res = nullptr;
+        const bool block_output = (pl == 0) || (pl % 2 == 0);
+        if (block_output && pl + 2 < static_cast<int>(nl)) {
+          const LayerDesc& na = n->L[pl + 1];
+          g.p.g_res = n->at<__nv_bfloat16>(n->off.gz[(pl / 2) % 2]);
+          g.p.gres_mode = (na.stride == 2 || na.cin != na.cout) ? 2 : 1;
+        }
+        g.p.act_in = n->at<__nv_bfloat16>(n->off.a[pl]);
+        g.p.y_in = n->at<__nv_bfloat16>(n->off.y[pl]);
+        g.p.saved = saved + so[pl];
+        g.p.gamma = n->params + pd.gamma_off;
+        g.p.dgamma = n->grads + pd.gamma_off;
+        g.p.dbeta = n->grads + pd.beta_off;
+        g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 2]);
+        g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
+        g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
         if (d.stride == 2) {
-          ce = cudaMemset(n->ws + n->off.gyup[l], 0,
-                          static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
+          ce = cudaMemset(n->ws + n->off.gyup[l], 0, static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
           if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "gy_up clear"); }
         }
       }
@@ -487,37 +553,9 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
                                               n->at<LayerDesc>(n->off.table));
     WACIL_LAUNCH_CHECK("cast_weights_kernel");
     ++launches;
-    float* saved = n->at<float>(n->off.saved);
-    size_t soff = 0;
     for (size_t l = 0; l < nl; ++l) {
-      const LayerDesc& d = n->L[l];
       if ((e = launch_conv(n->fprop[l], st))) return e;
-      BnApplyParams bp{};
-      bp.y = n->at<__nv_bfloat16>(n->off.y[l]);
-      bp.out = n->at<__nv_bfloat16>(n->off.a[l]);
-      bp.res = nullptr;
-      bp.res_mode = 0;
-      if (l >= 2 && l % 2 == 0) {  // conv_b: add the block input through the shortcut
-        const LayerDesc& da = n->L[l - 1];
-        bp.res = n->act_in(static_cast<int>(l) - 1);
-        bp.res_mode = (da.stride == 2 || da.cin != da.cout) ? 2 : 1;
-      }
-      bp.stats = n->fprop[l].p.stats;
-      bp.gamma = n->params + d.gamma_off;
-      bp.beta = n->params + d.beta_off;
-      bp.running_mean = n->bn + d.rmean_off;
-      bp.running_var = n->bn + d.rvar_off;
-      bp.saved = saved + soff;
-      soff += 2 * d.cout;
-      bp.C = d.cout;
-      bp.Ho = d.H_out;
-      bp.Wo = d.H_out;
-      bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
-      bp.eps = kBnEps;
-      bp.momentum = kBnMomentum;
-      bn_apply_fwd_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 4), 256, 0, st>>>(bp);
-      WACIL_LAUNCH_CHECK("bn_apply_fwd_kernel");
-      launches += 2;
+      ++launches;
     }
     last = n->at<__nv_bfloat16>(n->off.a[nl - 1]);
   } else {
@@ -560,28 +598,20 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     size_t o = 0;
     for (int l = 0; l < nl; ++l) { soff[l] = o; o += 2 * n->L[l].cout; }
   }
-  for (int l = nl - 1; l >= 0; --l) {
+  {
+    // the last layer's gradient comes from the pooled features: stand-alone ReLU-mask + BatchNorm backward
+    const int l = nl - 1;
     const LayerDesc& d = n->L[l];
     BnBwdParams bp{};
-    if (l == nl - 1) {
-      bp.g_pool = dfeats;
-      bp.inv_hw = 1.f / static_cast<float>(d.H_out * d.H_out);
-    } else {
-      bp.g_main = n->at<__nv_bfloat16>(n->off.gd);
-    }
-    const bool block_output = (l == 0) || (l % 2 == 0);
-    if (block_output && l + 2 < nl) {
-      const LayerDesc& na = n->L[l + 1];
-      bp.g_res = n->at<__nv_bfloat16>(n->off.gz[(l / 2) % 2]);
-      bp.gres_mode = (na.stride == 2 || na.cin != na.cout) ? 2 : 1;
-    }
+    bp.g_pool = dfeats;
+    bp.inv_hw = 1.f / static_cast<float>(d.H_out * d.H_out);
     bp.act = n->at<__nv_bfloat16>(n->off.a[l]);
     bp.y = n->at<__nv_bfloat16>(n->off.y[l]);
     bp.saved = saved + soff[l];
     bp.gamma = n->params + d.gamma_off;
     bp.dgamma = n->grads + d.gamma_off;
     bp.dbeta = n->grads + d.beta_off;
-    bp.gy = n->at<__nv_bfloat16>(n->off.gy);
+    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l % 2]);
     bp.gy_up = d.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[l]) : nullptr;
     bp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
     bp.C = d.cout;
@@ -595,10 +625,13 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 2), 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
-    if ((e = launch_wgrad(n->wgrad[l], st))) return e;
-    launches += 3;
+    launches += 2;
+  }
+  for (int l = nl - 1; l >= 0; --l) {
+    if ((e = launch_wgrad(n->wgrad[l], st))) return e;  // dW_l from (a_{l-1}, GY_l)
+    ++launches;
     if (l > 0) {
-      if ((e = launch_conv(n->dgrad[l], st))) return e;
+      if ((e = launch_conv(n->dgrad[l], st))) return e;  // dgrad_l fused with BatchNorm backward of layer l-1 -> GY_{l-1}
       ++launches;
     }
   }

@@ -10,7 +10,8 @@ rounding points, explicit backward formulas), and this model is tied to the fp32
 disabled it must reproduce `wa_oracle.train_step`'s autograd gradients (tests/test_oracle_golden.py).
 
 Rounding points (DESIGN.md "Numerics"): network input, conv weights (operand copies), every conv output `y`, every
-post-ReLU activation, every activation gradient written by a BN-backward or dgrad kernel, the shortcut gradient.
+post-ReLU activation, every gradient wrt a conv output (`gy`) and the shortcut gradient (`gz`); the data-gradient
+convolution's result is consumed in fp32 (fused with the BatchNorm backward of the layer below).
 fp32: accumulators, batch statistics, x-hat, d-gamma/d-beta, weight gradients, features, logits, loss.
 """
 from __future__ import annotations
@@ -68,10 +69,12 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, rnd=bf16_r
     return st
 
 
-def backward(sd: Dict[str, torch.Tensor], st, depth: int, dlogits: torch.Tensor, rnd=bf16_round):
+def backward(sd: Dict[str, torch.Tensor], st, depth: int, dlogits: torch.Tensor, rnd=bf16_round,
+             round_dgrad: bool = False):
     """Backward with explicit formulas from a forward state `st` (from `forward`, or read back from the GPU plan:
     with the masks fixed by the given activations the map dlogits -> gradients is linear, so the comparison with the
-    kernels is free of the rounding avalanche of a deep bf16 forward)."""
+    kernels is free of the rounding avalanche of a deep bf16 forward).  `round_dgrad=False`: the data-gradient conv
+    is fused with the ReLU mask + BatchNorm backward of the layer below and consumed in fp32 straight from TMEM."""
     layers = wo.conv_bn_names(depth)
     nl = len(layers)
     feats = st["feats"]
@@ -114,7 +117,9 @@ def backward(sd: Dict[str, torch.Tensor], st, depth: int, dlogits: torch.Tensor,
             gz_next_mode = 2 if (ca[4] != 1 or ca[2] != ca[3]) else 1
         grads[conv + ".weight"] = conv2d_weight(ins[l], sd[conv + ".weight"].shape, gy, stride=stride, padding=1)
         if l > 0:
-            g = rnd(conv2d_input(ins[l].shape, rnd(sd[conv + ".weight"]), gy, stride=stride, padding=1))
+            g = conv2d_input(ins[l].shape, rnd(sd[conv + ".weight"]), gy, stride=stride, padding=1)
+            if round_dgrad:
+                g = rnd(g)
     return grads
 
 
