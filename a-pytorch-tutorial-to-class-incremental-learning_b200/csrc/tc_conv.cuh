@@ -71,6 +71,7 @@ struct ConvGemmParams {
   __nv_bfloat16* gy;            // out: gradient wrt y_l
   __nv_bfloat16* gy_up;         // optional zero-upsampled copy (stride-2 layer l)
   __nv_bfloat16* gz;            // optional masked gradient (shortcut of the previous block)
+  long long* dbg;               // optional [gridDim.x][16] clock64 timestamps of pipeline milestones (profiling)
 };
 
 // Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
@@ -96,6 +97,11 @@ __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
+
+#define WACIL_STAMP(slot)                                                        \
+  do {                                                                           \
+    if (p.dbg != nullptr) p.dbg[blockIdx.x * 16 + (slot)] = clock64();           \
+  } while (0)
 
 __device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&v)[16]) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) WACIL_STAMP(0);  // kernel entry
   const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
   const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
   const uint32_t stage_bytes = p.tps * a_bytes;  // one pipeline stage = tps tap tiles
@@ -206,11 +213,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 2 * p.nc; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) WACIL_STAMP(1);  // barriers initialised, TMEM allocated
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -238,6 +246,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           }
         }
       }
+      WACIL_STAMP(2);  // producer: every TMA load issued
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const int ksteps = p.kc / 16;
       mbar_wait(wfull, 0);
       tc_fence_after();
+      WACIL_STAMP(3);  // weights landed
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
           const uint32_t s_addr = smem_u32(smem_a + stage * stage_bytes);
           for (int j = 0; j < ntap; ++j) {
             const uint32_t a_addr = s_addr + j * a_bytes;
@@ -283,6 +294,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           aphase ^= 1;
         }
       }
+      WACIL_STAMP(5);  // every MMA issued
     }
   } else if (p.epi >= EPI_BN_TRAIN) {
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
       mbar_wait(&accfull[as], 0);
       tc_fence_after();
+      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
@@ -369,6 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
     {
       float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
       float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + p.nc : p.dgamma;
@@ -378,6 +392,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       }
     }
     grid_barrier_epi(p.grid_bar, tid128);
+    if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels);
     for (int c = tid128; c < p.nc; c += 128) {
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
       }
     }
+    if (tid128 == 0) WACIL_STAMP(9);  // phase 2 done
   } else {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;
@@ -470,6 +486,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&accfull[as], aphase);
       tc_fence_after();
+      if (threadIdx.x == 64 && tile == static_cast<int>(blockIdx.x)) WACIL_STAMP(6);
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const __nv_bfloat16* res_ptr = nullptr;
@@ -539,6 +556,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       if (blockIdx.x < p.num_tiles)
         for (int i = e; i < 2 * p.nc; i += 128) atomicAdd(&p.stats[i], s_stats[i]);
     }
+    if (threadIdx.x == 64) WACIL_STAMP(9);
   }
 
   tc_fence_before();
@@ -547,6 +565,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  if (threadIdx.x == 0) WACIL_STAMP(10);  // teardown done
 }
 
 // ------------------------------------------------------------------------------------------------

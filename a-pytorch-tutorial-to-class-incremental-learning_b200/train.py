@@ -116,6 +116,25 @@ def sampler_indices(n, epoch, rank, world_size, seed=0, shuffle=True):
     return idx[rank:total:world_size]
 
 
+def allreduce_grads_(flat_grads, world_size, group=None):
+    """The DDP exchange of template.py:243-244,270 on the ONE flat gradient arena: sum over ranks (NCCL on GPUs);
+    returns the factor (1/world) the SGD kernel folds into its update so that the result is DDP's mean."""
+    if world_size > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world_size
+
+
+def reduce_epoch_stats(acc, steps, n_samples, world_size, group=None):
+    """acc = per-rank running sums [ce, kd, loss, top1-count] over `steps` steps -> global means and top-1 % over
+    `n_samples` samples (the reference's MetricLogger.synchronize_between_processes, utils.py:36-43,117, once per epoch)."""
+    acc = acc.clone()
+    if world_size > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    ce, kd, loss, top1 = acc.tolist()
+    denom = max(steps, 1) * world_size
+    return {"ce": ce / denom, "kd": kd / denom, "loss": loss / denom, "acc1": 100.0 * top1 / max(n_samples, 1)}
+
+
 # ------------------------------------------------------------------------------------------------------------
 class _StepState:
     """Static buffers + captured graph for one batch size."""
@@ -192,7 +211,7 @@ class TaskTrainer:
         if not self.use_graph or st.warm < 2:
             n = self._fwd_bwd(st)
             if not single:
-                dist.all_reduce(self.model._arena.grads, group=self.pg)
+                allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
             n += self._opt()
             st.warm += 1
             self.launches_per_step = n
@@ -208,12 +227,12 @@ class TaskTrainer:
                 st.graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(st.graph_opt):
                     self._opt()
-                dist.all_reduce(self.model._arena.grads, group=self.pg)
+                allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
                 st.graph_opt.replay()
             return  # capture executed nothing for forward/backward: the caller's step counts from the next replay
         st.graph_fb.replay()
         if not single:
-            dist.all_reduce(self.model._arena.grads, group=self.pg)
+            allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
             st.graph_opt.replay()
 
     def step(self, x, y):
@@ -237,14 +256,8 @@ class TaskTrainer:
 
     def epoch_stats(self, n_samples):
         """Means of ce / kd / loss and top-1 % since the last call (one host sync per epoch)."""
-        acc = self.acc.clone()
-        if self.world_size > 1:
-            dist.all_reduce(acc, group=self.pg)
-        steps = max(self.steps_done, 1)
-        ce, kd, loss, top1 = acc.tolist()
+        out = reduce_epoch_stats(self.acc, self.steps_done, n_samples, self.world_size, self.pg)
         self.acc.zero_()
-        out = {"ce": ce / (steps * self.world_size), "kd": kd / (steps * self.world_size),
-               "loss": loss / (steps * self.world_size), "acc1": 100.0 * top1 / max(n_samples, 1)}
         self.steps_done = 0
         return out
 
