@@ -168,7 +168,7 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
 
 constexpr int kConvThreads = 192;
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   uint64_t* accfull = wfull + 1;          // [nacc]
   uint64_t* accempty = accfull + nacc;    // [nacc]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [8*64] per-channel scratch
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [13*64] per-channel scratch
 
   const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc));
 
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 13 * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -255,6 +255,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const uint32_t sbo = 8u * rowbytes;
       const uint32_t idesc = umma_idesc_bf16(128, p.nc, 0, 0);
       const int ksteps = p.kc / 16;
+      const uint64_t desc_hi = umma_smem_desc(0, 16, sbo, layout);
+      const uint32_t a_ring_addr = smem_u32(smem_a);
+      const uint32_t w_base_addr = smem_u32(smem_w);
       mbar_wait(wfull, 0);
       tc_fence_after();
       WACIL_STAMP(3);  // weights landed
@@ -272,15 +275,15 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
-          const uint32_t s_addr = smem_u32(smem_a + stage * stage_bytes);
+          // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
+          uint64_t adesc = desc_hi | ((a_ring_addr + stage * stage_bytes) >> 4);
+          uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
           for (int j = 0; j < ntap; ++j) {
-            const uint32_t a_addr = s_addr + j * a_bytes;
-            const uint32_t w_addr = smem_u32(smem_w + (tap_lo + j) * w_tap_bytes);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = umma_smem_desc(a_addr + k * 32, 16, sbo, layout);
-              const uint64_t bdesc = umma_smem_desc(w_addr + k * 32, 16, sbo, layout);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (tap_lo + j + k) != 0);
-            }
+#pragma unroll 4
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap_lo + j + k) != 0);
+            adesc += a_bytes >> 4;
+            bdesc += w_tap_bytes >> 4;
           }
           umma_commit(&empty[stage]);
           if (++stage == p.stages) {
@@ -302,13 +305,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const int m = quarter * 32 + lane;
     const int tid128 = threadIdx.x - 64;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    float* s_a0 = s_stats;            // [nc] sum      | d-beta partial
-    float* s_a1 = s_stats + 64;       // [nc] sumsq    | d-gamma partial
-    float* s_c0 = s_stats + 128;      // [nc] scale    | k = gamma * rstd
-    float* s_c1 = s_stats + 192;      // [nc] shift    | d-beta / M
-    float* s_c2 = s_stats + 256;      // [nc]          | d-gamma / M
-    float* s_mean = s_stats + 320;    // [nc]
-    float* s_rstd = s_stats + 384;    // [nc]
+    float* s_part = s_stats;          // [4 warps][2][64] private per-warp partial sums (zeroed at kernel start)
+    float* s_c0 = s_stats + 512;      // [nc] scale    | k = gamma * rstd
+    float* s_c1 = s_stats + 576;      // [nc] shift    | d-beta / M
+    float* s_c2 = s_stats + 640;      // [nc]          | d-gamma / M
+    float* s_mean = s_stats + 704;    // [nc]
+    float* s_rstd = s_stats + 768;    // [nc]
     if (p.epi == EPI_BNBWD) {
       for (int c = tid128; c < p.nc; c += 128) {
         s_mean[c] = p.saved[c];
@@ -374,10 +376,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         }
         const float t1 = warp_colsum16(s1, lane);
         const float t2 = warp_colsum16(s2, lane);
-        if ((lane & 1) == 0) {
+        if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
           const int c = c0 + warp_colsum16_col(lane);
-          atomicAdd(&s_a0[c], t1);
-          atomicAdd(&s_a1[c], t2);
+          s_part[(quarter * 2 + 0) * 64 + c] += t1;
+          s_part[(quarter * 2 + 1) * 64 + c] += t2;
         }
       }
     }
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
       float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + p.nc : p.dgamma;
       for (int c = tid128; c < p.nc; c += 128) {
-        atomicAdd(g0 + c, s_a0[c]);
-        atomicAdd(g1 + c, s_a1[c]);
+        atomicAdd(g0 + c, s_part[0 * 64 + c] + s_part[2 * 64 + c] + s_part[4 * 64 + c] + s_part[6 * 64 + c]);
+        atomicAdd(g1 + c, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
       }
     }
     grid_barrier_epi(p.grid_bar, tid128);
@@ -536,8 +538,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           const float t2 = warp_colsum16(s2, lane);
           if ((lane & 1) == 0) {
             const int c = c0 + warp_colsum16_col(lane);
-            atomicAdd(&s_stats[c], t1);
-            atomicAdd(&s_stats[p.nc + c], t2);
+            s_stats[(quarter * 2 + 0) * 64 + c] += t1;
+            s_stats[(quarter * 2 + 1) * 64 + c] += t2;
           }
         }
       }
@@ -553,8 +555,11 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       // the four epilogue warps only: named barrier 1, 128 threads
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;
-      if (blockIdx.x < p.num_tiles)
-        for (int i = e; i < 2 * p.nc; i += 128) atomicAdd(&p.stats[i], s_stats[i]);
+      for (int c = e; c < p.nc; c += 128) {
+        atomicAdd(&p.stats[c], s_stats[0 * 64 + c] + s_stats[2 * 64 + c] + s_stats[4 * 64 + c] + s_stats[6 * 64 + c]);
+        atomicAdd(&p.stats[p.nc + c],
+                  s_stats[1 * 64 + c] + s_stats[3 * 64 + c] + s_stats[5 * 64 + c] + s_stats[7 * 64 + c]);
+      }
     }
     if (threadIdx.x == 64) WACIL_STAMP(9);
   }
@@ -586,7 +591,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
     wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -815,19 +820,25 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
   return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
-         8 * 64 * 4 + 64;
+         13 * 64 * 4 + 64;
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
-inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages) {
+// Shared memory is capped near 108 KB so that two CTAs (of this or of a concurrently running kernel) share an SM:
+// these kernels are latency-bound (single-thread TMA/MMA issue, short tiles), and a second resident CTA hides it.
+constexpr size_t kConvSmemBudget = 108 * 1024;
+inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemBudget) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
-  const size_t budget = 208 * 1024 - w;
+  const size_t budget = total_budget - 4096 - w;
   const size_t tap_bytes = (size_t)128 * kc * 2;
-  tps = taps;
-  if (taps == 9 && (size_t)2 * 9 * tap_bytes > budget) tps = 3;
-  stages = (int)(budget / (tps * tap_bytes));
-  if (stages > 6) stages = 6;
-  if (stages < 2) { tps = 1; stages = (int)(budget / tap_bytes); if (stages > 9) stages = 9; }
+  const int cand[3] = {9, 3, 1};
+  tps = 1;
+  stages = 2;
+  for (int c : cand) {
+    if (c > taps || taps % c) continue;
+    const int st = (int)(budget / (c * tap_bytes));
+    if (st >= 2) { tps = c; stages = st > 6 ? 6 : st; break; }
+  }
 }
 inline size_t wgrad_smem_bytes(const WgradParams& p) {
   const size_t y = (((size_t)128 * p.cout * 2) + 1023) & ~size_t(1023);

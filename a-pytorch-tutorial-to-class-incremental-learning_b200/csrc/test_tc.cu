@@ -124,15 +124,15 @@ static int run_conv(const Case& c) {
   int e1 = make_act_map(&mapA, dx, c.N, c.H, c.W, c.kc, c.stride, p.Ht, p.Nt);
   int e2 = make_mat_map(&mapW, dw, (long long)c.taps * c.nc, c.kc, c.nc);
   if (e1 || e2) { printf("  tensor map encode failed: %d %d\n", e1, e2); return 1; }
-  int grid = p.num_tiles < 148 ? p.num_tiles : 148;
+  int grid = p.num_tiles < 296 ? p.num_tiles : 296;
   __nv_bfloat16* dact = nullptr;
   float* dscratch = nullptr;
   unsigned* dbar = nullptr;
   long long* ddbg = nullptr;
   const bool fused = c.epi == EPI_BN_TRAIN;
   if (g_timing) {
-    CK(cudaMalloc(&ddbg, 148 * 16 * sizeof(long long)));
-    CK(cudaMemset(ddbg, 0, 148 * 16 * sizeof(long long)));
+    CK(cudaMalloc(&ddbg, 296 * 16 * sizeof(long long)));
+    CK(cudaMemset(ddbg, 0, 296 * 16 * sizeof(long long)));
     p.dbg = ddbg;
   }
   if (fused) {
@@ -170,7 +170,7 @@ static int run_conv(const Case& c) {
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     {
       // per-CTA timeline of the last launch (SM cycles since kernel entry of that CTA), CTA 0 and the slowest CTA
-      std::vector<long long> h(148 * 16);
+      std::vector<long long> h(296 * 16);
       CK(cudaMemcpy(h.data(), ddbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       int slow = 0;
       for (int b = 0; b < grid; ++b)
@@ -255,7 +255,7 @@ static int run_wgrad(const Case& c) {
   p.cin = cin; p.cout = cout; p.taps = c.taps; p.stride = c.stride;
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   p.num_tiles = (int)((npix + 127) / 128);
-  p.ring = 4;
+  p.ring = 2;
   p.dw = ddw;
   CUtensorMap mapX, mapDY;
   int e1 = make_act_map(&mapX, dx, c.N, c.H, c.W, cin, c.stride, p.Ht, p.Nt);
@@ -265,7 +265,7 @@ static int run_wgrad(const Case& c) {
   CK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.num_tiles < 148 ? p.num_tiles : 148;
   if (grid > 3 && !g_timing) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
-  if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 148) grid = 148; }
+  if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 296) grid = 296; }
   wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());

@@ -221,7 +221,7 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   if (e) return fail(WACIL_E_DRIVER, "activation tensor map (N=%d H=%d C=%d s=%d): %d", N, H, kc, stride, e);
   e = make_mat_map(&c.mapW, wts, static_cast<long long>(taps) * nc, kc, nc);
   if (e) return fail(WACIL_E_DRIVER, "weight tensor map (%dx%d): %d", nc, kc, e);
-  c.grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  c.grid = p.num_tiles < 2 * num_sms() ? p.num_tiles : 2 * num_sms();  // two CTAs per SM
   c.smem = conv_smem_bytes(p);
   return 0;
 }
@@ -230,9 +230,9 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   static size_t smem_set = 0;
   if (c.smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(220 * 1024));
+                                         static_cast<int>(kConvSmemBudget));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
-    smem_set = 220 * 1024;
+    smem_set = kConvSmemBudget;
   }
   if (c.p.epi >= EPI_BN_TRAIN) {
     // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
@@ -274,14 +274,14 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   const long long npix = static_cast<long long>(N) * Ho * Wo;
   p.num_tiles = static_cast<int>((npix + 127) / 128);
-  p.ring = 4;
+  p.ring = 2;
   p.dw = dw;
   int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
   if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
   e = make_mat_map(&w.mapDY, dy, npix, cout, 128);
   if (e) return fail(WACIL_E_DRIVER, "wgrad dY tensor map: %d", e);
   int g = (p.num_tiles + 1) / 2;
-  if (g > num_sms()) g = num_sms();
+  if (g > 2 * num_sms()) g = 2 * num_sms();
   if (g < 1) g = 1;
   w.grid = g;
   w.smem = wgrad_smem_bytes(p);
@@ -292,7 +292,7 @@ int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(220 * 1024));
+                                         static_cast<int>(kConvSmemBudget));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad_gemm_kernel)");
     set = true;
   }
