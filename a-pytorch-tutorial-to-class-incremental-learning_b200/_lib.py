@@ -52,6 +52,7 @@ SIGNATURES = {
     "wacil_net_forward": (I, [P, P, I, P, P, P]),
     "wacil_net_backward": (I, [P, P, I, P]),
     "wacil_net_last_launches": (I, [P]),
+    "wacil_net_set_side_stream": (I, [P, P]),
     "wacil_net_tensor": (I, [P, I, I, C.POINTER(P), C.POINTER(Z)]),
     "wacil_conv3x3_fprop": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "wacil_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),

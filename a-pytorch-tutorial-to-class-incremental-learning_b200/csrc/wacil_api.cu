@@ -133,7 +133,7 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[2], gz[2], tmp[3];
+  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3];
   std::vector<size_t> y, a, gyup;
   size_t stat_elems = 0, wbuf_elems = 0, total = 0;
 };
@@ -173,14 +173,13 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
       o.a[l] = c.take(out_b);
       if (L[l].stride == 2) o.gyup[l] = c.take(out_b * 4);
     }
-    o.gy[0] = c.take(max_act);
-    o.gy[1] = c.take(max_act);
+    for (int i = 0; i < 3; ++i) o.gy[i] = c.take(max_act);
     o.gz[0] = c.take(max_act);
     o.gz[1] = c.take(max_act);
     o.tmp[0] = o.tmp[1] = o.tmp[2] = 0;
   } else {
     for (int i = 0; i < 3; ++i) o.tmp[i] = c.take(max_act);
-    o.gy[0] = o.gy[1] = o.gz[0] = o.gz[1] = 0;
+    o.gy[0] = o.gy[1] = o.gy[2] = o.gz[0] = o.gz[1] = 0;
   }
   o.total = c.off;
 }
@@ -314,6 +313,8 @@ struct wacil_net {
   std::vector<ConvLaunch> fprop, dgrad;
   std::vector<WgradLaunch> wgrad;
   bool fwd_done = false;
+  cudaStream_t side = nullptr;          // optional second stream: weight gradients overlap the data-gradient chain
+  std::vector<cudaEvent_t> ev_gy, ev_wg;  // GY_l ready (main) / wgrad_l done (side)
   const float* last_feats = nullptr;
   bool folded = false;
   int launches = 0;
@@ -418,15 +419,15 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         c.p.res_stride = ds ? 2 : 1;
         c.p.res_c = ds ? da.cin : d.cout;
       }
-      // ---- wgrad: X = layer input, dY = GY[l % 2]
-      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 2]),
+      // ---- wgrad: X = layer input, dY = GY[l % 3]
+      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
                       n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
       if (l > 0) {
         // ---- dgrad of layer l (stride-1 conv over GY or its zero-upsampled copy, flipped [cin][cout] weights)
         //      fused with the ReLU mask + BatchNorm backward of layer l-1
         const LayerDesc& pd = n->L[l - 1];
-        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 2]);
+        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 3]);
         ConvLaunch& g = n->dgrad[l];
         e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
         if (e) { delete n; return e; }
@@ -445,7 +446,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         g.p.gamma = n->params + pd.gamma_off;
         g.p.dgamma = n->grads + pd.gamma_off;
         g.p.dbeta = n->grads + pd.beta_off;
-        g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 2]);
+        g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 3]);
         g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
         g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
         if (d.stride == 2) {
@@ -492,7 +493,28 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   return 0;
 }
 
-void wacil_net_destroy(wacil_net_t* net) { delete net; }
+void wacil_net_destroy(wacil_net_t* net) {
+  if (!net) return;
+  for (cudaEvent_t e : net->ev_gy) cudaEventDestroy(e);
+  for (cudaEvent_t e : net->ev_wg) cudaEventDestroy(e);
+  delete net;
+}
+
+int wacil_net_set_side_stream(wacil_net_t* n, void* side_stream) {
+  if (!n) return fail(WACIL_E_NULL, "net is NULL");
+  n->side = static_cast<cudaStream_t>(side_stream);
+  if (n->side != nullptr && n->ev_gy.empty()) {
+    const size_t nl = n->L.size();
+    n->ev_gy.resize(nl);
+    n->ev_wg.resize(nl);
+    for (size_t l = 0; l < nl; ++l) {
+      cudaError_t e = cudaEventCreateWithFlags(&n->ev_gy[l], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&n->ev_wg[l], cudaEventDisableTiming);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    }
+  }
+  return 0;
+}
 
 int wacil_net_last_launches(const wacil_net_t* net) { return net ? net->launches : 0; }
 
@@ -611,7 +633,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     bp.gamma = n->params + d.gamma_off;
     bp.dgamma = n->grads + d.gamma_off;
     bp.dbeta = n->grads + d.beta_off;
-    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l % 2]);
+    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l % 3]);
     bp.gy_up = d.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[l]) : nullptr;
     bp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
     bp.C = d.cout;
@@ -627,14 +649,30 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
     launches += 2;
   }
+  // dW_l needs (a_{l-1}, GY_l); the fused dgrad_l + BN-backward_{l-1} needs GY_l and writes GY_{l-1} into buffer
+  // (l-1) % 3, which is the buffer wgrad_{l+2} reads.  With a side stream the weight gradients run beside that chain.
+  cudaStream_t ws = n->side ? n->side : st;
+  const bool par = n->side != nullptr;
+#define WACIL_EV(call, what)                                   \
+  do {                                                         \
+    cudaError_t ce_ = (call);                                  \
+    if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
+  } while (0)
+  if (par) WACIL_EV(cudaEventRecord(n->ev_gy[nl - 1], st), "event record");
   for (int l = nl - 1; l >= 0; --l) {
-    if ((e = launch_wgrad(n->wgrad[l], st))) return e;  // dW_l from (a_{l-1}, GY_l)
+    if (par) WACIL_EV(cudaStreamWaitEvent(ws, n->ev_gy[l], 0), "event wait");
+    if ((e = launch_wgrad(n->wgrad[l], ws))) return e;
+    if (par) WACIL_EV(cudaEventRecord(n->ev_wg[l], ws), "event record");
     ++launches;
     if (l > 0) {
-      if ((e = launch_conv(n->dgrad[l], st))) return e;  // dgrad_l fused with BatchNorm backward of layer l-1 -> GY_{l-1}
+      if (par && l + 2 <= nl - 1) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[l + 2], 0), "event wait");
+      if ((e = launch_conv(n->dgrad[l], st))) return e;
+      if (par) WACIL_EV(cudaEventRecord(n->ev_gy[l - 1], st), "event record");
       ++launches;
     }
   }
+  if (par) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[0], 0), "event wait");  // join (the side stream is in order)
+#undef WACIL_EV
   n->launches = launches;
   return 0;
 }

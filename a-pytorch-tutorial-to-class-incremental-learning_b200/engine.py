@@ -140,6 +140,12 @@ class Plan:
         check(lib().wacil_net_backward(self.handle, dlogits.data_ptr(), dlogits.shape[1],
                                        torch.cuda.current_stream().cuda_stream), "wacil_net_backward")
 
+    def set_side_stream(self, stream):
+        """Overlap the weight-gradient kernels of backward() on `stream` (a torch.cuda.Stream) or None."""
+        self._side = stream  # keep it alive
+        check(lib().wacil_net_set_side_stream(self.handle, stream.cuda_stream if stream is not None else None),
+              "wacil_net_set_side_stream")
+
     def tensor(self, what, layer=0):
         """A view of a tensor the TRAIN plan keeps after a forward (parity tests): 0 packed input, 1 conv output,
         2 activation (all bf16 NHWC), 3 BatchNorm batch mean / rstd (fp32 [2, C])."""

@@ -148,6 +148,8 @@ class _StepState:
         self.dlogits = torch.zeros((batch, tr.c_seen), dtype=torch.float32, device=dev)
         self.ws = torch.zeros(_lib.lib().wacil_kd_workspace_bytes(batch), dtype=torch.uint8, device=dev)
         self.plan_s = tr.model._plan(_lib.NET_TRAIN, batch)
+        if tr.overlap:
+            self.plan_s.set_side_stream(tr.side_w)
         self.plan_t = None
         if tr.teacher is not None:
             self.plan_t = tr.teacher._plan(_lib.NET_INFER, batch)
@@ -163,7 +165,7 @@ class TaskTrainer:
     schedule, template.py:246-249)."""
 
     def __init__(self, model: CilModel, teacher, known_classes, lr=0.1, momentum=0.9, weight_decay=5e-4,
-                 lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None):
+                 lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None, overlap=True):
         if not model.arena.is_cuda:
             raise _lib.WacilError("TaskTrainer needs the model on a CUDA device (no CPU path)")
         self.model, self.teacher = model, teacher
@@ -173,6 +175,11 @@ class TaskTrainer:
         self.lambda_kd, self.T, self.smooth = lambda_kd, T, smooth
         self.world_size, self.pg = world_size, process_group
         self.use_graph = use_graph
+        # two extra streams: the frozen teacher's forward runs beside the student's, the weight gradients beside the
+        # data-gradient chain (independent work that otherwise leaves these latency-bound kernels' SMs half idle)
+        self.overlap = overlap
+        self.side_t = torch.cuda.Stream(device=self.device) if overlap else None
+        self.side_w = torch.cuda.Stream(device=self.device) if overlap else None
         self.mom = torch.zeros_like(model._arena.params)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
         self.acc = torch.zeros(4, dtype=torch.float32, device=self.device)  # running sums of [ce, kd, loss, top1]
@@ -187,12 +194,22 @@ class TaskTrainer:
 
     # -- pieces -------------------------------------------------------------------------------------------------
     def _fwd_bwd(self, st):
-        logits, _ = st.plan_s.forward(st.x, self.c_seen)
-        n = st.plan_s.launches
         t_logits = None
+        n = 0
+        main = torch.cuda.current_stream()
+        if st.plan_t is not None and self.overlap:
+            self.side_t.wait_stream(main)
+            with torch.cuda.stream(self.side_t):
+                t_logits, _ = st.plan_t.forward(st.x, self.known)
+                n += st.plan_t.launches
+        logits, _ = st.plan_s.forward(st.x, self.c_seen)
+        n += st.plan_s.launches
         if st.plan_t is not None:
-            t_logits, _ = st.plan_t.forward(st.x, self.known)
-            n += st.plan_t.launches
+            if self.overlap:
+                main.wait_stream(self.side_t)
+            else:
+                t_logits, _ = st.plan_t.forward(st.x, self.known)
+                n += st.plan_t.launches
         ops.ce_kd_fwd_bwd(logits, st.y, t_logits, self.known, self.T, self.lambda_kd, self.smooth, st.losses,
                           st.dlogits, st.ws)
         st.plan_s.backward(st.dlogits)

@@ -158,6 +158,10 @@ int wacil_net_forward(wacil_net_t* net, const float* x, int C_seen, float* feats
  * accumulated: the arena is zeroed inside).  feats/logits of that forward must still be intact. */
 int wacil_net_backward(wacil_net_t* net, const float* dlogits, int C_seen, void* stream);
 
+/* Optional second stream for wacil_net_backward: weight-gradient kernels are issued on it and ordered against the
+ * data-gradient chain with events (captured as parallel graph branches).  NULL restores single-stream order. */
+int wacil_net_set_side_stream(wacil_net_t* net, void* side_stream);
+
 /* Introspection for the parity tests: device pointer + size of a tensor the TRAIN plan keeps in its workspace
  * after a forward: WACIL_T_INPUT packed input bf16 [B][32][32][16] (layer ignored); WACIL_T_CONV_OUT raw conv
  * output y_l bf16 [B][H][W][C]; WACIL_T_ACT post-BN/ReLU activation a_l bf16; WACIL_T_BN_SAVED fp32 [2C] batch mean
