@@ -826,10 +826,10 @@ inline size_t conv_smem_bytes(const ConvGemmParams& p) {
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
 // Shared memory is capped near 108 KB so that two CTAs (of this or of a concurrently running kernel) share an SM:
 // these kernels are latency-bound (single-thread TMA/MMA issue, short tiles), and a second resident CTA hides it.
-constexpr size_t kConvSmemBudget = 108 * 1024;
-inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemBudget) {
+constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
+inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
-  const size_t budget = total_budget - 4096 - w;
+  const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch
   const size_t tap_bytes = (size_t)128 * kc * 2;
   const int cand[3] = {9, 3, 1};
   tps = 1;

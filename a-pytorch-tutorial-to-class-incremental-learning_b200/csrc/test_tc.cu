@@ -146,8 +146,17 @@ static int run_conv(const Case& c) {
     p.running_var = dscratch + 128; p.saved = dscratch + 256; p.eps = 1e-5f; p.momentum = 0.1f;
     if (!c.res_mode) p.res = nullptr;
   }
+  if (fused) p.acc_stages = (p.num_tiles + 147) / 148;  // upper bound for the shared-memory size
   const size_t smem = conv_smem_bytes(p);
   CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem));
+    if (g_timing) printf("   occupancy %d CTAs/SM at %zu B smem\n", occ, smem);
+    if (grid > occ * 148) grid = occ * 148;
+    if (fused) { p.acc_stages = (p.num_tiles + grid - 1) / grid; }
+  }
   auto launch = [&]() {
     if (fused) {
       void* args[] = {&mapA, &mapW, &p};
@@ -263,6 +272,7 @@ static int run_wgrad(const Case& c) {
   if (e1 || e2) { printf("  tensor map encode failed: %d %d\n", e1, e2); return 1; }
   const size_t smem = wgrad_smem_bytes(p);
   CK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int grid = p.num_tiles < 148 ? p.num_tiles : 148;
   if (grid > 3 && !g_timing) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
   if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 296) grid = 296; }

@@ -197,6 +197,8 @@ struct WgradLaunch {
   size_t smem;
 };
 
+int conv_max_resident(size_t smem);
+
 int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int nc, int stride, int taps,
                const void* wts, int epi) {
   ConvGemmParams& p = c.p;
@@ -220,19 +222,44 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   if (e) return fail(WACIL_E_DRIVER, "activation tensor map (N=%d H=%d C=%d s=%d): %d", N, H, kc, stride, e);
   e = make_mat_map(&c.mapW, wts, static_cast<long long>(taps) * nc, kc, nc);
   if (e) return fail(WACIL_E_DRIVER, "weight tensor map (%dx%d): %d", nc, kc, e);
-  c.grid = p.num_tiles < 2 * num_sms() ? p.num_tiles : 2 * num_sms();  // two CTAs per SM
   c.smem = conv_smem_bytes(p);
+  const int cap = conv_max_resident(c.smem);  // two CTAs per SM when they fit
+  c.grid = p.num_tiles < cap ? p.num_tiles : cap;
   return 0;
 }
 
+int conv_attrs() {
+  static bool set = false;
+  if (set) return 0;
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kConvSmemMax));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kConvSmemMax));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv/wgrad)");
+  set = true;
+  return 0;
+}
+
+// CTAs of conv_gemm_kernel that fit on the device at once with `smem` bytes of dynamic shared memory.
+int conv_max_resident(size_t smem) {
+  int occ = 0;
+  if (conv_attrs()) return num_sms();
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem) != cudaSuccess || occ < 1)
+    occ = 1;
+  if (occ > 2) occ = 2;
+  return occ * num_sms();
+}
+
 int launch_conv(const ConvLaunch& c, cudaStream_t st) {
-  static size_t smem_set = 0;
-  if (c.smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kConvSmemBudget));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
-    smem_set = kConvSmemBudget;
-  }
+  if (c.smem > kConvSmemMax) return fail(WACIL_E_SHAPE, "conv configuration needs %zu bytes of shared memory", c.smem);
+  { int e0 = conv_attrs(); if (e0) return e0; }
   if (c.p.epi >= EPI_BN_TRAIN) {
     // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
     void* args[] = {const_cast<CUtensorMap*>(&c.mapA), const_cast<CUtensorMap*>(&c.mapW),
@@ -258,6 +285,15 @@ int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
   c.p.eps = kBnEps;
   c.p.momentum = kBnMomentum;
   c.smem = conv_smem_bytes(c.p);
+  const int cap = conv_max_resident(c.smem);  // cooperative launch: the whole grid must be resident
+  if (c.grid > cap) {
+    c.grid = cap;
+    c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
+    c.smem = conv_smem_bytes(c.p);
+  }
+  if (c.p.acc_stages * c.p.nc > 256)
+    return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path (%d tiles x %d channels per CTA)",
+                c.p.acc_stages, c.p.nc);
   return 0;
 }
 
@@ -288,13 +324,7 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
 }
 
 int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kConvSmemBudget));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(wgrad_gemm_kernel)");
-    set = true;
-  }
+  { int e0 = conv_attrs(); if (e0) return e0; }
   wgrad_gemm_kernel<<<w.grid, kConvThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
   WACIL_LAUNCH_CHECK("wgrad_gemm_kernel");
   return 0;
