@@ -168,7 +168,7 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
 
 constexpr int kConvThreads = 192;
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -318,26 +318,72 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
-    int as = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
-      mbar_wait(&accfull[as], 0);
-      tc_fence_after();
-      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
-      const int pix = tile * 128 + m;
-      const bool valid = pix < p.num_pixels;
-      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      const __nv_bfloat16* gres_ptr = nullptr;
-      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
-        if (p.gres_mode == 1) {
-          gres_ptr = p.g_res + base;
-        } else {
-          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (((w | h) & 1) == 0)
-            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+    // Work items = (tile, 16-channel chunk) pairs of this CTA, walked in order.  The global-memory operands of item
+    // i+1 (shortcut / activation / raw output) are requested before item i is processed so their latency overlaps.
+    const int nch = p.nc / 16;
+    const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_items = my_tiles * nch;
+    struct Aux {
+      uint4 r[2], a[2], y[2];
+      bool has_r;
+    };
+    auto item_pix = [&](int it) { return (static_cast<int>(blockIdx.x) + (it / nch) * static_cast<int>(gridDim.x)) * 128 + m; };
+    auto issue = [&](int it, Aux& x) {
+      x.has_r = false;
+      if (it >= n_items) return;
+      const int pix = item_pix(it);
+      if (pix >= p.num_pixels) return;
+      const int c0 = (it % nch) * 16;
+      const size_t base = static_cast<size_t>(pix) * p.nc + c0;
+      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+      if (p.epi == EPI_BN_TRAIN) {
+        if (p.res != nullptr && c0 < p.res_c) {
+          const __nv_bfloat16* rp =
+              p.res_stride == 1 ? p.res + static_cast<size_t>(pix) * p.res_c + c0
+                                : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c + c0;
+          x.r[0] = __ldg(reinterpret_cast<const uint4*>(rp));
+          x.r[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+          x.has_r = true;
+        }
+      } else {
+        x.a[0] = __ldg(reinterpret_cast<const uint4*>(p.act_in + base));
+        x.a[1] = __ldg(reinterpret_cast<const uint4*>(p.act_in + base) + 1);
+        x.y[0] = __ldg(reinterpret_cast<const uint4*>(p.y_in + base));
+        x.y[1] = __ldg(reinterpret_cast<const uint4*>(p.y_in + base) + 1);
+        if (p.g_res != nullptr) {
+          const __nv_bfloat16* gp = nullptr;
+          if (p.gres_mode == 1) gp = p.g_res + base;
+          else if (((w | h) & 1) == 0)
+            gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc) + c0;
+          if (gp != nullptr) {
+            x.r[0] = __ldg(reinterpret_cast<const uint4*>(gp));
+            x.r[1] = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
+            x.has_r = true;
+          }
         }
       }
-      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+    };
+    auto unpack16 = [](const uint4 (&q)[2], float (&v)[16]) {
+      const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(q);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __bfloat162float(b[i]);
+    };
+
+    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
+    {
+      Aux cur, nxt;
+      if (p.epi == EPI_BNBWD) issue(0, cur);
+      for (int it = 0; it < n_items; ++it) {
+        const int as = it / nch, c0 = (it % nch) * 16;
+        if (c0 == 0) {
+          mbar_wait(&accfull[as], 0);
+          tc_fence_after();
+          if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
+        }
+        if (p.epi == EPI_BNBWD) issue(it + 1, nxt);
+        const int pix = item_pix(it);
+        const bool valid = pix < p.num_pixels;
+        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
         float v[16], s1[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
@@ -358,11 +404,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         } else {
           float a[16], yv[16];
           if (valid) {
-            load16_bf16(p.act_in + base + c0, a);
-            load16_bf16(p.y_in + base + c0, yv);
-            if (gres_ptr != nullptr) {
+            unpack16(cur.a, a);
+            unpack16(cur.y, yv);
+            if (cur.has_r) {
               float r[16];
-              load16_bf16(gres_ptr + c0, r);
+              unpack16(cur.r, r);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += r[i];
             }
@@ -373,6 +419,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
             s1[i] = gzv;
             s2[i] = valid ? gzv * (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;
           }
+          cur = nxt;
         }
         const float t1 = warp_colsum16(s1, lane);
         const float t2 = warp_colsum16(s2, lane);
@@ -393,6 +440,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         atomicAdd(g1 + c, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
       }
     }
+    Aux cur2;
+    issue(0, cur2);  // first phase-2 operands travel while the grid barrier is pending
     grid_barrier_epi(p.grid_bar, tid128);
     if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
@@ -420,62 +469,55 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---------------- phase 2: normalise (forward) / BN backward, from the accumulators still in TMEM
-    as = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
-      const int pix = tile * 128 + m;
-      const bool valid = pix < p.num_pixels;
-      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-      const __nv_bfloat16* res_ptr = nullptr;
-      const __nv_bfloat16* gres_ptr = nullptr;
-      if (valid && p.epi == EPI_BN_TRAIN && p.res != nullptr) {
-        res_ptr = p.res_stride == 1
-                      ? p.res + static_cast<size_t>(pix) * p.res_c
-                      : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
-      }
-      if (valid && p.epi == EPI_BNBWD && p.g_res != nullptr) {
-        if (p.gres_mode == 1) gres_ptr = p.g_res + base;
-        else if (((w | h) & 1) == 0)
-          gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
-      }
-      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+    {
+      Aux nxt;
+      for (int it = 0; it < n_items; ++it) {
+        const int as = it / nch, c0 = (it % nch) * 16;
+        issue(it + 1, nxt);
+        const int pix = item_pix(it);
+        const bool valid = pix < p.num_pixels;
+        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (!valid) continue;
-        if (p.epi == EPI_BN_TRAIN) {
+        if (valid) {
+          if (p.epi == EPI_BN_TRAIN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
-          if (res_ptr != nullptr && c0 < p.res_c) {
-            float r[16];
-            load16_bf16(res_ptr + c0, r);
+            for (int i = 0; i < 16; ++i)
+              v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
+            if (cur2.has_r) {
+              float r[16];
+              unpack16(cur2.r, r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            store16_bf16(p.act_out + base + c0, v);
+          } else {
+            float a[16], yv[16], o[16];
+            unpack16(cur2.a, a);
+            unpack16(cur2.y, yv);
+            if (cur2.has_r) {
+              float r[16];
+              unpack16(cur2.r, r);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
+              const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+              o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
+            }
+            store16_bf16(p.gy + base + c0, o);
+            if (p.gy_up != nullptr) {
+              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+              store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
+            }
+            if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          store16_bf16(p.act_out + base + c0, v);
-        } else {
-          float a[16], yv[16], o[16];
-          load16_bf16(p.act_in + base + c0, a);
-          load16_bf16(p.y_in + base + c0, yv);
-          if (gres_ptr != nullptr) {
-            float r[16];
-            load16_bf16(gres_ptr + c0, r);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
-            const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
-            o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
-          }
-          store16_bf16(p.gy + base + c0, o);
-          if (p.gy_up != nullptr)
-            store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
-          if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
         }
+        cur2 = nxt;
       }
     }
     if (tid128 == 0) WACIL_STAMP(9);  // phase 2 done
@@ -591,7 +633,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
     wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -824,9 +866,9 @@ inline size_t conv_smem_bytes(const ConvGemmParams& p) {
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
-// Shared memory is capped near 108 KB so that two CTAs (of this or of a concurrently running kernel) share an SM:
-// these kernels are latency-bound (single-thread TMA/MMA issue, short tiles), and a second resident CTA hides it.
-constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
+// A kernel that allocates TMEM is resident alone on its SM (EIATTR_TCGEN05_1CTA_USED: occupancy 1 for any shared
+// memory / register footprint, measured with csrc/occ_probe.cu), so the pipeline may use the whole 227 KB.
+constexpr size_t kConvSmemMax = 216 * 1024;
 inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch
@@ -837,7 +879,7 @@ inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, 
   for (int c : cand) {
     if (c > taps || taps % c) continue;
     const int st = (int)(budget / (c * tap_bytes));
-    if (st >= 2) { tps = c; stages = st > 6 ? 6 : st; break; }
+    if (st >= 2) { tps = c; stages = st > 5 ? 5 : st; break; }
   }
 }
 inline size_t wgrad_smem_bytes(const WgradParams& p) {

@@ -253,7 +253,6 @@ int conv_max_resident(size_t smem) {
   if (conv_attrs()) return num_sms();
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem) != cudaSuccess || occ < 1)
     occ = 1;
-  if (occ > 2) occ = 2;
   return occ * num_sms();
 }
 
@@ -291,7 +290,7 @@ int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
     c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
     c.smem = conv_smem_bytes(c.p);
   }
-  if (c.p.acc_stages * c.p.nc > 256)
+  if (c.p.acc_stages * c.p.nc > 512)
     return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path (%d tiles x %d channels per CTA)",
                 c.p.acc_stages, c.p.nc);
   return 0;
@@ -309,7 +308,7 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   const long long npix = static_cast<long long>(N) * Ho * Wo;
   p.num_tiles = static_cast<int>((npix + 127) / 128);
-  p.ring = 2;
+  p.ring = 4;
   p.dw = dw;
   int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
   if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
