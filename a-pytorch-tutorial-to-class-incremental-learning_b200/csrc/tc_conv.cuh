@@ -866,9 +866,11 @@ inline size_t conv_smem_bytes(const ConvGemmParams& p) {
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
-// A kernel that allocates TMEM is resident alone on its SM (EIATTR_TCGEN05_1CTA_USED: occupancy 1 for any shared
-// memory / register footprint, measured with csrc/occ_probe.cu), so the pipeline may use the whole 227 KB.
-constexpr size_t kConvSmemMax = 216 * 1024;
+// Shared memory per CTA is capped at 113 KB (2 x (113 + 1 reserved) = 228 KB per SM).  The occupancy API reports one
+// CTA per SM for any tcgen05 kernel (EIATTR_TCGEN05_1CTA_USED, csrc/occ_probe.cu), but measured on the overlapped step
+// graph the small footprint is 17 % faster than 194 KB pipelines (1.48 vs 1.78 ms): CTAs of the two concurrently
+// running branches get placed sooner.  The kernels are latency-bound, so deeper rings buy nothing.
+constexpr size_t kConvSmemMax = 113 * 1024;
 inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch
@@ -879,7 +881,7 @@ inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, 
   for (int c : cand) {
     if (c > taps || taps % c) continue;
     const int st = (int)(budget / (c * tap_bytes));
-    if (st >= 2) { tps = c; stages = st > 5 ? 5 : st; break; }
+    if (st >= 2) { tps = c; stages = st > 6 ? 6 : st; break; }
   }
 }
 inline size_t wgrad_smem_bytes(const WgradParams& p) {

@@ -264,7 +264,7 @@ static int run_wgrad(const Case& c) {
   p.cin = cin; p.cout = cout; p.taps = c.taps; p.stride = c.stride;
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   p.num_tiles = (int)((npix + 127) / 128);
-  p.ring = 4;
+  p.ring = 2;
   p.dw = ddw;
   CUtensorMap mapX, mapDY;
   int e1 = make_act_map(&mapX, dx, c.N, c.H, c.W, cin, c.stride, p.Ht, p.Nt);

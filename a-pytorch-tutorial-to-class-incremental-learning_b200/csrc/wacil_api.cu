@@ -308,7 +308,7 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   const long long npix = static_cast<long long>(N) * Ho * Wo;
   p.num_tiles = static_cast<int>((npix + 127) / 128);
-  p.ring = 4;
+  p.ring = 2;
   p.dw = dw;
   int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
   if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
