@@ -324,7 +324,7 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
 
 int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
-  wgrad_gemm_kernel<<<w.grid, kConvThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
+  wgrad_gemm_kernel<<<w.grid, kWgradThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
   WACIL_LAUNCH_CHECK("wgrad_gemm_kernel");
   return 0;
 }
