@@ -171,7 +171,7 @@ constexpr int kConvThreads = 320;   // 2 + 8 warps
 constexpr int kWgradThreads = 192;  // 2 + 4 warps
 constexpr int kEpiThreads = 256;
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 2)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -655,7 +655,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kWgradThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 2)
     wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
