@@ -15,9 +15,8 @@
 //                       (LBO = tap-slot stride), K = pixels, accumulators live in TMEM across all of a CTA's
 //                       pixel tiles and are flushed once with vector fp32 reductions.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue, then the epilogue warps (TMEM lane quarter =
-// warp_idx % 4): eight in conv_gemm_kernel (two per quarter, splitting the (tile, 16-channel chunk) work items by
-// parity — the epilogues are instruction-issue bound with one warp per scheduler), four in wgrad_gemm_kernel.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_idx % 4).
 #pragma once
 #include "tc_prims.cuh"
 
@@ -75,11 +74,11 @@ struct ConvGemmParams {
   long long* dbg;               // optional [gridDim.x][16] clock64 timestamps of pipeline milestones (profiling)
 };
 
-// Grid-wide barrier among the epilogue thread groups (256 threads, named barrier 1) of all CTAs.  Needs a
+// Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
 // cooperative launch (all CTAs co-resident).  bar[0], bar[1] are zero at rest; bounded spin (a bug must trap, not hang).
-__device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid_epi) {
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (tid_epi == 0) {
+__device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid128 == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
     const long long t0 = clock64();
@@ -96,7 +95,7 @@ __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid_epi) {
       bar[0] = 0u;
     }
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 #define WACIL_STAMP(slot)                                                        \
@@ -167,9 +166,7 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
-constexpr int kConvThreads = 320;   // 2 + 8 warps
-constexpr int kWgradThreads = 192;  // 2 + 4 warps
-constexpr int kEpiThreads = 256;
+constexpr int kConvThreads = 192;
 
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
@@ -197,7 +194,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   uint64_t* accfull = wfull + 1;          // [nacc]
   uint64_t* accempty = accfull + nacc;    // [nacc]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [21*64] per-channel scratch
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [13*64] per-channel scratch
 
   const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc));
 
@@ -211,12 +208,12 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     mbar_init(wfull, 1);
     for (int i = 0; i < nacc; ++i) {
       mbar_init(&accfull[i], 1);
-      mbar_init(&accempty[i], 8);
+      mbar_init(&accempty[i], 4);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 21 * 64; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 13 * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -305,92 +302,42 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   } else if (p.epi >= EPI_BN_TRAIN) {
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
     const int quarter = warp & 3;
-    const int ew = warp - 2;          // epilogue warp 0..7
-    const int half = ew >> 2;         // the two warps of a lane quarter take the even / odd work items
     const int m = quarter * 32 + lane;
-    const int tid128 = threadIdx.x - 64;  // 0..255 within the epilogue group
+    const int tid128 = threadIdx.x - 64;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    float* s_part = s_stats;          // [8 warps][2][64] private per-warp partial sums (zeroed at kernel start)
-    float* s_c0 = s_stats + 1024;     // [nc] scale    | k = gamma * rstd
-    float* s_c1 = s_stats + 1088;     // [nc] shift    | d-beta / M
-    float* s_c2 = s_stats + 1152;     // [nc]          | d-gamma / M
-    float* s_mean = s_stats + 1216;   // [nc]
-    float* s_rstd = s_stats + 1280;   // [nc]
+    float* s_part = s_stats;          // [4 warps][2][64] private per-warp partial sums (zeroed at kernel start)
+    float* s_c0 = s_stats + 512;      // [nc] scale    | k = gamma * rstd
+    float* s_c1 = s_stats + 576;      // [nc] shift    | d-beta / M
+    float* s_c2 = s_stats + 640;      // [nc]          | d-gamma / M
+    float* s_mean = s_stats + 704;    // [nc]
+    float* s_rstd = s_stats + 768;    // [nc]
     if (p.epi == EPI_BNBWD) {
-      for (int c = tid128; c < p.nc; c += kEpiThreads) {
+      for (int c = tid128; c < p.nc; c += 128) {
         s_mean[c] = p.saved[c];
         s_rstd[c] = p.saved[p.nc + c];
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // Work items = (tile, 16-channel chunk) pairs of this CTA, walked in order.  The global-memory operands of item
-    // i+1 (shortcut / activation / raw output) are requested before item i is processed so their latency overlaps.
-    const int nch = p.nc / 16;
-    const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int n_items = my_tiles * nch;
-    struct Aux {
-      uint4 r[2], a[2], y[2];
-      bool has_r;
-    };
-    auto item_pix = [&](int it) { return (static_cast<int>(blockIdx.x) + (it / nch) * static_cast<int>(gridDim.x)) * 128 + m; };
-    auto issue = [&](int it, Aux& x) {
-      x.has_r = false;
-      if (it >= n_items) return;
-      const int pix = item_pix(it);
-      if (pix >= p.num_pixels) return;
-      const int c0 = (it % nch) * 16;
-      const size_t base = static_cast<size_t>(pix) * p.nc + c0;
-      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-      if (p.epi == EPI_BN_TRAIN) {
-        if (p.res != nullptr && c0 < p.res_c) {
-          const __nv_bfloat16* rp =
-              p.res_stride == 1 ? p.res + static_cast<size_t>(pix) * p.res_c + c0
-                                : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c + c0;
-          x.r[0] = __ldg(reinterpret_cast<const uint4*>(rp));
-          x.r[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-          x.has_r = true;
-        }
-      } else {
-        x.a[0] = __ldg(reinterpret_cast<const uint4*>(p.act_in + base));
-        x.a[1] = __ldg(reinterpret_cast<const uint4*>(p.act_in + base) + 1);
-        x.y[0] = __ldg(reinterpret_cast<const uint4*>(p.y_in + base));
-        x.y[1] = __ldg(reinterpret_cast<const uint4*>(p.y_in + base) + 1);
-        if (p.g_res != nullptr) {
-          const __nv_bfloat16* gp = nullptr;
-          if (p.gres_mode == 1) gp = p.g_res + base;
-          else if (((w | h) & 1) == 0)
-            gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc) + c0;
-          if (gp != nullptr) {
-            x.r[0] = __ldg(reinterpret_cast<const uint4*>(gp));
-            x.r[1] = __ldg(reinterpret_cast<const uint4*>(gp) + 1);
-            x.has_r = true;
-          }
+    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
+    int as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      mbar_wait(&accfull[as], 0);
+      tc_fence_after();
+      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      const __nv_bfloat16* gres_ptr = nullptr;
+      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
+        if (p.gres_mode == 1) {
+          gres_ptr = p.g_res + base;
+        } else {
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          if (((w | h) & 1) == 0)
+            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
         }
       }
-    };
-    auto unpack16 = [](const uint4 (&q)[2], float (&v)[16]) {
-      const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(q);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __bfloat162float(b[i]);
-    };
-
-    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
-    {
-      Aux cur, nxt;
-      if (p.epi == EPI_BNBWD) issue(half, cur);
-      int waited = -1;
-      for (int it = half; it < n_items; it += 2) {
-        const int as = it / nch, c0 = (it % nch) * 16;
-        if (as != waited) {
-          mbar_wait(&accfull[as], 0);
-          tc_fence_after();
-          waited = as;
-          if (tid128 == 0 && it == 0) WACIL_STAMP(6);  // first accumulator complete
-        }
-        if (p.epi == EPI_BNBWD) issue(it + 2, nxt);
-        const int pix = item_pix(it);
-        const bool valid = pix < p.num_pixels;
-        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16], s1[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
@@ -411,11 +358,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         } else {
           float a[16], yv[16];
           if (valid) {
-            unpack16(cur.a, a);
-            unpack16(cur.y, yv);
-            if (cur.has_r) {
+            load16_bf16(p.act_in + base + c0, a);
+            load16_bf16(p.y_in + base + c0, yv);
+            if (gres_ptr != nullptr) {
               float r[16];
-              unpack16(cur.r, r);
+              load16_bf16(gres_ptr + c0, r);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += r[i];
             }
@@ -426,40 +373,31 @@ __global__ void __launch_bounds__(kConvThreads, 2)
             s1[i] = gzv;
             s2[i] = valid ? gzv * (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;
           }
-          cur = nxt;
         }
         const float t1 = warp_colsum16(s1, lane);
         const float t2 = warp_colsum16(s2, lane);
         if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
           const int c = c0 + warp_colsum16_col(lane);
-          s_part[(ew * 2 + 0) * 64 + c] += t1;
-          s_part[(ew * 2 + 1) * 64 + c] += t2;
+          s_part[(quarter * 2 + 0) * 64 + c] += t1;
+          s_part[(quarter * 2 + 1) * 64 + c] += t2;
         }
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
     {
       float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
       float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + p.nc : p.dgamma;
-      for (int c = tid128; c < p.nc; c += kEpiThreads) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) {
-          a0 += s_part[(wv * 2 + 0) * 64 + c];
-          a1 += s_part[(wv * 2 + 1) * 64 + c];
-        }
-        atomicAdd(g0 + c, a0);
-        atomicAdd(g1 + c, a1);
+      for (int c = tid128; c < p.nc; c += 128) {
+        atomicAdd(g0 + c, s_part[0 * 64 + c] + s_part[2 * 64 + c] + s_part[4 * 64 + c] + s_part[6 * 64 + c]);
+        atomicAdd(g1 + c, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
       }
     }
-    Aux cur2;
-    issue(half, cur2);  // first phase-2 operands travel while the grid barrier is pending
     grid_barrier_epi(p.grid_bar, tid128);
     if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels);
-    for (int c = tid128; c < p.nc; c += kEpiThreads) {
+    for (int c = tid128; c < p.nc; c += 128) {
       if (p.epi == EPI_BN_TRAIN) {
         const float mean = __ldcg(p.stats + c) / cnt;
         float var = __ldcg(p.stats + p.nc + c) / cnt - mean * mean;
@@ -480,70 +418,74 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         s_c2[c] = __ldcg(p.dgamma + c) / cnt;
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---------------- phase 2: normalise (forward) / BN backward, from the accumulators still in TMEM
-    {
-      Aux nxt;
-      for (int it = half; it < n_items; it += 2) {
-        const int as = it / nch, c0 = (it % nch) * 16;
-        issue(it + 2, nxt);
-        const int pix = item_pix(it);
-        const bool valid = pix < p.num_pixels;
-        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+    as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+      const __nv_bfloat16* res_ptr = nullptr;
+      const __nv_bfloat16* gres_ptr = nullptr;
+      if (valid && p.epi == EPI_BN_TRAIN && p.res != nullptr) {
+        res_ptr = p.res_stride == 1
+                      ? p.res + static_cast<size_t>(pix) * p.res_c
+                      : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+      }
+      if (valid && p.epi == EPI_BNBWD && p.g_res != nullptr) {
+        if (p.gres_mode == 1) gres_ptr = p.g_res + base;
+        else if (((w | h) & 1) == 0)
+          gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+      }
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (valid) {
-          if (p.epi == EPI_BN_TRAIN) {
+        if (!valid) continue;
+        if (p.epi == EPI_BN_TRAIN) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
-            if (cur2.has_r) {
-              float r[16];
-              unpack16(cur2.r, r);
+          for (int i = 0; i < 16; ++i)
+            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
+          if (res_ptr != nullptr && c0 < p.res_c) {
+            float r[16];
+            load16_bf16(res_ptr + c0, r);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += r[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            store16_bf16(p.act_out + base + c0, v);
-          } else {
-            float a[16], yv[16], o[16];
-            unpack16(cur2.a, a);
-            unpack16(cur2.y, yv);
-            if (cur2.has_r) {
-              float r[16];
-              unpack16(cur2.r, r);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += r[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
-              const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
-              o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
-            }
-            store16_bf16(p.gy + base + c0, o);
-            if (p.gy_up != nullptr) {
-              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-              store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
-            }
-            if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          store16_bf16(p.act_out + base + c0, v);
+        } else {
+          float a[16], yv[16], o[16];
+          load16_bf16(p.act_in + base + c0, a);
+          load16_bf16(p.y_in + base + c0, yv);
+          if (gres_ptr != nullptr) {
+            float r[16];
+            load16_bf16(gres_ptr + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
+            const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+            o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
+          }
+          store16_bf16(p.gy + base + c0, o);
+          if (p.gy_up != nullptr)
+            store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
+          if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
         }
-        cur2 = nxt;
       }
     }
     if (tid128 == 0) WACIL_STAMP(9);  // phase 2 done
   } else {
-    // ------------------------------------------------------------ epilogue (8 warps, two per TMEM lane quarter)
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;
-    const int ew = warp - 2;
-    const int half = ew >> 2;
     const int m = quarter * 32 + lane;
-    const int nch = p.nc / 16;
-    int as = 0, seq = 0;
+    int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++seq) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&accfull[as], aphase);
       tc_fence_after();
       if (threadIdx.x == 64 && tile == static_cast<int>(blockIdx.x)) WACIL_STAMP(6);
@@ -560,19 +502,18 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
         }
       }
-      for (int ch = 0; ch < nch; ++ch) {
-        if (((seq * nch + ch) & 1) != half) continue;  // the partner warp of this quarter takes this chunk
-        const int c0 = ch * 16;
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * p.nc + c0, v);
         if (p.epi == EPI_INFER) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
           if (res_ptr != nullptr && c0 < p.res_c) {
-            float r[16];
-            load16_bf16(res_ptr + c0, r);
+            const uint4* rp = reinterpret_cast<const uint4*>(res_ptr + c0);
+            uint4 r4[2] = {__ldg(rp), __ldg(rp + 1)};
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(r4);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
+            for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(rb[i]);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -597,8 +538,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           const float t2 = warp_colsum16(s2, lane);
           if ((lane & 1) == 0) {
             const int c = c0 + warp_colsum16_col(lane);
-            s_stats[(ew * 2 + 0) * 64 + c] += t1;
-            s_stats[(ew * 2 + 1) * 64 + c] += t2;
+            s_stats[(quarter * 2 + 0) * 64 + c] += t1;
+            s_stats[(quarter * 2 + 1) * 64 + c] += t2;
           }
         }
       }
@@ -611,18 +552,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
     }
     if (p.epi == EPI_STATS) {
-      // the eight epilogue warps only: named barrier 1, 256 threads
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // the four epilogue warps only: named barrier 1, 128 threads
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;
-      for (int c = e; c < p.nc; c += kEpiThreads) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) {
-          a0 += s_stats[(wv * 2 + 0) * 64 + c];
-          a1 += s_stats[(wv * 2 + 1) * 64 + c];
-        }
-        atomicAdd(&p.stats[c], a0);
-        atomicAdd(&p.stats[p.nc + c], a1);
+      for (int c = e; c < p.nc; c += 128) {
+        atomicAdd(&p.stats[c], s_stats[0 * 64 + c] + s_stats[2 * 64 + c] + s_stats[4 * 64 + c] + s_stats[6 * 64 + c]);
+        atomicAdd(&p.stats[p.nc + c],
+                  s_stats[1 * 64 + c] + s_stats[3 * 64 + c] + s_stats[5 * 64 + c] + s_stats[7 * 64 + c]);
       }
     }
     if (threadIdx.x == 64) WACIL_STAMP(9);
@@ -655,7 +591,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kWgradThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 2)
     wgrad_gemm_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDY,
                       const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -884,15 +820,17 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
   return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
-         21 * 64 * 4 + 64;
+         13 * 64 * 4 + 64;
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
-// Shared memory per CTA is capped at 113 KB (2 x (113 + 1 reserved) = 228 KB per SM).  The occupancy API reports one
-// CTA per SM for any tcgen05 kernel (EIATTR_TCGEN05_1CTA_USED, csrc/occ_probe.cu), but measured on the overlapped step
-// graph the small footprint is 17 % faster than 194 KB pipelines (1.48 vs 1.78 ms): CTAs of the two concurrently
-// running branches get placed sooner.  The kernels are latency-bound, so deeper rings buy nothing.
-constexpr size_t kConvSmemMax = 113 * 1024;
+// Per-CTA footprint is kept under half an SM in BOTH shared memory (<= 113 KB) and registers (192 threads x 160 regs =
+// 30.7 K) so that CTAs of the two concurrently running graph branches (teacher || student forward, weight gradients ||
+// data-gradient chain) can share an SM.  Measured on the overlapped step graph (profiles/r01_footprint_experiments.md):
+// 1.48 ms with this footprint vs 1.78 ms with 194 KB pipelines and 1.71 ms with 320 threads x 168 regs, although
+// those variants are as fast or faster in isolation: the kernels are latency-bound, a second resident CTA hides it.
+// (The occupancy API reports 1 CTA/SM for any tcgen05 kernel — csrc/occ_probe.cu — so a cooperative grid is <= #SMs.)
+constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
 inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch

@@ -276,7 +276,7 @@ static int run_wgrad(const Case& c) {
   int grid = p.num_tiles < 148 ? p.num_tiles : 148;
   if (grid > 3 && !g_timing) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
   if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 296) grid = 296; }
-  wgrad_gemm_kernel<<<grid, kWgradThreads, smem>>>(mapX, mapDY, p);
+  wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   if (g_timing) {
@@ -284,7 +284,7 @@ static int run_wgrad(const Case& c) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = 50;
     cudaEventRecord(e0);
-    for (int i = 0; i < reps; ++i) wgrad_gemm_kernel<<<grid, kWgradThreads, smem>>>(mapX, mapDY, p);
+    for (int i = 0; i < reps; ++i) wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -253,6 +253,7 @@ int conv_max_resident(size_t smem) {
   if (conv_attrs()) return num_sms();
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem) != cudaSuccess || occ < 1)
     occ = 1;
+  if (occ > 2) occ = 2;
   return occ * num_sms();
 }
 
@@ -290,7 +291,7 @@ int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
     c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
     c.smem = conv_smem_bytes(c.p);
   }
-  if (c.p.acc_stages * c.p.nc > 512)
+  if (c.p.acc_stages * c.p.nc > 256)
     return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path (%d tiles x %d channels per CTA)",
                 c.p.acc_stages, c.p.nc);
   return 0;
@@ -324,7 +325,7 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
 
 int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
-  wgrad_gemm_kernel<<<w.grid, kWgradThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
+  wgrad_gemm_kernel<<<w.grid, kConvThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
   WACIL_LAUNCH_CHECK("wgrad_gemm_kernel");
   return 0;
 }
