@@ -72,6 +72,8 @@ struct ConvGemmParams {
   __nv_bfloat16* gy_up;         // optional zero-upsampled copy (stride-2 layer l)
   __nv_bfloat16* gz;            // optional masked gradient (shortcut of the previous block)
   long long* dbg;               // optional [gridDim.x][16] clock64 timestamps of pipeline milestones (profiling)
+  int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
+  int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
 };
 
 // Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
@@ -220,11 +222,24 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) WACIL_STAMP(1);  // barriers initialised, TMEM allocated
 
+  // Programmatic dependent launch: everything above (and the weight TMA when the weights are older than the upstream
+  // grid) overlaps the tail of the previous kernel; its outputs are only touched after griddepcontrol.wait.
+  if (p.pdl && p.w_early && warp == 0 && lane == 0) {
+    mbar_expect_tx(wfull, w_bytes);
+    for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+  }
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(wfull, w_bytes);
-      for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+      if (!(p.pdl && p.w_early)) {
+        mbar_expect_tx(wfull, w_bytes);
+        for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -584,6 +599,7 @@ struct WgradParams {
   int num_tiles;      // pixel tiles in total
   int ring;           // group ring depth (32 KB each)
   float* dw;          // [taps*cin][cout] fp32, accumulated with red.global.add
+  int pdl;            // launched with programmatic stream serialization
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -644,6 +660,10 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     if (lane == 0) {

@@ -2,6 +2,7 @@
 // Host code only sequences kernels; it never allocates device memory and never synchronises.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,6 +36,15 @@ int cuda_fail(cudaError_t e, const char* what) {
     cudaError_t e_ = cudaGetLastError();                   \
     if (e_ != cudaSuccess) return cuda_fail(e_, what);     \
   } while (0)
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WACIL_PDL");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 int num_sms() {
   static int n = 0;
@@ -260,17 +270,27 @@ int conv_max_resident(size_t smem) {
 int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   if (c.smem > kConvSmemMax) return fail(WACIL_E_SHAPE, "conv configuration needs %zu bytes of shared memory", c.smem);
   { int e0 = conv_attrs(); if (e0) return e0; }
-  if (c.p.epi >= EPI_BN_TRAIN) {
-    // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
-    void* args[] = {const_cast<CUtensorMap*>(&c.mapA), const_cast<CUtensorMap*>(&c.mapW),
-                    const_cast<ConvGemmParams*>(&c.p)};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(conv_gemm_kernel), dim3(c.grid),
-                                                dim3(kConvThreads), args, c.smem, st);
-    if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel (cooperative)");
-    return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(c.grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (c.p.epi >= EPI_BN_TRAIN) {  // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
+    ++na;
   }
-  conv_gemm_kernel<<<c.grid, kConvThreads, c.smem, st>>>(c.mapA, c.mapW, c.p);
-  WACIL_LAUNCH_CHECK("conv_gemm_kernel");
+  if (c.p.pdl) {  // start under the tail of the previous kernel of this stream (the kernel waits before reading)
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel");
   return 0;
 }
 
@@ -325,8 +345,18 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
 
 int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
-  wgrad_gemm_kernel<<<w.grid, kConvThreads, w.smem, st>>>(w.mapX, w.mapDY, w.p);
-  WACIL_LAUNCH_CHECK("wgrad_gemm_kernel");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(w.grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = w.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = w.p.pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel, w.mapX, w.mapDY, w.p);
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad_gemm_kernel");
   return 0;
 }
 
@@ -433,6 +463,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
                      wbuf + d.wf_off, EPI_STATS);
       if (e) { delete n; return e; }
       if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) { delete n; return e; }
+      c.p.pdl = pdl_enabled() ? 1 : 0;
+      c.p.w_early = l > 0 ? 1 : 0;  // layer 0 is launched right after cast_weights
       c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
       c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
       c.p.stats = stats + so[l];
@@ -453,6 +485,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
                       n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
+      n->wgrad[l].p.pdl = pdl_enabled() ? 1 : 0;
       if (l > 0) {
         // ---- dgrad of layer l (stride-1 conv over GY or its zero-upsampled copy, flipped [cin][cout] weights)
         //      fused with the ReLU mask + BatchNorm backward of layer l-1
@@ -462,6 +495,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
         if (e) { delete n; return e; }
         if ((e = make_fused(g, EPI_BNBWD, gbar))) { delete n; return e; }
+        g.p.pdl = pdl_enabled() ? 1 : 0;
+        g.p.w_early = 1;  // operand copies were written by cast_weights in the forward
         const int pl = static_cast<int>(l) - 1;
         g.p.g_res = nullptr;
         const bool block_output = (pl == 0) || (pl % 2 == 0);
@@ -512,6 +547,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
       if (e) { delete n; return e; }
+      c.p.pdl = pdl_enabled() ? 1 : 0;
+      c.p.w_early = 1;  // folded once per task by wacil_net_fold
       c.p.out = outp;
       c.p.bias = bias + d.bias_off;
       c.p.res = res;
