@@ -216,6 +216,11 @@ def kernel_rooflines(w, pk):
     return out
 
 
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args, rank, local_rank, world):
     import wacil_b200 as w
     torch.cuda.set_device(local_rank)
@@ -244,17 +249,22 @@ def run_ours(args, rank, local_rank, world):
         loss_host[i % loss_host.shape[0]].copy_(losses, non_blocking=True)
 
     warm = max(args.warmup, 3)
+    _dbg('model ready; first eager steps + graph capture')
     for i in range(3):  # two eager steps and the graph capture happen before anything is warmed up or timed
         step_dev(i)
     torch.cuda.synchronize()
+    _dbg('graph captured; soak')
     with ClockSampler(local_rank) as clk:  # clocks under load: warm-up, both timed regions and the soak in between
         for i in range(max(warm, 400)):  # >= W warm-up steps; a fixed count (same on every rank) long enough
             step_dev(i)                  # (~0.5 s) for the 200 ms sampler to see the clocks under load
         torch.cuda.synchronize()
+        _dbg('soak done; timed region')
         ms = timed(step_dev, args.steps, world)
+        _dbg(f'timed done: {ms / args.steps:.3f} ms/step; e2e')
         for i in range(3):
             step_e2e(i)
         ms_e2e = timed(step_e2e, args.steps, world)
+    _dbg('e2e done')
     launches_per_step = tr.launches_per_step
     imgs = args.steps * BATCH * world
     value = imgs / (ms / 1e3)
@@ -263,6 +273,7 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     roof = kernel_rooflines(w, pk) if world == 1 else None
+    _dbg('rooflines done; cpu baseline')
     cpu = None
     if world == 1:
         ips, done, threads, dt = cpu_steps(60, 1, budget_s=15.0)
