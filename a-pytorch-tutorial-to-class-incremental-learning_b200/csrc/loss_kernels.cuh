@@ -146,28 +146,27 @@ __global__ void __launch_bounds__(256) kd_rows_kernel(const T* __restrict__ s, i
   }
   RowReduce<TPR>::max2(ma, mb, red);
   if (!live) { ma = 0.f; mb = 0.f; }
-  float sa = 0.f, sb = 0.f;
+  // One exponential per element: the cache is overwritten with e^(x - max); the KL sum is accumulated unnormalised,
+  //   sum_i p_t,i (log p_t,i - log p_s,i) = (sum_i e_b,i (b_i - a_i)) / S_b - log S_b + log S_a     (shifted logits)
+  // with 0 * log 0 := 0 (xlogy semantics of F.kl_div) for underflowed / padded entries.
+  float sa = 0.f, sb = 0.f, acc = 0.f;
 #pragma unroll
   for (int i = 0; i < kRowCache; ++i) {
-    a[i] = (a[i] - ma);                        // shifted logit (<= 0; -inf for padding)
-    b[i] = (b[i] - mb);
-    sa += exp2f(a[i] * kLog2e);
-    sb += exp2f(b[i] * kLog2e);
+    const float as = a[i] - ma, bs = b[i] - mb;  // <= 0; -inf for padding
+    const float ea = exp2f(as * kLog2e), eb = exp2f(bs * kLog2e);
+    sa += ea;
+    sb += eb;
+    acc += (eb > 0.f) ? eb * (bs - as) : 0.f;
+    a[i] = ea;
+    b[i] = eb;
   }
   RowReduce<TPR>::sum2(sa, sb, red);
-  const float lsa_acc = logf(sa), lsb_acc = logf(sb);
+  float dummy = 0.f;
+  RowReduce<TPR>::sum2(acc, dummy, red);
   const float inv_sa = 1.f / sa, inv_sb = 1.f / sb;
-  float kl = 0.f, dummy = 0.f;
+  const float kl = acc * inv_sb - logf(sb) + logf(sa);
 #pragma unroll
-  for (int i = 0; i < kRowCache; ++i) {
-    const float ps = exp2f(a[i] * kLog2e) * inv_sa;
-    const float pt = exp2f(b[i] * kLog2e) * inv_sb;
-    // p_t (log p_t - log p_s), with 0 * log 0 := 0 (xlogy semantics of F.kl_div)
-    const float d = (b[i] - lsb_acc) - (a[i] - lsa_acc);
-    kl += (pt > 0.f) ? pt * d : 0.f;
-    a[i] = (ps - pt) * gscale;                 // gradient, reusing the cache
-  }
-  RowReduce<TPR>::sum2(kl, dummy, red);
+  for (int i = 0; i < kRowCache; ++i) a[i] = (a[i] * inv_sa - b[i] * inv_sb) * gscale;  // gradient, reusing the cache
   if (g != nullptr && live) {
     T* gp = g + static_cast<int64_t>(row) * g_ld;
     if (VEC) {
@@ -194,8 +193,8 @@ __global__ void __launch_bounds__(256) kd_rows_kernel(const T* __restrict__ s, i
     }
   }
   if (live && tid == 0) part[row] = kl;
-  float acc[1];
-  if (finish_rows<1>(part, counter, B, acc)) *loss_out = acc[0] * lscale;
+  float tot[1];
+  if (finish_rows<1>(part, counter, B, tot)) *loss_out = tot[0] * lscale;
 }
 
 // ------------------------------------------------------------------------------------------------ CE + KD
