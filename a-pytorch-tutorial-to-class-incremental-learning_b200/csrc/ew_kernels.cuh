@@ -465,7 +465,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
-    while (atomicAdd(bar, 0u) < gridDim.x) __nanosleep(64);
+    while (atomicAdd(bar, 0u) < gridDim.x) {
+    }
     __threadfence();
     if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
       bar[1] = 0u;
@@ -497,13 +498,21 @@ __global__ void __launch_bounds__(256) weight_align_kernel(T* __restrict__ W, in
     const T* row = W + static_cast<long long>(r) * D;
     float ss = 0.f;
     if (vec) {
-      for (int k = lane * VW; k < D; k += 32 * VW) {
-        const uint4 q = *reinterpret_cast<const uint4*>(row + k);
-        const T* e = reinterpret_cast<const T*>(&q);
+      for (int k0 = lane * VW; k0 < D; k0 += 4 * 32 * VW) {
+        uint4 q[4];
 #pragma unroll
-        for (int i = 0; i < VW; ++i) {
-          const float f = wa_ld<T>(e + i);
-          ss += f * f;
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j * 32 * VW;
+          q[j] = k < D ? __ldcs(reinterpret_cast<const uint4*>(row + k)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T* e = reinterpret_cast<const T*>(&q[j]);
+#pragma unroll
+          for (int i = 0; i < VW; ++i) {
+            const float f = wa_ld<T>(e + i);
+            ss += f * f;
+          }
         }
       }
     } else {

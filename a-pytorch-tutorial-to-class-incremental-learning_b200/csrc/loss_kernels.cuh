@@ -45,7 +45,7 @@ template <> struct Vec4<__nv_bfloat16> {
 
 // Reductions over the TPR threads that own a row (TPR = 32: one warp; TPR = 256: the whole CTA).
 template <int TPR> struct RowReduce {
-  // red: shared scratch of at least 16 floats (TPR == 256 only)
+  // red: shared scratch of 64 floats (TPR > 32 only)
   static __device__ __forceinline__ void max2(float& a, float& b, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -55,11 +55,11 @@ template <int TPR> struct RowReduce {
     if (TPR > 32) {
       const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
       __syncthreads();
-      if (l == 0) { red[w] = a; red[8 + w] = b; }
+      if (l == 0) { red[w] = a; red[32 + w] = b; }
       __syncthreads();
-      a = red[0]; b = red[8];
+      a = red[0]; b = red[32];
 #pragma unroll
-      for (int i = 1; i < TPR / 32; ++i) { a = fmaxf(a, red[i]); b = fmaxf(b, red[8 + i]); }
+      for (int i = 1; i < TPR / 32; ++i) { a = fmaxf(a, red[i]); b = fmaxf(b, red[32 + i]); }
     }
   }
   static __device__ __forceinline__ void sum2(float& a, float& b, float* red) {
@@ -71,11 +71,11 @@ template <int TPR> struct RowReduce {
     if (TPR > 32) {
       const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
       __syncthreads();
-      if (l == 0) { red[w] = a; red[8 + w] = b; }
+      if (l == 0) { red[w] = a; red[32 + w] = b; }
       __syncthreads();
-      a = red[0]; b = red[8];
+      a = red[0]; b = red[32];
 #pragma unroll
-      for (int i = 1; i < TPR / 32; ++i) { a += red[i]; b += red[8 + i]; }
+      for (int i = 1; i < TPR / 32; ++i) { a += red[i]; b += red[32 + i]; }
     }
   }
 };
@@ -84,9 +84,9 @@ template <int TPR> struct RowReduce {
 // part layout: float part[NPARTS][B].  Returns true on exactly one thread of the grid (thread 0 of the last CTA)
 // with acc[] holding the ordered sums; the counter is re-armed for the next launch.
 template <int NPARTS>
-__device__ __forceinline__ bool finish_rows(float* part, unsigned* counter, int B, float (&acc)[NPARTS]) {
+__device__ __forceinline__ bool finish_rows(float* part, unsigned* counter, int B, float (&acc)[NPARTS], bool wrote_part) {
   __shared__ unsigned s_last;
-  __threadfence();
+  if (wrote_part) __threadfence();  // only the threads that published a row partial; the gradient stores need no fence
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
@@ -108,12 +108,12 @@ __device__ __forceinline__ bool finish_rows(float* part, unsigned* counter, int 
 
 // ------------------------------------------------------------------------------------------------ KD
 template <typename T, int TPR, int kRowCache, bool VEC>
-__global__ void __launch_bounds__(256) kd_rows_kernel(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
+__global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
                                                       int64_t t_ld, int B, int C, float invT, float gscale,
                                                       float lscale, float* __restrict__ loss_out, T* __restrict__ g,
                                                       int64_t g_ld, int accumulate, float* part, unsigned* counter) {
-  __shared__ float red[16];
-  constexpr int RPB = 256 / TPR;  // rows per block
+  __shared__ float red[64];
+  constexpr int RPB = TPR >= 256 ? 1 : 256 / TPR;  // rows per block
   const int tid = threadIdx.x % TPR;
   const int row = blockIdx.x * RPB + threadIdx.x / TPR;
   const bool live = row < B;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) kd_rows_kernel(const T* __restrict__ s, i
   }
   if (live && tid == 0) part[row] = kl;
   float tot[1];
-  if (finish_rows<1>(part, counter, B, tot)) *loss_out = tot[0] * lscale;
+  if (finish_rows<1>(part, counter, B, tot, live && tid == 0)) *loss_out = tot[0] * lscale;
 }
 
 // ------------------------------------------------------------------------------------------------ CE + KD
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ tz, int64_t t_ld, int B, int Cs, int Ck, float invT, float kd_gscale,
                       float kd_lscale, float smooth, float* __restrict__ losses, float* __restrict__ dz, int64_t d_ld,
                       float* part, unsigned* counter) {
-  __shared__ float red[16];
+  __shared__ float red[64];
   constexpr int RPB = 256 / TPR;
   const int tid = threadIdx.x % TPR;
   const int row = blockIdx.x * RPB + threadIdx.x / TPR;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256)
     part[2 * B + row] = (amax == y) ? 1.f : 0.f;
   }
   float acc[3];
-  if (finish_rows<3>(part, counter, B, acc)) {
+  if (finish_rows<3>(part, counter, B, acc, live && tid == 0)) {
     const float ce = acc[0] * invB, kd = acc[1] * kd_lscale;
     losses[0] = ce;
     losses[1] = kd;

@@ -765,16 +765,19 @@ int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B,
                    (reinterpret_cast<uintptr_t>(s) % vb == 0) && (reinterpret_cast<uintptr_t>(t) % vb == 0) &&
                    (!g || reinterpret_cast<uintptr_t>(g) % vb == 0);
 #define KD_LAUNCH(TPR, CACHE, VEC)                                                                              \
-  kd_rows_kernel<T, TPR, CACHE, VEC><<<(B + (256 / TPR) - 1) / (256 / TPR), 256, 0, st>>>(                      \
-      sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp, g_ld, accumulate, part, counter)
+  kd_rows_kernel<T, TPR, CACHE, VEC>                                                                            \
+      <<<(TPR >= 256 ? B : (B + (256 / TPR) - 1) / (256 / TPR)), (TPR >= 256 ? TPR : 256), 0, st>>>(            \
+          sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp, g_ld, accumulate, part, counter)
   if (C <= 128) {
     if (vec) KD_LAUNCH(32, 4, true); else KD_LAUNCH(32, 4, false);
   } else if (C <= 1024) {
     if (vec) KD_LAUNCH(32, 32, true); else KD_LAUNCH(32, 32, false);
   } else if (C <= 2048) {
     if (vec) KD_LAUNCH(256, 8, true); else KD_LAUNCH(256, 8, false);
+  } else if (C <= 4096) {
+    if (vec) KD_LAUNCH(512, 8, true); else KD_LAUNCH(512, 8, false);
   } else if (C <= 8192) {
-    if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);
+    if (vec) KD_LAUNCH(1024, 8, true); else KD_LAUNCH(1024, 8, false);
   } else {
     return fail(WACIL_E_SHAPE, "C = %d > 8192 columns is not supported", C);
   }
@@ -832,9 +835,12 @@ extern "C++" {
 namespace {
 template <typename T>
 int wa_launch(void* W, int C_total, int D, int n_new, float* gamma_out, void* ws, cudaStream_t st) {
-  int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weight_align_kernel<T>, 256, 0);
-  if (e != cudaSuccess || occ < 1) return cuda_fail(e, "occupancy(weight_align_kernel)");
+  static int occ = 0;  // per instantiation
+  cudaError_t e = cudaSuccess;
+  if (occ == 0) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weight_align_kernel<T>, 256, 0);
+    if (e != cudaSuccess || occ < 1) { occ = 0; return cuda_fail(e, "occupancy(weight_align_kernel)"); }
+  }
   int grid = (C_total + 7) / 8;
   const int cap = occ * num_sms();
   if (grid > cap) grid = cap;

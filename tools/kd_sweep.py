@@ -64,8 +64,13 @@ def wa_case(C, D, n_new, dtype):
     nb = max(2, min(10, int(300e6 // (C * D * esz)) + 1))
     Ws = [(torch.randn(C, D, device=dev) * 0.1).to(dtype) for _ in range(nb)]
 
+    lib, st = w._lib.lib(), torch.cuda.current_stream().cuda_stream
+    gamma = torch.empty((), device=dev)
+    ws = torch.zeros(lib.wacil_weight_align_workspace_bytes(C), dtype=torch.uint8, device=dev)
+    code = 0 if dtype == torch.float32 else 1
+
     def ours(i):
-        w.ops.weight_align_(Ws[i % nb], n_new)
+        lib.wacil_weight_align(Ws[i % nb].data_ptr(), C, D, n_new, gamma.data_ptr(), code, ws.data_ptr(), st)
 
     def eager(i):  # template.py:156-166
         W = Ws[i % nb]
