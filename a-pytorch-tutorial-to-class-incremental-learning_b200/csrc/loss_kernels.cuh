@@ -107,6 +107,16 @@ __device__ __forceinline__ bool finish_rows(float* part, unsigned* counter, int 
 }
 
 // ------------------------------------------------------------------------------------------------ KD
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Row arithmetic in the log2 domain: u = x * (log2(e) / T), so e^(x/T - max) = 2^(u - max_u) is one FADD + one MUFU;
+// padding lanes hold a large negative FINITE sentinel (2^sentinel = 0 and no inf - inf), which removes every select.
+constexpr float kRowPad = -1.0e30f;
+
 template <typename T, int TPR, int kRowCache, bool VEC>
 __global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
                                                       int64_t t_ld, int B, int C, float invT, float gscale,
@@ -119,18 +129,21 @@ __global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T*
   const bool live = row < B;
   const T* sp = s + static_cast<int64_t>(live ? row : 0) * s_ld;
   const T* tp = t + static_cast<int64_t>(live ? row : 0) * t_ld;
+  const float k2 = invT * kLog2e;
 
   float a[kRowCache], b[kRowCache];
-  float ma = -INFINITY, mb = -INFINITY;
+  float ma = kRowPad, mb = kRowPad;
   if (VEC) {
 #pragma unroll
     for (int i = 0; i < kRowCache / 4; ++i) {
       const int col = (i * TPR + tid) * 4;
-      float va[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, vb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (live && col < C) { Vec4<T>::load(sp + col, va); Vec4<T>::load(tp + col, vb); }
+      float va[4], vb[4];
+      const bool in = live && col < C;
+      if (in) { Vec4<T>::load(sp + col, va); Vec4<T>::load(tp + col, vb); }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        a[i * 4 + j] = va[j] * invT; b[i * 4 + j] = vb[j] * invT;
+        a[i * 4 + j] = in ? va[j] * k2 : kRowPad;
+        b[i * 4 + j] = in ? vb[j] * k2 : kRowPad;
         ma = fmaxf(ma, a[i * 4 + j]); mb = fmaxf(mb, b[i * 4 + j]);
       }
     }
@@ -139,24 +152,23 @@ __global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T*
     for (int i = 0; i < kRowCache; ++i) {
       const int col = i * TPR + tid;
       const bool in = live && col < C;
-      a[i] = in ? Vec4<T>::ld1(sp + col) * invT : -INFINITY;
-      b[i] = in ? Vec4<T>::ld1(tp + col) * invT : -INFINITY;
+      a[i] = in ? Vec4<T>::ld1(sp + col) * k2 : kRowPad;
+      b[i] = in ? Vec4<T>::ld1(tp + col) * k2 : kRowPad;
       ma = fmaxf(ma, a[i]); mb = fmaxf(mb, b[i]);
     }
   }
   RowReduce<TPR>::max2(ma, mb, red);
-  if (!live) { ma = 0.f; mb = 0.f; }
-  // One exponential per element: the cache is overwritten with e^(x - max); the KL sum is accumulated unnormalised,
-  //   sum_i p_t,i (log p_t,i - log p_s,i) = (sum_i e_b,i (b_i - a_i)) / S_b - log S_b + log S_a     (shifted logits)
-  // with 0 * log 0 := 0 (xlogy semantics of F.kl_div) for underflowed / padded entries.
+  // One exponential per element: the cache is overwritten with 2^(u - max); the KL sum is accumulated unnormalised,
+  //   sum_i p_t,i (log p_t,i - log p_s,i) = ln2 * (sum_i e_b,i (db_i - da_i)) / S_b - ln S_b + ln S_a
+  // (da, db = shifted log2-domain logits); entries whose e_b underflows contribute 0, the xlogy(0, .) = 0 of F.kl_div.
   float sa = 0.f, sb = 0.f, acc = 0.f;
 #pragma unroll
   for (int i = 0; i < kRowCache; ++i) {
-    const float as = a[i] - ma, bs = b[i] - mb;  // <= 0; -inf for padding
-    const float ea = exp2f(as * kLog2e), eb = exp2f(bs * kLog2e);
+    const float da = a[i] - ma, db = b[i] - mb;
+    const float ea = ex2_approx(da), eb = ex2_approx(db);
     sa += ea;
     sb += eb;
-    acc += (eb > 0.f) ? eb * (bs - as) : 0.f;
+    acc = fmaf(eb, db - da, acc);
     a[i] = ea;
     b[i] = eb;
   }
@@ -164,9 +176,10 @@ __global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T*
   float dummy = 0.f;
   RowReduce<TPR>::sum2(acc, dummy, red);
   const float inv_sa = 1.f / sa, inv_sb = 1.f / sb;
-  const float kl = acc * inv_sb - logf(sb) + logf(sa);
+  const float kl = 0.6931471805599453f * acc * inv_sb - logf(sb) + logf(sa);
+  const float ca = inv_sa * gscale, cb = inv_sb * gscale;
 #pragma unroll
-  for (int i = 0; i < kRowCache; ++i) a[i] = (a[i] * inv_sa - b[i] * inv_sb) * gscale;  // gradient, reusing the cache
+  for (int i = 0; i < kRowCache; ++i) a[i] = fmaf(a[i], ca, -(b[i] * cb));  // gradient, reusing the cache
   if (g != nullptr && live) {
     T* gp = g + static_cast<int64_t>(row) * g_ld;
     if (VEC) {
