@@ -55,6 +55,8 @@ SIGNATURES = {
     "wacil_net_set_side_stream": (I, [P, P]),
     "wacil_net_tensor": (I, [P, I, I, C.POINTER(P), C.POINTER(Z)]),
     "wacil_conv3x3_fprop": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "wacil_conv3x3_bn_relu_workspace_bytes": (Z, [I]),
+    "wacil_conv3x3_bn_relu": (I, [P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P]),
     "wacil_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),
 }
 

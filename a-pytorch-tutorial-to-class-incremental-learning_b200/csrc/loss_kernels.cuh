@@ -118,7 +118,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 constexpr float kRowPad = -1.0e30f;
 
 template <typename T, int TPR, int kRowCache, bool VEC>
-__global__ void __launch_bounds__(TPR > 256 ? TPR : 256) kd_rows_kernel(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
+__global__ void __launch_bounds__(TPR > 256 ? TPR : 256, TPR > 256 ? 1 : 3) kd_rows_kernel(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
                                                       int64_t t_ld, int B, int C, float invT, float gscale,
                                                       float lscale, float* __restrict__ loss_out, T* __restrict__ g,
                                                       int64_t g_ld, int accumulate, float* part, unsigned* counter) {

@@ -909,6 +909,40 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
   return launch_conv(c, S(stream));
 }
 
+size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout) { return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8; }
+
+int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
+                          int res_mode, void* y, void* a, float* mean_rstd, float* running_mean, float* running_var,
+                          int N, int H, int W, int cin, int cout, int stride, void* workspace, void* stream) {
+  if (!x || !w || !gamma || !beta || !y || !a || !mean_rstd || !running_mean || !running_var || !workspace)
+    return fail(WACIL_E_NULL, "NULL argument");
+  if ((cin != 16 && cin != 32 && cin != 64) || (cout != 16 && cout != 32 && cout != 64) || (stride != 1 && stride != 2) ||
+      H != W || (H != 32 && H != 16 && H != 8) || (H / stride) < 8 || N < 1 || res_mode < 0 || res_mode > 2 ||
+      (res_mode != 0 && !res))
+    return fail(WACIL_E_SHAPE, "conv3x3_bn_relu N=%d H=%d cin=%d cout=%d stride=%d res_mode=%d", N, H, cin, cout, stride,
+                res_mode);
+  unsigned* gbar = static_cast<unsigned*>(workspace);
+  float* stats = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 64);
+  cudaError_t ce = cudaMemsetAsync(stats, 0, static_cast<size_t>(cout) * 8, S(stream));
+  if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
+  ConvLaunch c;
+  int e = setup_conv(c, x, N, H, W, cin, cout, stride, 9, w, EPI_STATS);
+  if (e) return e;
+  if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) return e;
+  c.p.out = static_cast<__nv_bfloat16*>(y);
+  c.p.act_out = static_cast<__nv_bfloat16*>(a);
+  c.p.stats = stats;
+  c.p.saved = mean_rstd;
+  c.p.gamma = gamma;
+  c.p.beta = beta;
+  c.p.running_mean = running_mean;
+  c.p.running_var = running_var;
+  c.p.res = res_mode ? static_cast<const __nv_bfloat16*>(res) : nullptr;
+  c.p.res_stride = res_mode == 2 ? 2 : 1;
+  c.p.res_c = res_mode == 2 ? cout / 2 : cout;
+  return launch_conv(c, S(stream));
+}
+
 int wacil_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
                         void* stream) {
   if (!x || !dy || !dw) return fail(WACIL_E_NULL, "NULL argument");

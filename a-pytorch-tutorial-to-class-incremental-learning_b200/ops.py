@@ -135,6 +135,23 @@ def conv3x3_fprop(x, w, stride=1, want_stats=False):
     return (y, stats) if want_stats else y
 
 
+def conv3x3_bn_relu(x, w, gamma, beta, running_mean, running_var, res=None, res_mode=0, stride=1):
+    """One fused launch: y = conv3x3(x, w); a = relu(batchnorm_train(y) + shortcut).  x [N,H,W,cin] bf16, w [9,cout,cin]
+    bf16, gamma/beta/running_* fp32 [cout] (running statistics updated in place).  Returns (y, a, mean_rstd[2,cout])."""
+    _need_cuda(x, w, gamma, beta, running_mean, running_var, res)
+    N, H, W_, cin = x.shape
+    cout = w.shape[1]
+    y = torch.empty((N, H // stride, W_ // stride, cout), dtype=torch.bfloat16, device=x.device)
+    a = torch.empty_like(y)
+    saved = torch.empty((2, cout), dtype=torch.float32, device=x.device)
+    ws = _workspace("convbn", lib().wacil_conv3x3_bn_relu_workspace_bytes(cout), x.device)
+    check(lib().wacil_conv3x3_bn_relu(x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                      res.data_ptr() if res is not None else None, int(res_mode), y.data_ptr(),
+                                      a.data_ptr(), saved.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
+                                      N, H, W_, cin, cout, stride, ws.data_ptr(), _stream()), "wacil_conv3x3_bn_relu")
+    return y, a, saved
+
+
 def conv3x3_wgrad(x, dy, stride=1):
     """x [N,H,W,cin] bf16, dy [N,H/s,W/s,cout] bf16 -> dW [9,cin,cout] fp32."""
     _need_cuda(x, dy)

@@ -212,3 +212,45 @@ def test_conv3x3_fprop_and_wgrad_vs_torch(w, N, H, cin, cout, stride):
     dw = w.ops.conv3x3_wgrad(x.cuda(), dy.cuda(), stride)  # [9][cin][cout]
     dw_ref = w_oihw.grad.permute(2, 3, 1, 0).reshape(9, cin, cout)
     assert (dw.cpu() - dw_ref).abs().max().item() <= 2e-3 * dw_ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("N,H,cin,cout,stride,res_mode", [(16, 32, 16, 16, 1, 1), (128, 32, 16, 16, 1, 0), (16, 32, 16, 32, 2, 0),
+                                                         (16, 16, 32, 32, 1, 2), (32, 8, 64, 64, 1, 1), (7, 8, 64, 64, 1, 1)])
+def test_fused_conv_bn_relu_vs_torch(w, N, H, cin, cout, stride, res_mode):
+    """The fused layer kernel (conv -> batch statistics -> grid barrier -> BN + shortcut + ReLU) against CPU math on the same
+    bf16 operands: y within 1 bf16 ulp, statistics 1e-4, a within 1 ulp of BN applied to the kernel's own y."""
+    gen = torch.Generator().manual_seed(N * 7 + H + cin + cout + res_mode)
+    x = torch.randn(N, H, H, cin, generator=gen).bfloat16()
+    wt = (torch.randn(9, cout, cin, generator=gen) * 0.15).bfloat16()
+    gamma = torch.rand(cout, generator=gen) + 0.5
+    beta = torch.randn(cout, generator=gen) * 0.2
+    rm, rv = torch.randn(cout, generator=gen) * 0.1, torch.rand(cout, generator=gen) + 0.5
+    Ho = H // stride
+    res = None
+    if res_mode == 1:
+        res = torch.randn(N, Ho, Ho, cout, generator=gen).bfloat16()
+    elif res_mode == 2:
+        res = torch.randn(N, 2 * Ho, 2 * Ho, cout // 2, generator=gen).bfloat16()
+    rm_d, rv_d = rm.cuda(), rv.cuda()
+    y, a, saved = w.ops.conv3x3_bn_relu(x.cuda(), wt.cuda(), gamma.cuda(), beta.cuda(), rm_d, rv_d,
+                                        res.cuda() if res is not None else None, res_mode, stride)
+    w_oihw = wt.float().view(3, 3, cout, cin).permute(2, 3, 0, 1).contiguous()
+    yref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w_oihw, stride=stride, padding=1)
+    yg = y.float().cpu().permute(0, 3, 1, 2)
+    assert ((yg - yref).abs() <= yref.abs().clamp_min(1e-3) * 2.0 ** -7).all()
+    m = N * Ho * Ho
+    mean, var = yg.mean(dim=(0, 2, 3)), (yg * yg).mean(dim=(0, 2, 3)) - yg.mean(dim=(0, 2, 3)) ** 2
+    sv = saved.cpu()
+    assert (sv[0] - mean).abs().max() <= 1e-4 * (mean.abs().max() + var.sqrt().max())
+    assert (sv[1] - torch.rsqrt(var + 1e-5)).abs().max() <= 1e-4 * sv[1].abs().max()
+    z = (yg - sv[0][None, :, None, None]) * sv[1][None, :, None, None] * gamma[None, :, None, None] + beta[None, :, None, None]
+    if res_mode == 1:
+        z = z + res.float().permute(0, 3, 1, 2)
+    elif res_mode == 2:
+        r = res.float().permute(0, 3, 1, 2)[:, :, ::2, ::2]
+        z = z + torch.cat([r, torch.zeros_like(r)], dim=1)
+    aref = torch.relu(z)
+    ag = a.float().cpu().permute(0, 3, 1, 2)
+    assert ((ag - aref).abs() <= aref.abs().clamp_min(1e-2) * 2.0 ** -7).all()
+    np.testing.assert_allclose(rm_d.cpu().numpy(), (0.9 * rm + 0.1 * mean).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rv_d.cpu().numpy(), (0.9 * rv + 0.1 * var * m / (m - 1)).numpy(), rtol=1e-4, atol=1e-6)
