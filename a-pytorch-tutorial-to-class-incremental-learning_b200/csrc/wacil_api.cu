@@ -777,7 +777,12 @@ int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B,
   } else if (C <= 4096) {
     if (vec) KD_LAUNCH(512, 8, true); else KD_LAUNCH(512, 8, false);
   } else if (C <= 8192) {
-    if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);  // 1024 x 8 measured 2x slower
+    static int math = -1;
+    if (math < 0) { const char* ev = getenv("WACIL_KD_MATH"); math = (ev && ev[0] == '0') ? 0 : 1; }
+    if (math == 0 && vec) {
+      kd_rows_kernel_v2<T, 256, 32, true><<<B, 256, 0, st>>>(sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp,
+                                                             g_ld, accumulate, part, counter);
+    } else if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);  // 1024 x 8 measured 2x slower
   } else {
     return fail(WACIL_E_SHAPE, "C = %d > 8192 columns is not supported", C);
   }
