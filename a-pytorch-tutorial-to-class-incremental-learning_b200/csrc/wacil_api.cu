@@ -777,8 +777,11 @@ int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B,
   } else if (C <= 4096) {
     if (vec) KD_LAUNCH(512, 8, true); else KD_LAUNCH(512, 8, false);
   } else if (C <= 8192) {
-    static int math = -1;
-    if (math < 0) { const char* ev = getenv("WACIL_KD_MATH"); math = (ev && ev[0] == '0') ? 0 : 1; }
+    // A/B on B200 at B=1024, C=8192 (profiles/r01_kd_variants.log): natural-domain exp2f variant 24.2 us fp32 /
+    // 24.7 us bf16; log2-domain ex2.approx variant 32.4 us fp32 / 21.3 us bf16 -> pick per dtype (env override).
+    static int math_env = -2;
+    if (math_env == -2) { const char* ev = getenv("WACIL_KD_MATH"); math_env = ev ? (ev[0] == '0' ? 0 : 1) : -1; }
+    const int math = math_env >= 0 ? math_env : (sizeof(T) == 4 ? 0 : 1);
     if (math == 0 && vec) {
       kd_rows_kernel_v2<T, 256, 32, true><<<B, 256, 0, st>>>(sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp,
                                                              g_ld, accumulate, part, counter);
