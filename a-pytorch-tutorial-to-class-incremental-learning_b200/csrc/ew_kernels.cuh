@@ -405,28 +405,39 @@ __global__ void __launch_bounds__(64) pool_fc_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-// blocks [0, C_seen): dW[j][:] and db[j];  blocks [C_seen, C_seen + B): dfeats[b][:].  64 threads, no atomics.
-__global__ void __launch_bounds__(64) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ feats,
-                                                    const float* __restrict__ W, int B, int C_seen, int D,
-                                                    float* __restrict__ dW, float* __restrict__ db,
-                                                    float* __restrict__ dfeats) {
-  const int c = threadIdx.x;
+// blocks [0, C_seen): dW[j][:] and db[j];  blocks [C_seen, C_seen + B): dfeats[b][:].  256 threads = 4 groups of 64
+// (one per feature column) that split the reduction 4 ways; fixed-order combine, no atomics.
+__global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ feats,
+                                                     const float* __restrict__ W, int B, int C_seen, int D,
+                                                     float* __restrict__ dW, float* __restrict__ db,
+                                                     float* __restrict__ dfeats) {
+  __shared__ float s_acc[4][64], s_accb[4];
+  const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
   if (static_cast<int>(blockIdx.x) < C_seen) {
     const int j = blockIdx.x;
     float acc = 0.f, accb = 0.f;
-    for (int n = 0; n < B; ++n) {
+#pragma unroll 8
+    for (int n = grp; n < B; n += 4) {
       const float g = __ldg(dlogits + static_cast<long long>(n) * C_seen + j);
-      acc += g * __ldg(feats + static_cast<long long>(n) * D + c);
+      acc = fmaf(g, __ldg(feats + static_cast<long long>(n) * D + c), acc);
       accb += g;
     }
-    dW[static_cast<long long>(j) * D + c] = acc;
-    if (c == 0) db[j] = accb;
+    s_acc[grp][c] = acc;
+    if (c == 0) s_accb[grp] = accb;
+    __syncthreads();
+    if (grp == 0) {
+      dW[static_cast<long long>(j) * D + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
+      if (c == 0) db[j] = (s_accb[0] + s_accb[1]) + (s_accb[2] + s_accb[3]);
+    }
   } else {
     const int n = blockIdx.x - C_seen;
     float acc = 0.f;
-    for (int j = 0; j < C_seen; ++j)
-      acc += __ldg(dlogits + static_cast<long long>(n) * C_seen + j) * __ldg(W + static_cast<long long>(j) * D + c);
-    dfeats[static_cast<long long>(n) * D + c] = acc;
+#pragma unroll 4
+    for (int j = grp; j < C_seen; j += 4)
+      acc = fmaf(__ldg(dlogits + static_cast<long long>(n) * C_seen + j), __ldg(W + static_cast<long long>(j) * D + c), acc);
+    s_acc[grp][c] = acc;
+    __syncthreads();
+    if (grp == 0) dfeats[static_cast<long long>(n) * D + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
   }
 }
 

@@ -637,7 +637,7 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
   if (n->mode == WACIL_NET_TRAIN) {
     cudaError_t ce = cudaMemsetAsync(n->ws + n->off.stats, 0, n->off.stat_elems * 4, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
-    dim3 grid(8, static_cast<unsigned>(nl));
+    dim3 grid(36, static_cast<unsigned>(nl));  // <= 4 elements per thread for the largest (64x64x9) layers
     cast_weights_kernel<<<grid, 256, 0, st>>>(n->params, n->at<__nv_bfloat16>(n->off.wbuf),
                                               n->at<LayerDesc>(n->off.table));
     WACIL_LAUNCH_CHECK("cast_weights_kernel");
@@ -676,7 +676,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
   float* dfeats = n->at<float>(n->off.dfeats);
-  fc_bwd_kernel<<<C_seen + n->batch, 64, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
+  fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
                                                   C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
                                                   n->grads + n->lay.fc_bias_off, dfeats);
   WACIL_LAUNCH_CHECK("fc_bwd_kernel");
