@@ -130,6 +130,32 @@ def cpu_steps(n_steps, warmup, budget_s=None):
     return done * BATCH / dt, done, threads, dt
 
 
+def gpu_eager_steps(n_steps, autocast):
+    """the reference's step sequence as PyTorch eager on this GPU (cuDNN/cuBLAS/ATen), through the oracle
+    port of template.py:255-271 with CUDA tensors — the incumbent GPU path next to which the native kernels are read.
+    fp32 like the reference, or under bf16 autocast.  Returns img/s."""
+    import wa_oracle as wo
+    sd, tsd = make_states()
+    sd = {k: v.cuda() for k, v in sd.items()}
+    tsd = {k: v.cuda() for k, v in tsd.items()}
+    x, y = synthetic_pool(4, 1234)
+    x, y = x.cuda(), y.cuda()
+    bufs = {}
+
+    def step(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            wo.train_step(sd, tsd, x[i % 4], y[i % 4], DEPTH, KNOWN, 0.05, bufs)
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        step(i)
+    torch.cuda.synchronize()
+    return n_steps * BATCH / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -325,6 +351,13 @@ def run_ours(args, rank, local_rank, world):
         line["kd_kernel"] = roof["kd"]
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if world == 1:
+        try:
+            line["gpu_eager_baseline"] = {"fp32_img_s": gpu_eager_steps(20, False), "bf16_autocast_img_s": gpu_eager_steps(20, True),
+                                          "what": "the reference's step (oracle port of template.py:255-271) as PyTorch eager on "
+                                                  "this B200: cuDNN/cuBLAS/ATen kernels, no CUDA graph; 20 steps, wall clock"}
+        except Exception as ex:  # a baseline must never take the bench line down
+            line["gpu_eager_baseline"] = {"error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
 
 
