@@ -3,9 +3,8 @@
 //   cast_weights      fp32 master weights [9][cin][cout] -> bf16 fprop ([9][cout][cin]) and dgrad
 //                     ([9 flipped][cin][cout]) operand copies, all layers in one launch
 //   fold_bn           eval-mode BatchNorm folded into bf16 weights + fp32 bias (teacher / feature extraction)
-//   bn_apply_fwd      train-mode BatchNorm normalise + affine (+ residual, option-A shortcut) + ReLU,
-//                     running-statistics update                                            (resnet.py:43-53,15-17)
-//   bn_bwd_reduce / bn_bwd_apply   ReLU mask + BatchNorm backward (+ shortcut gradient gather)
+//   bn_bwd_reduce / bn_bwd_apply   stand-alone ReLU mask + BatchNorm backward (last layer; the other layers' BN forward
+//                     and backward are fused into conv_gemm_kernel, tc_conv.cuh)
 //   pool_fc_fwd / fc_bwd           8x8 average pool + classifier heads                      (resnet.py:114-115,
 //                                                                                          template.py:99-101)
 //   sgd_step          momentum SGD with weight decay on the flat arena                      (template.py:246-247,271)
@@ -89,89 +88,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ params, const float* __
     if (e < L.cout) {
       const float s2 = g[e] * rsqrtf(rv[e] + eps);
       bias[L.bias_off + e] = b[e] - rm[e] * s2;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ BN forward
-struct BnApplyParams {
-  const __nv_bfloat16* y;    // raw conv output [pix][C]
-  __nv_bfloat16* out;        // [pix][C]
-  const __nv_bfloat16* res;  // residual source or nullptr
-  int res_mode;              // 0 none, 1 same shape, 2 option-A shortcut: res is [N][2Ho][2Wo][C/2]
-  const float* stats;        // [2C] sum, sumsq over the batch
-  const float* gamma;
-  const float* beta;
-  float* running_mean;
-  float* running_var;
-  float* saved;              // [2C] mean, rstd (for the backward)
-  int C, Ho, Wo;
-  long long num_pixels;
-  float eps, momentum;
-};
-
-__global__ void __launch_bounds__(256) bn_apply_fwd_kernel(const BnApplyParams p) {
-  __shared__ float s_scale[64], s_shift[64];
-  const float cnt = static_cast<float>(p.num_pixels);
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float mean = p.stats[c] / cnt;
-    float var = p.stats[p.C + c] / cnt - mean * mean;
-    var = fmaxf(var, 0.f);
-    const float rstd = rsqrtf(var + p.eps);
-    const float sc = p.gamma[c] * rstd;
-    s_scale[c] = sc;
-    s_shift[c] = p.beta[c] - mean * sc;
-    if (blockIdx.x == 0) {
-      p.saved[c] = mean;
-      p.saved[p.C + c] = rstd;
-      p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (cnt / (cnt - 1.f));
-    }
-  }
-  __syncthreads();
-  // Each thread owns one 8-channel group (grid stride is a multiple of C/8) and streams kU vectors per pass with
-  // all loads issued before the first use.
-  constexpr int kU = 4;
-  const int cv = p.C / 8;
-  const long long total = p.num_pixels * cv;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const int c0 = static_cast<int>(v0 % cv) * 8;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { sc[i] = s_scale[c0 + i]; sh[i] = s_shift[c0 + i]; }
-  const bool res_a = p.res_mode == 2 && c0 < p.C / 2;
-  for (long long vb = v0; vb < total; vb += stride * kU) {
-    uint4 qy[kU], qr[kU];
-    bool ok[kU];
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      const long long v = vb + j * stride;
-      ok[j] = v < total;
-      qr[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[j]) {
-        qy[j] = __ldg(reinterpret_cast<const uint4*>(p.y) + v);
-        if (p.res_mode == 1) {
-          qr[j] = __ldg(reinterpret_cast<const uint4*>(p.res) + v);
-        } else if (res_a) {
-          const long long pix = v / cv;
-          const int w = static_cast<int>(pix % p.Wo);
-          const int h = static_cast<int>((pix / p.Wo) % p.Ho);
-          const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-          const long long rp = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * (p.C / 2) + c0;
-          qr[j] = __ldg(reinterpret_cast<const uint4*>(p.res + rp));
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      if (!ok[j]) continue;
-      float f[8], r[8];
-      bf16x8_to_float(qy[j], f);
-      bf16x8_to_float(qr[j], r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i] * sc[i] + sh[i] + r[i], 0.f);
-      reinterpret_cast<uint4*>(p.out)[vb + j * stride] = float_to_bf16x8(f);
     }
   }
 }
