@@ -81,23 +81,28 @@ struct ConvGemmParams {
 __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (tid128 == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // arrive with release semantics (cumulative over the partner threads' writes ordered by the bar.sync above),
+    // then poll with acquire loads: two L2 round trips instead of fence + atomic + atomic polling
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     const long long t0 = clock64();
-    while (atomicAdd(bar, 0u) < gridDim.x) {
-      if (clock64() - t0 > 4000000000LL) {
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (seen < gridDim.x && clock64() - t0 > 4000000000LL) {
         printf("wacil: grid barrier timeout (block %d)\n", blockIdx.x);
         __trap();
       }
-    }
-    __threadfence();
+    } while (seen < gridDim.x);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid128 == 0) {
+    // self-reset, off the critical path: the last CTA to check out knows every CTA has left the polling loop
     if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
       bar[1] = 0u;
       __threadfence();
       bar[0] = 0u;
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 #define WACIL_STAMP(slot)                                                        \
