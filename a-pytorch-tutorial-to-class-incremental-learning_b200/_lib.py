@@ -41,6 +41,7 @@ SIGNATURES = {
     "wacil_weight_align_workspace_bytes": (Z, [I]),
     "wacil_weight_align": (I, [P, I, I, I, P, I, P, P]),
     "wacil_sgd_step": (I, [P, P, P, L, P, F, F, F, P]),
+    "wacil_allreduce_sgd": (I, [P, P, P, P, I, I, L, P, F, F, P, P]),
     "wacil_herd_workspace_bytes": (Z, [L, I]),
     "wacil_herd_barycenter": (I, [P, L, P, I, I, I, P, P, P, P]),
     "wacil_net_layout": (I, [I, I, C.POINTER(NetLayout)]),

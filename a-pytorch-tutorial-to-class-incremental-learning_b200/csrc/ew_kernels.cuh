@@ -385,6 +385,98 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused all-reduce + SGD
+// DDP gradient mean (template.py:243-244,270) + SGD (template.py:271) in ONE kernel over NVLink peer memory:
+// every rank reads all ranks' gradient arenas (peer-mapped, "symmetric" allocations) in rank order — the sum is bit-
+// identical on every rank, so replicas stay in lock step without a broadcast — and applies the update to its own
+// parameters.  Cross-GPU ordering uses epoch-stamped flags in a peer-writable pad:
+//   pad[r]          <- E+1 written by rank r when ITS gradients are complete ("ready")
+//   pad[kMaxRanks+r]<- E+1 written by rank r when it has finished READING ("done": its peers may overwrite their grads)
+// The epoch E lives in device memory and is advanced by the last block, so a captured graph can be replayed.
+constexpr int kMaxRanks = 16;
+struct AllreduceSgdParams {
+  const float* grads[kMaxRanks];  // peer-mapped gradient arenas, index = rank
+  unsigned* pads[kMaxRanks];      // peer-mapped flag pads, index = rank (2 * kMaxRanks words each)
+  int world, rank;
+  float* p;
+  float* v;
+  long long n;
+  const float* lr_dev;
+  float mom, wd;
+  unsigned* epoch;       // [0] epoch, [1] blocks-done counter (local device memory, zero initially)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned val) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(val) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_flags(const unsigned* pad, int world, unsigned target, const char* what) {
+  const long long t0 = clock64();
+  for (int r = 0; r < world; ++r) {
+    while (static_cast<int>(ld_acquire_sys(pad + r) - target) < 0) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a missing peer must trap, not hang the GPU
+        printf("wacil: allreduce_sgd timeout waiting for rank %d (%s)\n", r, what);
+        __trap();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) allreduce_sgd_kernel(const AllreduceSgdParams q) {
+  __shared__ unsigned s_epoch, s_last;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile unsigned*>(q.epoch);
+  __syncthreads();
+  const unsigned target = s_epoch + 1u;
+  // my gradients were completed by earlier kernels of this stream: announce them to every rank (block 0 only)
+  if (blockIdx.x == 0 && threadIdx.x < q.world) {
+    __threadfence_system();
+    st_release_sys(q.pads[threadIdx.x] + q.rank, target);
+  }
+  if (threadIdx.x == 0) wait_flags(q.pads[q.rank], q.world, target, "ready");
+  __syncthreads();
+  const float lr = __ldg(q.lr_dev);
+  const float gscale = 1.f / static_cast<float>(q.world);
+  const long long n4 = q.n / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < q.world; ++r) {
+      const float4 t = __ldcv(reinterpret_cast<const float4*>(q.grads[r]) + i);  // peer read, never from a stale L1 line
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    float4 pp = reinterpret_cast<float4*>(q.p)[i];
+    float4 vv = reinterpret_cast<float4*>(q.v)[i];
+    vv.x = q.mom * vv.x + (g.x * gscale + q.wd * pp.x); pp.x -= lr * vv.x;
+    vv.y = q.mom * vv.y + (g.y * gscale + q.wd * pp.y); pp.y -= lr * vv.y;
+    vv.z = q.mom * vv.z + (g.z * gscale + q.wd * pp.z); pp.z -= lr * vv.z;
+    vv.w = q.mom * vv.w + (g.w * gscale + q.wd * pp.w); pp.w -= lr * vv.w;
+    reinterpret_cast<float4*>(q.p)[i] = pp;
+    reinterpret_cast<float4*>(q.v)[i] = vv;
+  }
+  // n is a multiple of 4 by construction of the arena layout (wacil_net_layout)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(q.epoch + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last block: every block of this rank has finished reading -> tell the peers, wait until they have finished
+  // reading MY gradients (the next backward overwrites them), then open the next epoch
+  if (threadIdx.x < q.world) st_release_sys(q.pads[threadIdx.x] + kMaxRanks + q.rank, target);
+  if (threadIdx.x == 0) {
+    wait_flags(q.pads[q.rank] + kMaxRanks, q.world, target, "done");
+    q.epoch[1] = 0u;
+    __threadfence();
+    q.epoch[0] = target;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight align
 // Cooperative launch (all CTAs co-resident).  bar[0], bar[1]: grid barrier counters, left at zero.
 __device__ __forceinline__ void grid_barrier(unsigned* bar) {

@@ -886,6 +886,27 @@ int wacil_sgd_step(float* p, const float* g, float* v, int64_t n, const float* l
   return 0;
 }
 
+int wacil_allreduce_sgd(float* p, float* v, const void* const* grad_ptrs, void* const* pad_ptrs, int world, int rank,
+                        int64_t n, const float* lr_dev, float momentum, float weight_decay, void* epoch_ws, void* stream) {
+  if (!p || !v || !grad_ptrs || !pad_ptrs || !lr_dev || !epoch_ws) return fail(WACIL_E_NULL, "NULL argument");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(WACIL_E_SHAPE, "world=%d rank=%d", world, rank);
+  if (n <= 0 || (n & 3)) return fail(WACIL_E_SHAPE, "n=%lld must be a positive multiple of 4", static_cast<long long>(n));
+  AllreduceSgdParams q{};
+  for (int r = 0; r < world; ++r) {
+    if (!grad_ptrs[r] || !pad_ptrs[r]) return fail(WACIL_E_NULL, "peer pointer %d is NULL", r);
+    if (reinterpret_cast<uintptr_t>(grad_ptrs[r]) & 15) return fail(WACIL_E_ALIGN, "peer gradient pointer %d", r);
+    q.grads[r] = static_cast<const float*>(grad_ptrs[r]);
+    q.pads[r] = static_cast<unsigned*>(pad_ptrs[r]);
+  }
+  q.world = world; q.rank = rank; q.p = p; q.v = v; q.n = n; q.lr_dev = lr_dev; q.mom = momentum; q.wd = weight_decay;
+  q.epoch = static_cast<unsigned*>(epoch_ws);
+  int grid = ew_grid(n / 4);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  allreduce_sgd_kernel<<<grid, 256, 0, S(stream)>>>(q);
+  WACIL_LAUNCH_CHECK("allreduce_sgd_kernel");
+  return 0;
+}
+
 size_t wacil_herd_workspace_bytes(int64_t n, int D) {
   if (n <= 0 || D <= 0) return 0;
   return align_up(static_cast<size_t>(n) * D * 4, 256) + static_cast<size_t>(n) * 4;

@@ -106,6 +106,15 @@ def sgd_step_(p, g, v, lr_dev, momentum=0.9, weight_decay=5e-4, grad_scale=1.0):
                                float(weight_decay), float(grad_scale), _stream()), "wacil_sgd_step")
 
 
+def allreduce_sgd_(p, v, peer_grad_ptrs, peer_pad_ptrs, world, rank, lr_dev, epoch_ws, momentum=0.9, weight_decay=5e-4):
+    """Fused DDP mean + SGD over NVLink peer memory (wacil_allreduce_sgd).  peer_*_ptrs: ctypes arrays of `world` device
+    pointers (symmetric-memory / IPC mappings of every rank's gradient arena and flag pad)."""
+    _need_cuda(p, v, lr_dev, epoch_ws)
+    check(lib().wacil_allreduce_sgd(p.data_ptr(), v.data_ptr(), peer_grad_ptrs, peer_pad_ptrs, int(world), int(rank), p.numel(),
+                                    lr_dev.data_ptr(), float(momentum), float(weight_decay), epoch_ws.data_ptr(), _stream()),
+          "wacil_allreduce_sgd")
+
+
 def herd_barycenter(features, class_offsets, quota):
     """features [n,D] fp32 grouped by class; class_offsets int32 [n_classes+1].  Returns (idx [n_classes,quota]
     int32 row-local, counts [n_classes] int32)."""

@@ -165,7 +165,8 @@ class TaskTrainer:
     schedule, template.py:246-249)."""
 
     def __init__(self, model: CilModel, teacher, known_classes, lr=0.1, momentum=0.9, weight_decay=5e-4,
-                 lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None, overlap=True):
+                 lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None, overlap=True,
+                 fused_allreduce=True):
         if not model.arena.is_cuda:
             raise _lib.WacilError("TaskTrainer needs the model on a CUDA device (no CPU path)")
         self.model, self.teacher = model, teacher
@@ -180,6 +181,9 @@ class TaskTrainer:
         self.overlap = overlap
         self.side_t = torch.cuda.Stream(device=self.device) if overlap else None
         self.side_w = torch.cuda.Stream(device=self.device) if overlap else None
+        self.peer = None
+        if world_size > 1 and fused_allreduce:
+            self.peer = self._setup_peer_memory(process_group)
         self.mom = torch.zeros_like(model._arena.params)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
         self.acc = torch.zeros(4, dtype=torch.float32, device=self.device)  # running sums of [ce, kd, loss, top1]
@@ -188,6 +192,39 @@ class TaskTrainer:
         self.launches_per_step = 0
         if teacher is not None and teacher.num_classes != self.known:
             raise _lib.WacilError(f"teacher has {teacher.num_classes} classes, known_classes = {self.known}")
+
+    def _setup_peer_memory(self, group):
+        """Put the gradient arena and a flag pad into symmetric (peer-mapped) memory so that the fused all-reduce + SGD
+        kernel can read every rank's gradients over NVLink.  Returns None (NCCL all-reduce is used instead) when this
+        torch build / topology cannot provide peer mappings."""
+        import ctypes
+        import warnings
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            arena = self.model._arena
+            n = arena.grads.numel()
+            g = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+            g.zero_()
+            pad = symm_mem.empty(64, dtype=torch.int32, device=self.device)
+            pad.zero_()
+            hg = symm_mem.rendezvous(g, grp)
+            hp = symm_mem.rendezvous(pad, grp)
+            world, rank = hg.world_size, hg.rank
+            if world != self.world_size:
+                raise RuntimeError("world size mismatch")
+            peer = {"grads": g, "pad": pad, "handles": (hg, hp), "rank": rank,
+                    "grad_ptrs": (ctypes.c_void_p * world)(*[int(x) for x in hg.buffer_ptrs]),
+                    "pad_ptrs": (ctypes.c_void_p * world)(*[int(x) for x in hp.buffer_ptrs]),
+                    "epoch": torch.zeros(2, dtype=torch.int32, device=self.device)}
+            arena.grads = g          # plans bind the gradient pointer at creation: drop the stale ones
+            self.model._plans = {}
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            return peer
+        except Exception as ex:  # noqa: BLE001
+            warnings.warn(f"symmetric memory unavailable ({ex}); gradients go through NCCL all-reduce")
+            return None
 
     def set_lr(self, lr):
         self.lr_dev.fill_(float(lr))
@@ -219,12 +256,16 @@ class TaskTrainer:
 
     def _opt(self):
         a = self.model._arena
-        ops.sgd_step_(a.params, a.grads, self.mom, self.lr_dev, self.momentum, self.weight_decay,
-                      1.0 / self.world_size)
+        if self.peer is not None:  # gradient mean over NVLink peer memory + SGD in one kernel
+            ops.allreduce_sgd_(a.params, self.mom, self.peer["grad_ptrs"], self.peer["pad_ptrs"], self.world_size,
+                               self.peer["rank"], self.lr_dev, self.peer["epoch"], self.momentum, self.weight_decay)
+        else:
+            ops.sgd_step_(a.params, a.grads, self.mom, self.lr_dev, self.momentum, self.weight_decay,
+                          1.0 / self.world_size)
         return 1
 
     def _run(self, st):
-        single = self.world_size == 1
+        single = self.world_size == 1 or self.peer is not None  # one graph holds the whole step
         if not self.use_graph or st.warm < 2:
             n = self._fwd_bwd(st)
             if not single:

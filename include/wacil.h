@@ -84,6 +84,16 @@ int wacil_weight_align(void* W, int C_total, int D, int n_new, float* gamma_out,
 int wacil_sgd_step(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
                    float weight_decay, float grad_scale, void* stream);
 
+/* DDP gradient mean + SGD fused over NVLink peer memory (template.py:243-244,270-271): every rank reads all ranks'
+ * gradient arenas (grad_ptrs[r] = rank r's arena mapped into this process: CUDA IPC / symmetric memory) in rank order —
+ * bit-identical sums on all ranks — and updates its own p, v:  g = mean_r grad_r + wd*p; v = mom*v + g; p -= lr*v.
+ * pad_ptrs[r]: rank r's peer-writable flag pad (>= 128 bytes, zero initially); epoch_ws: 8 bytes of LOCAL device memory,
+ * zero initially.  Host arrays of `world` pointers (world <= 16); n must be a multiple of 4.  All ranks must call it the
+ * same number of times; the kernel returns only when every peer has finished reading this rank's gradients, so the
+ * caller may overwrite them right after (stream order).  Capturable: one graph holds the whole step. */
+int wacil_allreduce_sgd(float* p, float* v, const void* const* grad_ptrs, void* const* pad_ptrs, int world, int rank,
+                        int64_t n, const float* lr_dev, float momentum, float weight_decay, void* epoch_ws, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Herding  (continuum.rehearsal.herd_closest_to_barycenter, call site template.py:300-302)
  * features: fp32 [n][D] row-major; class_offsets: int32 [n_classes + 1], samples of
