@@ -30,16 +30,20 @@ def _worker(rank, world, port, q):
         t = w.CilModel("resnet20"); t.load_state_dict(tsd); t = t.cuda().copy().freeze()
         tr = w.TaskTrainer(m, t, 10, lr=0.05, world_size=world, fused_allreduce=fused, use_graph=True)
         assert (tr.peer is not None) == fused, "symmetric memory must be available on an NVLink box"
-        for x, y in zip(xs, ys):
+        first = None
+        for i, (x, y) in enumerate(zip(xs, ys)):
             tr.step(x, y)
+            if i == 0:
+                torch.cuda.synchronize()
+                first = m.arena.detach().clone().cpu()
         torch.cuda.synchronize()
         p = m.arena.detach().clone()
         others = [torch.zeros_like(p) for _ in range(world)]
         dist.all_gather(others, p)
-        out[fused] = (p.cpu(), all(torch.equal(o, others[0]) for o in others))
+        out[fused] = (p.cpu(), all(torch.equal(o, others[0]) for o in others), first)
         dist.barrier()
-    rel = ((out[True][0] - out[False][0]).double().norm() / out[False][0].double().norm()).item()
-    q.put((rank, out[True][1], out[False][1], rel))
+    rel = lambda a, b: ((a - b).double().norm() / b.double().norm()).item()
+    q.put((rank, out[True][1], out[False][1], rel(out[True][2], out[False][2]), rel(out[True][0], out[False][0])))
     dist.destroy_process_group()
 
 
@@ -56,6 +60,7 @@ def test_fused_p2p_allreduce_sgd_matches_nccl():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, fused_identical, nccl_identical, rel in results:
+    for rank, fused_identical, nccl_identical, rel1, rel4 in results:
         assert fused_identical, "fused path: replicas must be bit-identical (fixed rank-order sums)"
-        assert rel < 2e-2, rel  # vs NCCL: different summation order upstream of 4 chaotic bf16 steps
+        assert rel1 < 1e-4, rel1  # one step: same gradients up to fp32 summation order
+        assert rel4 < 6e-2, rel4  # four steps: that round-off is amplified by the chaotic bf16 forward
