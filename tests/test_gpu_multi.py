@@ -43,7 +43,32 @@ def _worker(rank, world, port, q):
         out[fused] = (p.cpu(), all(torch.equal(o, others[0]) for o in others), first)
         dist.barrier()
     rel = lambda a, b: ((a - b).double().norm() / b.double().norm()).item()
-    q.put((rank, out[True][1], out[False][1], rel(out[True][2], out[False][2]), rel(out[True][0], out[False][0])))
+    # the kernel alone, on identical inputs: fused peer-memory mean + SGD vs NCCL all-reduce + wacil_sgd_step
+    import ctypes
+    import torch.distributed._symmetric_memory as symm_mem
+    n = 100000
+    g = symm_mem.empty(n, dtype=torch.float32, device="cuda")
+    pad = symm_mem.empty(64, dtype=torch.int32, device="cuda")
+    pad.zero_()
+    hg, hp = symm_mem.rendezvous(g, dist.group.WORLD), symm_mem.rendezvous(pad, dist.group.WORLD)
+    gp = (ctypes.c_void_p * world)(*[int(v) for v in hg.buffer_ptrs])
+    pp = (ctypes.c_void_p * world)(*[int(v) for v in hp.buffer_ptrs])
+    epoch = torch.zeros(2, dtype=torch.int32, device="cuda")
+    gen2 = torch.Generator().manual_seed(7)
+    p0 = torch.randn(n, generator=gen2).cuda()
+    pa, va, pb, vb = p0.clone(), torch.zeros(n, device="cuda"), p0.clone(), torch.zeros(n, device="cuda")
+    lr = torch.full((1,), 0.1, device="cuda")
+    kerr = 0.0
+    for it in range(3):
+        g.copy_(torch.randn(n, generator=torch.Generator().manual_seed(1000 * rank + it)).cuda())
+        ref = g.clone()
+        torch.cuda.synchronize(); dist.barrier()
+        w.ops.allreduce_sgd_(pa, va, gp, pp, world, rank, lr, epoch)
+        dist.all_reduce(ref)
+        w.ops.sgd_step_(pb, ref, vb, lr, 0.9, 5e-4, 1.0 / world)
+        torch.cuda.synchronize(); dist.barrier()
+        kerr = max(kerr, (pa - pb).abs().max().item())
+    q.put((rank, out[True][1], out[False][1], rel(out[True][2], out[False][2]), rel(out[True][0], out[False][0]), kerr))
     dist.destroy_process_group()
 
 
@@ -60,7 +85,10 @@ def test_fused_p2p_allreduce_sgd_matches_nccl():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, fused_identical, nccl_identical, rel1, rel4 in results:
+    for rank, fused_identical, nccl_identical, rel1, rel4, kerr in results:
         assert fused_identical, "fused path: replicas must be bit-identical (fixed rank-order sums)"
-        assert rel1 < 1e-4, rel1  # one step: same gradients up to fp32 summation order
-        assert rel4 < 6e-2, rel4  # four steps: that round-off is amplified by the chaotic bf16 forward
+        assert kerr < 2e-6, kerr  # the kernel on identical inputs: fp32 summation order only
+        # whole training runs: the atomics-ordered reductions upstream differ run to run in the last bits and the bf16
+        # forward amplifies that, for either collective
+        assert rel1 < 5e-3, rel1
+        assert rel4 < 6e-2, rel4
