@@ -72,6 +72,7 @@ struct ConvGemmParams {
   __nv_bfloat16* gy_up;         // optional zero-upsampled copy (stride-2 layer l)
   __nv_bfloat16* gz;            // optional masked gradient (shortcut of the previous block)
   long long* dbg;               // optional [gridDim.x][16] clock64 timestamps of pipeline milestones (profiling)
+  int fold;                     // pixel-pair form: the nc columns are 2 x (nc/2) real channels (column c -> channel c % (nc/2))
   int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
   int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
 };
@@ -331,10 +332,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     float* s_c2 = s_stats + 640;      // [nc]          | d-gamma / M
     float* s_mean = s_stats + 704;    // [nc]
     float* s_rstd = s_stats + 768;    // [nc]
+    // Pixel-pair ("fold") form: a row is two horizontally adjacent pixels, its nc columns are (pixel parity, channel);
+    // BatchNorm parameters and statistics belong to the ncr = nc/2 real channels, a row counts as two pixels.
+    const int ncr = p.fold ? p.nc / 2 : p.nc;
     if (p.epi == EPI_BNBWD) {
       for (int c = tid128; c < p.nc; c += 128) {
-        s_mean[c] = p.saved[c];
-        s_rstd[c] = p.saved[p.nc + c];
+        s_mean[c] = p.saved[c % ncr];
+        s_rstd[c] = p.saved[ncr + c % ncr];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -353,8 +357,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           gres_ptr = p.g_res + base;
         } else {
           const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (((w | h) & 1) == 0)
+          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
+            if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
+          } else if (((w | h) & 1) == 0) {
             gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+          }
         }
       }
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           if (valid) {
             load16_bf16(p.act_in + base + c0, a);
             load16_bf16(p.y_in + base + c0, yv);
-            if (gres_ptr != nullptr) {
+            if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {  // fold: only the even pixel's half
               float r[16];
               load16_bf16(gres_ptr + c0, r);
 #pragma unroll
@@ -407,35 +414,36 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
     {
       float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
-      float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + p.nc : p.dgamma;
+      float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + ncr : p.dgamma;
       for (int c = tid128; c < p.nc; c += 128) {
-        atomicAdd(g0 + c, s_part[0 * 64 + c] + s_part[2 * 64 + c] + s_part[4 * 64 + c] + s_part[6 * 64 + c]);
-        atomicAdd(g1 + c, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
+        atomicAdd(g0 + c % ncr, s_part[0 * 64 + c] + s_part[2 * 64 + c] + s_part[4 * 64 + c] + s_part[6 * 64 + c]);
+        atomicAdd(g1 + c % ncr, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
       }
     }
     grid_barrier_epi(p.grid_bar, tid128);
     if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
-    const float cnt = static_cast<float>(p.num_pixels);
+    const float cnt = static_cast<float>(p.num_pixels) * (p.fold ? 2.f : 1.f);
     for (int c = tid128; c < p.nc; c += 128) {
+      const int cc = c % ncr;
       if (p.epi == EPI_BN_TRAIN) {
-        const float mean = __ldcg(p.stats + c) / cnt;
-        float var = __ldcg(p.stats + p.nc + c) / cnt - mean * mean;
+        const float mean = __ldcg(p.stats + cc) / cnt;
+        float var = __ldcg(p.stats + ncr + cc) / cnt - mean * mean;
         var = fmaxf(var, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        const float sc = p.gamma[c] * rstd;
+        const float sc = p.gamma[cc] * rstd;
         s_c0[c] = sc;
-        s_c1[c] = p.beta[c] - mean * sc;
-        if (blockIdx.x == 0) {
+        s_c1[c] = p.beta[cc] - mean * sc;
+        if (blockIdx.x == 0 && c < ncr) {
           p.saved[c] = mean;
-          p.saved[p.nc + c] = rstd;
+          p.saved[ncr + c] = rstd;
           p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
           p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (cnt / (cnt - 1.f));
         }
       } else {
-        s_c0[c] = p.gamma[c] * s_rstd[c];
-        s_c1[c] = __ldcg(p.dbeta + c) / cnt;
-        s_c2[c] = __ldcg(p.dgamma + c) / cnt;
+        s_c0[c] = p.gamma[cc] * s_rstd[c];
+        s_c1[c] = __ldcg(p.dbeta + cc) / cnt;
+        s_c2[c] = __ldcg(p.dgamma + cc) / cnt;
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -455,7 +463,9 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
       if (valid && p.epi == EPI_BNBWD && p.g_res != nullptr) {
         if (p.gres_mode == 1) gres_ptr = p.g_res + base;
-        else if (((w | h) & 1) == 0)
+        else if (p.fold) {
+          if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
+        } else if (((w | h) & 1) == 0)
           gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
       }
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
@@ -479,7 +489,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           float a[16], yv[16], o[16];
           load16_bf16(p.act_in + base + c0, a);
           load16_bf16(p.y_in + base + c0, yv);
-          if (gres_ptr != nullptr) {
+          if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {
             float r[16];
             load16_bf16(gres_ptr + c0, r);
 #pragma unroll

@@ -84,6 +84,9 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
     d.stride = stride;
     d.H_in = H_in;
     d.H_out = H_in / stride;
+    d.sup_f = (d.H_out == 32) ? 1 : 0;
+    d.sup_d = (d.H_in == 32 && !L.empty()) ? 1 : 0;  // the first layer has no data gradient
+    d.sup_w = (d.H_in == 32 && stride == 1) ? 1 : 0;
     L.push_back(d);
   };
   add(3, 16, 1, 32);
@@ -97,7 +100,7 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
       add(planes[s], planes[s], 1, H);
       inpl = planes[s];
     }
-  long long off = 0, boff = 0, woff = 0, bioff = 0;
+  long long off = 0, boff = 0, woff = 0, bioff = 0, scroff = 0;
   for (auto& d : L) {
     d.w_off = off;
     off += 9LL * d.cin_pad * d.cout;
@@ -112,11 +115,13 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
     d.rvar_off = boff;
     boff += d.cout;
     d.wf_off = woff;
-    woff += 9LL * d.cin_pad * d.cout;
+    woff += 9LL * d.cin_pad * d.cout * (d.sup_f ? 4 : 1);
     d.wd_off = woff;
-    woff += 9LL * d.cin_pad * d.cout;
+    woff += 9LL * d.cin_pad * d.cout * (d.sup_d ? 4 : 1);
     d.bias_off = bioff;
-    bioff += d.cout;
+    bioff += d.cout * (d.sup_f ? 2 : 1);
+    d.wscr_off = scroff;
+    if (d.sup_w) scroff += 36LL * d.cin_pad * d.cout;
   }
   if (lay) {
     lay->depth = depth;
@@ -143,7 +148,9 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3];
+  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wscr, which;
+  size_t wscr_elems = 0;
+  int n_sup_w = 0;
   std::vector<size_t> y, a, gyup;
   size_t stat_elems = 0, wbuf_elems = 0, total = 0;
 };
@@ -152,15 +159,21 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   Carve c;
   const size_t nl = L.size();
   o.table = c.take(nl * sizeof(LayerDesc));
-  size_t wel = 0, sel = 0;
+  size_t wel = 0, sel = 0, scr = 0;
+  int nsw = 0;
   for (auto& d : L) {
-    wel += 18ull * d.cin_pad * d.cout;
+    wel += 9ull * d.cin_pad * d.cout * ((d.sup_f ? 4 : 1) + (d.sup_d ? 4 : 1));
     sel += 2ull * d.cout;
+    if (d.sup_w) { scr += 36ull * d.cin_pad * d.cout; ++nsw; }
   }
+  o.wscr_elems = scr;
+  o.n_sup_w = nsw;
   o.wbuf_elems = wel;
   o.stat_elems = sel;
   o.wbuf = c.take(wel * 2);
-  o.bias = c.take(sel * 2);  // cout floats per layer (<= sel*2 bytes... sized generously: sel*4/2)
+  o.bias = c.take(sel * 4);  // <= 2*cout floats per layer (pixel-pair layers duplicate the bias)
+  o.wscr = c.take(scr * 4 + 16);
+  o.which = c.take(static_cast<size_t>(nsw + 1) * 4);
   o.stats = c.take(sel * 4);
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
@@ -441,6 +454,14 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   const size_t nl = n->L.size();
   cudaError_t ce = cudaMemcpy(n->ws + n->off.table, n->L.data(), nl * sizeof(LayerDesc), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "layer table upload"); }
+  {
+    std::vector<int> which;
+    for (size_t l = 0; l < nl; ++l)
+      if (n->L[l].sup_w) which.push_back(static_cast<int>(l));
+    which.push_back(-1);
+    ce = cudaMemcpy(n->ws + n->off.which, which.data(), which.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "pixel-pair layer list upload"); }
+  }
   __nv_bfloat16* wbuf = n->at<__nv_bfloat16>(n->off.wbuf);
   n->fprop.resize(nl);
   if (mode == WACIL_NET_TRAIN) {
@@ -460,10 +481,15 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       const LayerDesc& d = n->L[l];
       // ---- forward: conv + batch statistics + BatchNorm + shortcut + ReLU in one cooperative launch
       ConvLaunch& c = n->fprop[l];
-      e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
-                     wbuf + d.wf_off, EPI_STATS);
+      if (d.sup_f)  // 32x32 output: pixel-pair form, [N,32,32,C] read as [N,32,16,2C]
+        e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9,
+                       wbuf + d.wf_off, EPI_STATS);
+      else
+        e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
+                       wbuf + d.wf_off, EPI_STATS);
       if (e) { delete n; return e; }
       if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) { delete n; return e; }
+      c.p.fold = d.sup_f;
       c.p.pdl = pdl_enabled() ? 1 : 0;
       c.p.w_early = l > 0 ? 1 : 0;  // layer 0 is launched right after cast_weights
       c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
@@ -480,11 +506,15 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         c.p.res = n->act_in(static_cast<int>(l) - 1);
         const bool ds = (da.stride == 2 || da.cin != da.cout);
         c.p.res_stride = ds ? 2 : 1;
-        c.p.res_c = ds ? da.cin : d.cout;
+        c.p.res_c = ds ? da.cin : c.p.nc;
       }
       // ---- wgrad: X = layer input, dY = GY[l % 3]
-      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
-                      n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
+      if (d.sup_w)  // pixel-pair weight gradient into a scratch, folded onto the real gradient by wgrad_fold_kernel
+        e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
+                        n->at<float>(n->off.wscr) + d.wscr_off, batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9);
+      else
+        e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
+                        n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
       n->wgrad[l].p.pdl = pdl_enabled() ? 1 : 0;
       if (l > 0) {
@@ -493,9 +523,13 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         const LayerDesc& pd = n->L[l - 1];
         const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 3]);
         ConvLaunch& g = n->dgrad[l];
-        e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
+        if (d.sup_d)
+          e = setup_conv(g, src, batch, 32, 16, 2 * d.cout, 2 * d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
+        else
+          e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
         if (e) { delete n; return e; }
         if ((e = make_fused(g, EPI_BNBWD, gbar))) { delete n; return e; }
+        g.p.fold = d.sup_d;
         g.p.pdl = pdl_enabled() ? 1 : 0;
         g.p.w_early = 1;  // operand copies were written by cast_weights in the forward
         const int pl = static_cast<int>(l) - 1;
@@ -546,7 +580,12 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         if (da.stride == 2 || da.cin != da.cout) { res_stride = 2; res_c = da.cin; }
         cur = (cur + 2) % 3;
       }
-      e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
+      if (d.sup_f) {
+        e = setup_conv(c, in, batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9, wbuf + d.wf_off, EPI_INFER);
+        res_c = 2 * d.cout;  // identity shortcut on the pixel-pair view
+      } else {
+        e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
+      }
       if (e) { delete n; return e; }
       c.p.pdl = pdl_enabled() ? 1 : 0;
       c.p.w_early = 1;  // folded once per task by wacil_net_fold
@@ -676,6 +715,10 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   int launches = 0, e;
   cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
+  if (n->off.wscr_elems) {
+    ce = cudaMemsetAsync(n->ws + n->off.wscr, 0, n->off.wscr_elems * 4, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "weight-gradient scratch clear");
+  }
   float* dfeats = n->at<float>(n->off.dfeats);
   fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
                                                   C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
@@ -738,6 +781,14 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
       if (par) WACIL_EV(cudaEventRecord(n->ev_gy[l - 1], st), "event record");
       ++launches;
     }
+  }
+  if (n->off.n_sup_w > 0) {  // pixel-pair weight gradients -> real [9][cin][cout] gradients (after the last wgrad)
+    dim3 fgrid(9, static_cast<unsigned>(n->off.n_sup_w));
+    wgrad_fold_kernel<<<fgrid, 256, 0, ws>>>(n->at<float>(n->off.wscr), n->grads, n->at<LayerDesc>(n->off.table),
+                                             n->at<int>(n->off.which), n->off.n_sup_w);
+    WACIL_LAUNCH_CHECK("wgrad_fold_kernel");
+    ++launches;
+    if (par) WACIL_EV(cudaEventRecord(n->ev_wg[0], ws), "event record");
   }
   if (par) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[0], 0), "event wait");  // join (the side stream is in order)
 #undef WACIL_EV
