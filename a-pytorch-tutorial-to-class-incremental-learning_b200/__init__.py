@@ -8,8 +8,11 @@ from ._lib import WacilError, build  # noqa: F401
 
 _lib.lib()  # fail loudly at import time if the CUDA library is missing
 
-from . import ops  # noqa: E402,F401
+from . import checkpoint, data, ops  # noqa: E402,F401
 from .model import CilClassifier, CilModel, SoftTarget, freeze_parameters  # noqa: E402,F401
-from .rehearsal import RehearsalMemory, herd_closest_to_barycenter  # noqa: E402,F401
-from .train import (TaskTrainer, accuracy, eval, get_args_parser, init_distributed_mode, init_seed,  # noqa: E402,F401
-                    train_task, update_model)
+from .data import ClassIncrementalScenario, DeviceTaskSet, build_dataset  # noqa: E402,F401
+from .rehearsal import (RehearsalMemory, herd_closest_to_barycenter, herd_closest_to_cluster,  # noqa: E402,F401
+                        herd_random)
+from .train import (TaskTrainer, accuracy, eval, evaluate, extract_features, get_args_parser,  # noqa: E402,F401
+                    init_distributed_mode, init_seed, train_task, update_model)
+from . import template  # noqa: E402,F401

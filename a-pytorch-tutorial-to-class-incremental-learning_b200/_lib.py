@@ -38,12 +38,17 @@ SIGNATURES = {
     "wacil_kd_workspace_bytes": (Z, [I]),
     "wacil_kd_fwd_bwd": (I, [P, L, P, L, I, I, F, F, P, P, L, I, I, P, P]),
     "wacil_ce_kd_fwd_bwd": (I, [P, L, P, P, L, I, I, I, F, F, F, P, P, L, P, P]),
+    "wacil_ce_kd_fwd_bwd_w": (I, [P, L, P, P, L, I, I, I, F, F, F, F, P, P, L, P, P]),
+    "wacil_eval_workspace_bytes": (Z, [I]),
+    "wacil_eval_rows": (I, [P, L, P, I, I, I, P, P, P]),
     "wacil_weight_align_workspace_bytes": (Z, [I]),
     "wacil_weight_align": (I, [P, I, I, I, P, I, P, P]),
     "wacil_sgd_step": (I, [P, P, P, L, P, F, F, F, P]),
     "wacil_allreduce_sgd": (I, [P, P, P, P, I, I, L, P, F, F, P, P]),
     "wacil_herd_workspace_bytes": (Z, [L, I]),
     "wacil_herd_barycenter": (I, [P, L, P, I, I, I, P, P, P, P]),
+    "wacil_herd_cluster": (I, [P, L, P, I, I, I, P, P, P, P]),
+    "wacil_augment_u8": (I, [P, P, P, I, I, I, I, C.POINTER(F), C.POINTER(F), P, P]),
     "wacil_net_layout": (I, [I, I, C.POINTER(NetLayout)]),
     "wacil_net_layer_layout": (I, [I, I, I, C.POINTER(LayerLayout)]),
     "wacil_net_workspace_bytes": (Z, [I, I, I, I]),

@@ -735,4 +735,80 @@ __global__ void __launch_bounds__(256) herd_barycenter_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ cluster herding
+// continuum's herd_closest_to_cluster: per class the samples closest (L2) to the class-mean feature, nearest first.
+// One CTA per class; float32 operations in the order of oracle/herding.c (herd_cluster) so the indices are bit-exact.
+// dist: workspace [n].
+__global__ void __launch_bounds__(256) herd_cluster_kernel(const float* __restrict__ features,
+                                                           const int* __restrict__ class_offsets, int D, int quota,
+                                                           float* __restrict__ dist, int* __restrict__ out_idx,
+                                                           int* __restrict__ out_count) {
+  extern __shared__ float s_mem[];  // mean[D]
+  const int k_class = blockIdx.x;
+  const int lo = class_offsets[k_class], hi = class_offsets[k_class + 1];
+  const int m = hi - lo;
+  const int take = quota < m ? quota : m;
+  int* oidx = out_idx + static_cast<long long>(k_class) * quota;
+  for (int i = threadIdx.x; i < quota; i += blockDim.x) oidx[i] = -1;
+  if (threadIdx.x == 0) out_count[k_class] = take > 0 ? take : 0;
+  if (m <= 0) return;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {  // mean, sequential over the samples
+    float s = 0.f;
+    for (int i = 0; i < m; ++i) s = __fadd_rn(s, features[static_cast<long long>(lo + i) * D + k]);
+    s_mem[k] = __fdiv_rn(s, static_cast<float>(m));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {  // distance, sequential over the feature dimension
+    const float* f = features + static_cast<long long>(lo + i) * D;
+    float ss = 0.f;
+    for (int k = 0; k < D; ++k) {
+      const float d = __fsub_rn(s_mem[k], f[k]);
+      ss = __fadd_rn(ss, __fmul_rn(d, d));
+    }
+    dist[lo + i] = __fsqrt_rn(ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {  // stable rank = position in the ascending order
+    const float di = dist[lo + i];
+    int r = 0;
+    for (int j = 0; j < m; ++j) {
+      const float dj = dist[lo + j];
+      r += (dj < di || (dj == di && j < i)) ? 1 : 0;
+    }
+    if (r < take) oidx[r] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ device data path
+// The CIFAR train/eval transform of utils.py:210-251 without the host loader: gather sample idx[b] from the uint8 HWC
+// store, RandomCrop(32, padding=4) (zero fill) at offset (dy, dx), RandomHorizontalFlip, ToTensor (x / 255),
+// Normalize ((x - mean) / std) -> fp32 NCHW.  aug[b] = dy | dx << 8 | flip << 16 (NULL: centre crop dy = dx = pad, no
+// flip = the eval transform).  IEEE division in the order torchvision applies it: bit-exact with the CPU restatement.
+__global__ void augment_u8_kernel(const uint8_t* __restrict__ store, const int64_t* __restrict__ idx,
+                                  const int32_t* __restrict__ aug, int B, int H, int W, int pad, float m0, float m1,
+                                  float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // output pixel
+  const long long hw = static_cast<long long>(H) * W;
+  if (i >= B * hw) return;
+  const int b = static_cast<int>(i / hw);
+  const int p = static_cast<int>(i - b * hw);
+  const int y = p / W, x = p - y * W;
+  const int a = aug ? aug[b] : (pad | (pad << 8));
+  const int dy = a & 0xff, dx = (a >> 8) & 0xff, flip = (a >> 16) & 1;
+  const int sy = y + dy - pad;
+  const int sx = (flip ? (W - 1 - x) : x) + dx - pad;
+  float r = 0.f, g = 0.f, bl = 0.f;
+  if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+    const long long n = idx ? idx[b] : b;
+    const uint8_t* px = store + (n * hw + static_cast<long long>(sy) * W + sx) * 3;
+    r = static_cast<float>(px[0]);
+    g = static_cast<float>(px[1]);
+    bl = static_cast<float>(px[2]);
+  }
+  float* o = out + static_cast<long long>(b) * 3 * hw + p;
+  o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(r, 255.f), m0), s0);
+  o[hw] = __fdiv_rn(__fsub_rn(__fdiv_rn(g, 255.f), m1), s1);
+  o[2 * hw] = __fdiv_rn(__fsub_rn(__fdiv_rn(bl, 255.f), m2), s2);
+}
+
 }  // namespace wacil

@@ -46,6 +46,19 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+// Pixel-pair form of the 32x32-resolution layers: bit 0 fprop, bit 1 dgrad, bit 2 wgrad (WACIL_PAIR).  Off by default:
+// the A/B on one box (profiles/r01_pair_ab.md) shows the plain form 0.9 % faster on the step (the stage-1 main loop is
+// bound by L2->SM bytes, which the pair form does not change, not by TMA row count); tests/test_gpu_engine.py keeps the
+// pair form under parity in a subprocess.
+int pair_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WACIL_PAIR");
+    v = e ? (atoi(e) & 7) : 0;
+  }
+  return v;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -84,9 +97,10 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
     d.stride = stride;
     d.H_in = H_in;
     d.H_out = H_in / stride;
-    d.sup_f = (d.H_out == 32) ? 1 : 0;
-    d.sup_d = (d.H_in == 32 && !L.empty()) ? 1 : 0;  // the first layer has no data gradient
-    d.sup_w = (d.H_in == 32 && stride == 1) ? 1 : 0;
+    const int pm = pair_mask();
+    d.sup_f = ((pm & 1) && d.H_out == 32) ? 1 : 0;
+    d.sup_d = ((pm & 2) && d.H_in == 32 && !L.empty()) ? 1 : 0;  // the first layer has no data gradient
+    d.sup_w = ((pm & 4) && d.H_in == 32 && stride == 1) ? 1 : 0;
     L.push_back(d);
   };
   add(3, 16, 1, 32);
@@ -816,6 +830,56 @@ int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B,
   const bool vec = (C % 4 == 0) && (s_ld % 4 == 0) && (t_ld % 4 == 0) && (!g || g_ld % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(s) % vb == 0) && (reinterpret_cast<uintptr_t>(t) % vb == 0) &&
                    (!g || reinterpret_cast<uintptr_t>(g) % vb == 0);
+  // 16-byte aligned rows wider than 512 columns: the persistent TMA-streamed kernel (WACIL_KD_STREAM=0 selects the
+  // register-row kernels).  Configurations from the sweep in profiles/r01_kd_stream_sweep.log: as many row groups per
+  // CTA as the row width allows (32 elements per thread), the ring as deep as ~190 KB of shared memory permits.
+  {
+    static int stream_env = -2;
+    if (stream_env == -2) { const char* ev = getenv("WACIL_KD_STREAM"); stream_env = ev ? (ev[0] == '0' ? 0 : 1) : -1; }
+    const size_t es = sizeof(T);
+    const bool al16 = (C * es) % 16 == 0 && (s_ld * es) % 16 == 0 && (t_ld * es) % 16 == 0 && (!g || (g_ld * es) % 16 == 0) &&
+                      reinterpret_cast<uintptr_t>(s) % 16 == 0 && reinterpret_cast<uintptr_t>(t) % 16 == 0 &&
+                      (!g || reinterpret_cast<uintptr_t>(g) % 16 == 0);
+    if (stream_env != 0 && al16 && C > 512 && C <= 8192) {
+      int e = 0;
+#define KD_STREAM(TPR, EPT, NS)                                                                                     \
+  do {                                                                                                              \
+    using Cfg = KdStreamCfg<T, 512, TPR, EPT, NS>;                                                                  \
+    static_assert(Cfg::kSmemBytes <= 227 * 1024, "kd_stream_kernel ring exceeds the shared memory of an SM");       \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      cudaError_t ce = cudaFuncSetAttribute(kd_stream_kernel<T, 512, TPR, EPT, NS>,                                 \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                            static_cast<int>(Cfg::kSmemBytes));                                     \
+      if (ce != cudaSuccess) { e = cuda_fail(ce, "kd_stream_kernel smem attribute"); break; }                       \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    int grid = (B + Cfg::G - 1) / Cfg::G;                                                                           \
+    if (grid > num_sms()) grid = num_sms();                                                                         \
+    cudaLaunchConfig_t cfg{};                                                                                       \
+    cfg.gridDim = dim3(grid);                                                                                       \
+    cfg.blockDim = dim3(512);                                                                                       \
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;                                                                         \
+    cfg.stream = st;                                                                                                \
+    cudaLaunchAttribute at[1];                                                                                      \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                  \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                                           \
+    cfg.attrs = at;                                                                                                 \
+    cfg.numAttrs = pdl_enabled() ? 1 : 0; /* setup runs under the previous kernel's tail; the kernel waits before reading */ \
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kd_stream_kernel<T, 512, TPR, EPT, NS>, sp, s_ld, tp, t_ld, B, C, invT, \
+                                        gscale, lscale, loss_out, gp, g_ld, accumulate, part, counter);             \
+    if (le != cudaSuccess) e = cuda_fail(le, "kd_stream_kernel");                                                   \
+  } while (0)
+      constexpr bool kF32 = sizeof(T) == 4;
+      if (C <= 1024) KD_STREAM(64, 16, 16);
+      else if (C <= 2048) KD_STREAM(64, 32, (kF32 ? 12 : 16));
+      else if (C <= 4096) KD_STREAM(128, 32, (kF32 ? 6 : 12));
+      else KD_STREAM(256, 32, (kF32 ? 3 : 6));
+#undef KD_STREAM
+      if (e) return e;
+      return 0;
+    }
+  }
 #define KD_LAUNCH(TPR, CACHE, VEC)                                                                              \
   kd_rows_kernel<T, TPR, CACHE, VEC>                                                                            \
       <<<(TPR >= 256 ? B : (B + (256 / TPR) - 1) / (256 / TPR)), (TPR >= 256 ? TPR : 256), 0, st>>>(            \
@@ -865,6 +929,13 @@ int wacil_kd_fwd_bwd(const void* s, int64_t s_ld, const void* t, int64_t t_ld, i
 int wacil_ce_kd_fwd_bwd(const float* logits, int64_t l_ld, const int64_t* targets, const float* t_logits,
                         int64_t t_ld, int B, int C_seen, int C_known, float T, float lambda_kd, float smooth,
                         float* losses_out, float* dlogits, int64_t d_ld, void* workspace, void* stream) {
+  return wacil_ce_kd_fwd_bwd_w(logits, l_ld, targets, t_logits, t_ld, B, C_seen, C_known, T, 1.f, lambda_kd, smooth,
+                               losses_out, dlogits, d_ld, workspace, stream);
+}
+
+int wacil_ce_kd_fwd_bwd_w(const float* logits, int64_t l_ld, const int64_t* targets, const float* t_logits,
+                          int64_t t_ld, int B, int C_seen, int C_known, float T, float ce_weight, float lambda_kd,
+                          float smooth, float* losses_out, float* dlogits, int64_t d_ld, void* workspace, void* stream) {
   if (!logits || !targets || !losses_out || !workspace) return fail(WACIL_E_NULL, "NULL argument");
   if (B <= 0 || C_seen <= 0 || l_ld < C_seen || (dlogits && d_ld < C_seen)) return fail(WACIL_E_SHAPE, "B=%d C=%d", B, C_seen);
   if (t_logits && (C_known <= 0 || C_known > C_seen || t_ld < C_known)) return fail(WACIL_E_SHAPE, "C_known=%d", C_known);
@@ -878,8 +949,8 @@ int wacil_ce_kd_fwd_bwd(const float* logits, int64_t l_ld, const int64_t* target
   cudaStream_t st = S(stream);
 #define CK_LAUNCH(TPR, CACHE)                                                                                 \
   ce_kd_rows_kernel<TPR, CACHE><<<(B + (256 / TPR) - 1) / (256 / TPR), 256, 0, st>>>(                         \
-      logits, l_ld, targets, t_logits, t_ld, B, C_seen, C_known, invT, gsc, lsc, smooth, losses_out, dlogits, \
-      d_ld, part, counter)
+      logits, l_ld, targets, t_logits, t_ld, B, C_seen, C_known, invT, gsc, lsc, smooth, ce_weight, losses_out,  \
+      dlogits, d_ld, part, counter)
   if (C_seen <= 128) CK_LAUNCH(32, 4);
   else if (C_seen <= 1024) CK_LAUNCH(32, 32);
   else if (C_seen <= 8192) CK_LAUNCH(256, 32);
@@ -973,6 +1044,51 @@ int wacil_herd_barycenter(const float* features, int64_t n, const int32_t* class
   herd_barycenter_kernel<<<n_classes, 256, 2 * D * sizeof(float), S(stream)>>>(features, class_offsets, D, quota, n, dnT,
                                                                               rank, out_idx, out_count);
   WACIL_LAUNCH_CHECK("herd_barycenter_kernel");
+  return 0;
+}
+
+int wacil_herd_cluster(const float* features, int64_t n, const int32_t* class_offsets, int n_classes, int D, int quota,
+                       int32_t* out_idx, int32_t* out_count, void* workspace, void* stream) {
+  if (!features || !class_offsets || !out_idx || !out_count || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (n <= 0 || n_classes <= 0 || D <= 0 || D > 2048 || quota <= 0)
+    return fail(WACIL_E_SHAPE, "n=%lld classes=%d D=%d quota=%d", static_cast<long long>(n), n_classes, D, quota);
+  herd_cluster_kernel<<<n_classes, 256, D * sizeof(float), S(stream)>>>(features, class_offsets, D, quota,
+                                                                        static_cast<float*>(workspace), out_idx, out_count);
+  WACIL_LAUNCH_CHECK("herd_cluster_kernel");
+  return 0;
+}
+
+size_t wacil_eval_workspace_bytes(int B) { return 64 + static_cast<size_t>(B > 0 ? B : 0) * 3 * 4; }
+
+int wacil_eval_rows(const float* logits, int64_t l_ld, const int64_t* targets, int B, int C, int topk, double* meter,
+                    void* workspace, void* stream) {
+  if (!logits || !targets || !meter || !workspace) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || C <= 0 || l_ld < C || topk < 1) return fail(WACIL_E_SHAPE, "B=%d C=%d topk=%d", B, C, topk);
+  unsigned* counter = static_cast<unsigned*>(workspace);
+  float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 64);
+  cudaStream_t st = S(stream);
+#define EV_LAUNCH(TPR, CACHE)                                                                              \
+  eval_rows_kernel<TPR, CACHE><<<(B + (256 / TPR) - 1) / (256 / TPR), 256, 0, st>>>(logits, l_ld, targets, B, C, topk, \
+                                                                                     meter, part, counter)
+  if (C <= 128) EV_LAUNCH(32, 4);
+  else if (C <= 1024) EV_LAUNCH(32, 32);
+  else if (C <= 8192) EV_LAUNCH(256, 32);
+  else return fail(WACIL_E_SHAPE, "C = %d > 8192", C);
+#undef EV_LAUNCH
+  WACIL_LAUNCH_CHECK("eval_rows_kernel");
+  return 0;
+}
+
+int wacil_augment_u8(const uint8_t* store, const int64_t* idx, const int32_t* aug, int B, int H, int W, int pad,
+                     const float* mean3, const float* std3, float* out, void* stream) {
+  if (!store || !mean3 || !std3 || !out) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || H <= 0 || W <= 0 || pad < 0 || pad > 127) return fail(WACIL_E_SHAPE, "B=%d H=%d W=%d pad=%d", B, H, W, pad);
+  for (int c = 0; c < 3; ++c)
+    if (!(std3[c] > 0.f)) return fail(WACIL_E_SHAPE, "std[%d] must be positive", c);
+  const long long npix = static_cast<long long>(B) * H * W;
+  augment_u8_kernel<<<static_cast<int>((npix + 255) / 256), 256, 0, S(stream)>>>(
+      store, idx, aug, B, H, W, pad, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out);
+  WACIL_LAUNCH_CHECK("augment_u8_kernel");
   return 0;
 }
 

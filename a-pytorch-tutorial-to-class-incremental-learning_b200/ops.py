@@ -64,8 +64,9 @@ def kd_fwd_bwd(out_s, out_t, T, scale=1.0, grad_out=None, accumulate=False, need
 
 
 def ce_kd_fwd_bwd(logits, targets, t_logits, known, T=2.0, lambda_kd=0.5, smooth=0.0, losses=None, dlogits=None,
-                  workspace=None):
-    """CE + lambda*KD (template.py:259-266), forward and backward.  Returns (losses[4], dlogits[B,C_seen])."""
+                  workspace=None, ce_weight=1.0):
+    """ce_weight*CE + lambda*KD (template.py:259-266; README.md:172-176 for ce_weight = 1 - lambda), forward and
+    backward.  Returns (losses[4] = [ce_weight*CE, lambda*KD, sum, top-1 count], dlogits[B,C_seen])."""
     _need_cuda(logits, targets, t_logits)
     B, Cs = logits.shape
     if logits.dtype != torch.float32 or logits.stride(1) != 1 or targets.dtype != torch.int64:
@@ -76,11 +77,11 @@ def ce_kd_fwd_bwd(logits, targets, t_logits, known, T=2.0, lambda_kd=0.5, smooth
         dlogits = torch.empty((B, Cs), dtype=torch.float32, device=logits.device)
     ws = workspace if workspace is not None else _workspace("cekd", lib().wacil_kd_workspace_bytes(B), logits.device)
     tl = None if t_logits is None else t_logits
-    check(lib().wacil_ce_kd_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(),
-                                    tl.data_ptr() if tl is not None else None, tl.stride(0) if tl is not None else 0,
-                                    B, Cs, int(known) if tl is not None else 0, float(T), float(lambda_kd),
-                                    float(smooth), losses.data_ptr(), dlogits.data_ptr(), dlogits.stride(0),
-                                    ws.data_ptr(), _stream()), "wacil_ce_kd_fwd_bwd")
+    check(lib().wacil_ce_kd_fwd_bwd_w(logits.data_ptr(), logits.stride(0), targets.data_ptr(),
+                                      tl.data_ptr() if tl is not None else None, tl.stride(0) if tl is not None else 0,
+                                      B, Cs, int(known) if tl is not None else 0, float(T), float(ce_weight),
+                                      float(lambda_kd), float(smooth), losses.data_ptr(), dlogits.data_ptr(),
+                                      dlogits.stride(0), ws.data_ptr(), _stream()), "wacil_ce_kd_fwd_bwd_w")
     return losses, dlogits
 
 
@@ -129,6 +130,60 @@ def herd_barycenter(features, class_offsets, quota):
     check(lib().wacil_herd_barycenter(features.data_ptr(), n, class_offsets.data_ptr(), k, D, int(quota), idx.data_ptr(),
                                       cnt.data_ptr(), ws.data_ptr(), _stream()), "wacil_herd_barycenter")
     return idx, cnt
+
+
+def herd_cluster(features, class_offsets, quota):
+    """continuum's herd_closest_to_cluster on the GPU: same layout as herd_barycenter."""
+    _need_cuda(features, class_offsets)
+    if features.dtype != torch.float32 or not features.is_contiguous() or class_offsets.dtype != torch.int32:
+        raise _lib.WacilError("herd: features fp32 contiguous, class_offsets int32")
+    n, D = features.shape
+    k = class_offsets.numel() - 1
+    idx = torch.empty((k, quota), dtype=torch.int32, device=features.device)
+    cnt = torch.empty((k,), dtype=torch.int32, device=features.device)
+    ws = _workspace("herdc", n * 4, features.device)
+    check(lib().wacil_herd_cluster(features.data_ptr(), n, class_offsets.data_ptr(), k, D, int(quota), idx.data_ptr(),
+                                   cnt.data_ptr(), ws.data_ptr(), _stream()), "wacil_herd_cluster")
+    return idx, cnt
+
+
+def eval_rows_(logits, targets, meter, topk=5):
+    """Adds one validation batch to the float64[8] device meter (template.py:169-188): [samples, batches, sum of batch
+    mean CE, top-1 count, top-k count]; k = min(topk, C) like timm.utils.accuracy(topk=(1, min(5, C)))."""
+    _need_cuda(logits, targets, meter)
+    B, Cn = logits.shape
+    if logits.dtype != torch.float32 or logits.stride(1) != 1 or targets.dtype != torch.int64:
+        raise _lib.WacilError("eval_rows: logits fp32 with unit column stride, targets int64")
+    if meter.dtype != torch.float64 or meter.numel() < 5 or not meter.is_contiguous():
+        raise _lib.WacilError("eval_rows: meter is a contiguous float64 tensor of >= 5 elements")
+    ws = _workspace("eval", lib().wacil_eval_workspace_bytes(B), logits.device)
+    check(lib().wacil_eval_rows(logits.data_ptr(), logits.stride(0), targets.data_ptr(), B, Cn, min(int(topk), Cn),
+                                meter.data_ptr(), ws.data_ptr(), _stream()), "wacil_eval_rows")
+    return meter
+
+
+def augment_u8(store, idx=None, aug=None, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), pad=4, out=None):
+    """Device data path (utils.py:210-251): store uint8 [n,H,W,3] -> fp32 NCHW [B,3,H,W]: gather idx, RandomCrop(H, pad)
+    + horizontal flip from the packed `aug` words (dy | dx << 8 | flip << 16), ToTensor, Normalize(mean, std)."""
+    _need_cuda(store, idx, aug)
+    if store.dtype != torch.uint8 or store.dim() != 4 or store.shape[3] != 3 or not store.is_contiguous():
+        raise _lib.WacilError("augment_u8: store must be a contiguous uint8 [n,H,W,3] tensor")
+    n, H, W_, _ = store.shape
+    B = n if idx is None else idx.numel()
+    if idx is not None and (idx.dtype != torch.int64 or not idx.is_contiguous()):
+        raise _lib.WacilError("augment_u8: idx int64 contiguous")
+    if aug is not None and (aug.dtype != torch.int32 or aug.numel() != B or not aug.is_contiguous()):
+        raise _lib.WacilError("augment_u8: aug int32 [B] contiguous")
+    if out is None:
+        out = torch.empty((B, 3, H, W_), dtype=torch.float32, device=store.device)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (B, 3, H, W_) or not out.is_contiguous():
+        raise _lib.WacilError("augment_u8: out must be contiguous fp32 [B,3,H,W]")
+    import ctypes as C
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().wacil_augment_u8(store.data_ptr(), idx.data_ptr() if idx is not None else None,
+                                 aug.data_ptr() if aug is not None else None, B, H, W_, int(pad), m3, s3,
+                                 out.data_ptr(), _stream()), "wacil_augment_u8")
+    return out
 
 
 def conv3x3_fprop(x, w, stride=1, want_stats=False):

@@ -11,9 +11,10 @@ import torch
 from . import _lib, ops
 
 
-def herd_indices(features, y, nb_per_class, device=None):
+def herd_indices(features, y, nb_per_class, device=None, method="barycenter"):
     """Indices (into the rows of `features`) of the exemplars: classes in ascending id order, herding-rank order
-    inside a class.  `features`: [n, D] float32 numpy array or torch tensor; `y`: [n] integer labels."""
+    inside a class.  `features`: [n, D] float32 numpy array or torch tensor; `y`: [n] integer labels.
+    method: "barycenter" (iCaRL herding) or "cluster" (closest to the class mean)."""
     if isinstance(features, np.ndarray):
         if features.ndim != 2:
             raise ValueError(f"Expected features to have 2 dimensions, not {features.ndim}d.")
@@ -33,7 +34,12 @@ def herd_indices(features, y, nb_per_class, device=None):
     offsets = torch.zeros(classes.numel() + 1, dtype=torch.int32, device=device)
     offsets[1:] = torch.cumsum(counts, 0).int()
     grouped = feats.index_select(0, order).contiguous()
-    idx, cnt = ops.herd_barycenter(grouped, offsets, int(nb_per_class))
+    if method == "barycenter":
+        idx, cnt = ops.herd_barycenter(grouped, offsets, int(nb_per_class))
+    elif method == "cluster":
+        idx, cnt = ops.herd_cluster(grouped, offsets, int(nb_per_class))
+    else:
+        raise NotImplementedError(f"Unknown rehearsal method {method}.")
     # row-local -> original indices, trimmed to the per-class counts
     k, q = idx.shape
     valid = torch.arange(q, device=device)[None, :] < cnt[:, None]
@@ -47,6 +53,26 @@ def herd_closest_to_barycenter(x, y, t, features, nb_per_class):
     return x[idx], y[idx], t[idx]
 
 
+def herd_closest_to_cluster(x, y, t, features, nb_per_class):
+    """continuum.rehearsal.herd_closest_to_cluster (--herding_method cluster): distances and ranking on the GPU."""
+    idx = herd_indices(features, y, nb_per_class, method="cluster").cpu().numpy()
+    return x[idx], y[idx], t[idx]
+
+
+def herd_random(x, y, t, features, nb_per_class):
+    """continuum.rehearsal.herd_random (--herding_method random): index selection only (no arithmetic), drawn from
+    NumPy's global RNG like upstream (the reference seeds it, template.py:54)."""
+    indexes = []
+    for class_id in np.unique(y):
+        class_indexes = np.where(y == class_id)[0]
+        indexes.append(np.random.choice(class_indexes, size=min(nb_per_class, len(class_indexes)), replace=False))
+    indexes = np.concatenate(indexes)
+    return x[indexes], y[indexes], t[indexes]
+
+
+_HERDING = {"barycenter": herd_closest_to_barycenter, "cluster": herd_closest_to_cluster, "random": herd_random}
+
+
 class RehearsalMemory:
     """`rehearsal.RehearsalMemory(memory_size, herding_method, fixed_memory)` (template.py:212-216).
 
@@ -58,11 +84,11 @@ class RehearsalMemory:
     def __init__(self, memory_size, herding_method="barycenter", fixed_memory=False, nb_total_classes=None,
                  dedup_old=False):
         if isinstance(herding_method, str):
-            if herding_method != "barycenter":
+            if herding_method not in _HERDING:
                 raise NotImplementedError(f"Unknown rehearsal method {herding_method}.")
-            herding_method = herd_closest_to_barycenter
+            herding_method = _HERDING[herding_method]
         elif not callable(herding_method):
-            raise NotImplementedError("herding_method must be 'barycenter' or a callable")
+            raise NotImplementedError("herding_method must be 'barycenter', 'cluster', 'random' or a callable")
         if fixed_memory and nb_total_classes is None:
             raise ValueError("When memory is fixed, precise the `nb_total_classes` argument.")
         self.memory_size, self.herding_method = memory_size, herding_method

@@ -56,6 +56,18 @@ def get_args_parser():
     return p
 
 
+def add_runner_args(p):
+    """Flags of this implementation's runner (template.main) that the reference does not have."""
+    p.add_argument("--synthetic_per_class", default=500, type=int, help="--data_set synthetic: train images per class")
+    p.add_argument("--synthetic_val_per_class", default=100, type=int)
+    p.add_argument("--nb_classes", default=100, type=int, help="--data_set synthetic: number of classes")
+    p.add_argument("--checkpoint_dir", default="", type=str, help="write a checkpoint after every task")
+    p.add_argument("--resume", default="", type=str, help="checkpoint file to resume from")
+    p.add_argument("--dedup_old", action="store_true", help="keep each class once in the rehearsal memory")
+    p.add_argument("--max_tasks", default=0, type=int, help="stop after this many tasks (0 = all)")
+    return p
+
+
 def init_seed(args):
     """template.py:52-58."""
     np.random.seed(args.seed)
@@ -166,14 +178,14 @@ class TaskTrainer:
 
     def __init__(self, model: CilModel, teacher, known_classes, lr=0.1, momentum=0.9, weight_decay=5e-4,
                  lambda_kd=0.5, T=2.0, smooth=0.0, world_size=1, use_graph=True, process_group=None, overlap=True,
-                 fused_allreduce=True):
+                 fused_allreduce=True, ce_weight=1.0):
         if not model.arena.is_cuda:
             raise _lib.WacilError("TaskTrainer needs the model on a CUDA device (no CPU path)")
         self.model, self.teacher = model, teacher
         self.device = model.arena.device
         self.c_seen, self.known = model.num_classes, int(known_classes)
         self.momentum, self.weight_decay = momentum, weight_decay
-        self.lambda_kd, self.T, self.smooth = lambda_kd, T, smooth
+        self.lambda_kd, self.T, self.smooth, self.ce_weight = lambda_kd, T, smooth, ce_weight
         self.world_size, self.pg = world_size, process_group
         self.use_graph = use_graph
         # two extra streams: the frozen teacher's forward runs beside the student's, the weight gradients beside the
@@ -248,7 +260,7 @@ class TaskTrainer:
                 t_logits, _ = st.plan_t.forward(st.x, self.known)
                 n += st.plan_t.launches
         ops.ce_kd_fwd_bwd(logits, st.y, t_logits, self.known, self.T, self.lambda_kd, self.smooth, st.losses,
-                          st.dlogits, st.ws)
+                          st.dlogits, st.ws, ce_weight=self.ce_weight)
         st.plan_s.backward(st.dlogits)
         n += st.plan_s.launches + 1
         self.acc.add_(st.losses)
@@ -293,16 +305,13 @@ class TaskTrainer:
             allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
             st.graph_opt.replay()
 
-    def step(self, x, y):
-        """One optimisation step (template.py:255-271) on a [B,3,32,32] fp32 batch and int64 targets; `x`/`y` may live
-        in pinned host memory (copied asynchronously) or on the device.  Returns the device tensor [ce, kd, loss, top1
-        count] of this step (no host sync)."""
-        b = x.shape[0]
+    def _state(self, b):
         st = self._states.get(b)
         if st is None:
             st = self._states[b] = _StepState(self, b)
-        st.x.copy_(x, non_blocking=True)
-        st.y.copy_(y, non_blocking=True)
+        return st
+
+    def _execute(self, st):
         captured_now = self.use_graph and st.warm >= 2 and st.graph_fb is None
         self._run(st)
         if captured_now:
@@ -311,6 +320,23 @@ class TaskTrainer:
         self.model._num_batches_tracked += 1
         self.model._touch()
         return st.losses
+
+    def step(self, x, y):
+        """One optimisation step (template.py:255-271) on a [B,3,32,32] fp32 batch and int64 targets; `x`/`y` may live
+        in pinned host memory (copied asynchronously) or on the device.  Returns the device tensor [ce, kd, loss, top1
+        count] of this step (no host sync)."""
+        st = self._state(x.shape[0])
+        st.x.copy_(x, non_blocking=True)
+        st.y.copy_(y, non_blocking=True)
+        return self._execute(st)
+
+    def step_from_store(self, taskset, idx, aug=None):
+        """The same step fed by the device data path (utils.py:210-251 without the host loader): gather + RandomCrop +
+        flip + ToTensor + Normalize of samples `idx` of the uint8 store straight into the step's input buffer."""
+        st = self._state(idx.numel())
+        taskset.batch(idx, aug, out=st.x)
+        torch.index_select(taskset.y, 0, idx, out=st.y)
+        return self._execute(st)
 
     def epoch_stats(self, n_samples):
         """Means of ce / kd / loss and top-1 % since the last call (one host sync per epoch)."""
@@ -321,11 +347,22 @@ class TaskTrainer:
 
 
 # ------------------------------------------------------------------------------------------------------------
+def kd_weights(args, known, nb_new, has_teacher):
+    """(ce_weight, lambda_kd).  Default: CE + lambda_kd * KD (template.py:262-266).  --dynamic_lambda_kd (declared at
+    template.py:48, never read by the reference): the objective of README.md:172-176,
+    (1 - lambda) * CE + lambda * KD with lambda = n_old / (n_old + n_new)."""
+    if has_teacher and getattr(args, "dynamic_lambda_kd", False) and known > 0:
+        lam = known / float(known + nb_new)
+        return 1.0 - lam, lam
+    return 1.0, args.lambda_kd
+
+
 def train_task(model, teacher_model, data, args, rank=None, world_size=None, num_epochs=None, use_graph=True,
                on_epoch_end=None, log=print):
     """Train `model` on one task (template.py:246-283).  `data` = (x [N,3,32,32] fp32, y [N] int64) for this task
-    (new samples U rehearsal memory), device-resident or pinned host tensors.  Returns the per-epoch stats."""
-    x_all, y_all = data
+    (new samples U rehearsal memory), device-resident or pinned host tensors, or a data.DeviceTaskSet (uint8 store in
+    HBM, augmentation on the device).  Returns the per-epoch stats."""
+    from .data import DeviceTaskSet
     rank = getattr(args, "rank", 0) if rank is None else rank
     world_size = getattr(args, "world_size", 1) if world_size is None else world_size
     epochs = args.num_epochs if num_epochs is None else num_epochs
@@ -333,22 +370,31 @@ def train_task(model, teacher_model, data, args, rank=None, world_size=None, num
     known = getattr(args, "known_classes", 0)
     if teacher_model is None:
         known = 0
+    ce_w, lam = kd_weights(args, known, model.num_classes - known, teacher_model is not None)
     tr = TaskTrainer(model, teacher_model, known, lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay,
-                     lambda_kd=args.lambda_kd, T=2.0, smooth=getattr(args, "smooth", 0.0), world_size=world_size,
-                     use_graph=use_graph)
-    n = x_all.shape[0]
+                     lambda_kd=lam, T=2.0, smooth=getattr(args, "smooth", 0.0), world_size=world_size,
+                     use_graph=use_graph, ce_weight=ce_w)
+    from_store = isinstance(data, DeviceTaskSet)
+    if from_store:
+        n, dev = len(data), data.x.device
+    else:
+        x_all, y_all = data
+        n, dev = x_all.shape[0], (x_all.device if x_all.is_cuda else None)
     history = []
-    on_dev = x_all.is_cuda
     for epoch in range(epochs):
         model.train()
         tr.set_lr(cosine_lr(args.lr, epoch, epochs))
         idx = sampler_indices(n, epoch, rank, world_size, seed=0, shuffle=True)
-        if on_dev:
-            idx = idx.to(x_all.device)
+        if dev is not None:
+            idx = idx.to(dev)
+        aug = data.draw_aug(idx.numel(), seed=getattr(args, "seed", 0), epoch=epoch, rank=rank) if from_store else None
         seen = 0
         for s in range(0, idx.numel(), bs):
             bi = idx[s: s + bs]
-            tr.step(x_all.index_select(0, bi), y_all.index_select(0, bi))
+            if from_store:
+                tr.step_from_store(data, bi, aug[s: s + bs])
+            else:
+                tr.step(x_all.index_select(0, bi), y_all.index_select(0, bi))
             seen += bi.numel()
         stats = tr.epoch_stats(seen * world_size)
         stats["epoch"], stats["lr"] = epoch + 1, cosine_lr(args.lr, epoch, epochs)
@@ -375,35 +421,66 @@ def update_model(model, args, nb_new_classes, stage):
 
 @torch.no_grad()
 def extract_features(model, x_all, batch_size=128):
-    """Features of every sample for herding (template.py:292-299), eval-mode BN, kept on the device."""
+    """Features of every sample for herding (template.py:292-299), eval-mode BN, kept on the device.  `x_all`: fp32
+    [N,3,32,32] tensor or a data.DeviceTaskSet (centre crop, no flip: the reference extracts through the *train*
+    transform, whose random draws differ per rank — SURVEY 8e; here every rank computes identical features)."""
+    from .data import DeviceTaskSet
     was_training = model.training
     model.eval()
     outs = []
-    for s in range(0, x_all.shape[0], batch_size):
-        xb = x_all[s: s + batch_size]
-        if not xb.is_cuda:
-            xb = xb.to(model.arena.device, non_blocking=True)
+    n = len(x_all) if isinstance(x_all, DeviceTaskSet) else x_all.shape[0]
+    for s in range(0, n, batch_size):
+        if isinstance(x_all, DeviceTaskSet):
+            xb = x_all.batch(torch.arange(s, min(s + batch_size, n), device=x_all.x.device), None)
+        else:
+            xb = x_all[s: s + batch_size]
+            if not xb.is_cuda:
+                xb = xb.to(model.arena.device, non_blocking=True)
         outs.append(model.extract_vector(xb.contiguous()))
     model.train(was_training)
     return torch.cat(outs, 0)
 
 
+def _finish_meter(meter, log=print):
+    """MetricLogger.synchronize_between_processes + the global averages eval() prints (template.py:185-188)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(meter)
+    n, nb, loss_sum, top1, top5 = meter[:5].tolist()  # the one host sync of the evaluation
+    acc1, acc5 = 100.0 * top1 / max(n, 1.0), 100.0 * top5 / max(n, 1.0)
+    loss = loss_sum / max(nb, 1.0)
+    if log is not None:
+        log(" Acc@1 {:.3f}  loss {:.3f}".format(acc1, loss))
+    return acc1, acc5, loss
+
+
 @torch.no_grad()
 def eval(model, val_loader):  # noqa: A001  (the reference's name, template.py:169-188)
-    """Top-1 accuracy (%) over an iterable of (images, target, task_ids); cross-rank mean when distributed."""
+    """Top-1 accuracy (%) over an iterable of (images, target, task_ids) — this rank's shard, like the reference's
+    DistributedSampler'd loader; losses and hit counts are accumulated on the device by one fused kernel per batch
+    (wacil_eval_rows) and reduced across ranks once."""
     model.eval()
     dev = model.arena.device
-    tot = torch.zeros(4, dtype=torch.float64, device=dev)  # n, loss*n, top1*n, top5*n
+    meter = torch.zeros(8, dtype=torch.float64, device=dev)
     for images, target, *_ in val_loader:
         images, target = images.to(dev, non_blocking=True), target.to(dev, non_blocking=True)
         logits, _ = model(images.contiguous().float())
-        loss = torch.nn.functional.cross_entropy(logits, target)
-        a1, a5 = accuracy(logits, target, topk=(1, min(5, logits.shape[1])))
-        b = images.shape[0]
-        tot += torch.stack([torch.tensor(float(b), device=dev, dtype=torch.float64), loss.double() * b,
-                            a1.double() * b, a5.double() * b])
-    if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(tot)
-    n = max(tot[0].item(), 1.0)
-    print(" Acc@1 {:.3f}  loss {:.3f}".format(tot[2].item() / n, tot[1].item() / n))
-    return tot[2].item() / n
+        ops.eval_rows_(logits, target.long(), meter, topk=5)
+    return _finish_meter(meter)[0]
+
+
+@torch.no_grad()
+def evaluate(model, taskset, args=None, batch_size=None, log=print):
+    """eval() over a data.DeviceTaskSet (template.py:229,234-239,282-287): each rank takes its
+    DistributedSampler(shuffle=False) shard (padding duplicates included, like the reference), eval transform on the
+    device, fused meter kernel, one all-reduce.  Returns (acc1, acc5, loss)."""
+    model.eval()
+    rank, world = getattr(args, "rank", 0), getattr(args, "world_size", 1)
+    bs = batch_size or getattr(args, "batch_size", 128)
+    dev = taskset.x.device
+    idx = sampler_indices(len(taskset), 0, rank, world, shuffle=False).to(dev)
+    meter = torch.zeros(8, dtype=torch.float64, device=dev)
+    for s in range(0, idx.numel(), bs):
+        bi = idx[s: s + bs]
+        logits, _ = model(taskset.batch(bi, None))
+        ops.eval_rows_(logits, taskset.y.index_select(0, bi), meter, topk=5)
+    return _finish_meter(meter, log if rank == 0 else None)

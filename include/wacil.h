@@ -66,6 +66,24 @@ int wacil_ce_kd_fwd_bwd(const float* logits, int64_t l_ld, const int64_t* target
                         int64_t t_ld, int B, int C_seen, int C_known, float T, float lambda_kd, float smooth,
                         float* losses_out, float* dlogits, int64_t d_ld, void* workspace, void* stream);
 
+/* The same with a weight on the CrossEntropy term: loss = ce_weight * CE + lambda_kd * KD.  README.md:172-176 states
+ * the WA objective as (1 - lambda) * CE + lambda * KD with lambda = n_old / (n_old + n_new) ("--dynamic_lambda_kd",
+ * template.py:48, a flag the reference declares but never reads); losses_out[0] = ce_weight * CE. */
+int wacil_ce_kd_fwd_bwd_w(const float* logits, int64_t l_ld, const int64_t* targets, const float* t_logits,
+                          int64_t t_ld, int B, int C_seen, int C_known, float T, float ce_weight, float lambda_kd,
+                          float smooth, float* losses_out, float* dlogits, int64_t d_ld, void* workspace, void* stream);
+
+/* Validation meter of eval() (template.py:169-188): one pass over a batch of logits, accumulated on the device into
+ * meter (float64[8], zeroed by the caller before the first batch):
+ *   meter[0] += B   meter[1] += 1   meter[2] += mean CrossEntropy of the batch (MetricLogger.update(loss=..), utils.py:77-86)
+ *   meter[3] += #rows whose target is the top-1 logit   meter[4] += #rows whose target is among the top `topk`
+ * (timm.utils.accuracy(logits, target, topk=(1, min(5, C))), template.py:179-180: acc = 100 * count / samples).
+ * logits fp32 [B][C] row stride l_ld, targets int64 [B].  workspace: wacil_eval_workspace_bytes(B), zero on first use.
+ * The cross-rank reduction (MetricLogger.synchronize_between_processes, utils.py:36-43) is one all-reduce of meter. */
+size_t wacil_eval_workspace_bytes(int B);
+int wacil_eval_rows(const float* logits, int64_t l_ld, const int64_t* targets, int B, int C, int topk, double* meter,
+                    void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Weight aligning  (CilModel.weight_align, template.py:156-166)
  *   norms = ||W[r,:]||_2 ; gamma = mean(norms[:C_total-n_new]) / mean(norms[C_total-n_new:])
@@ -105,6 +123,24 @@ int wacil_allreduce_sgd(float* p, float* v, const void* const* grad_ptrs, void* 
 size_t wacil_herd_workspace_bytes(int64_t n, int D);
 int wacil_herd_barycenter(const float* features, int64_t n, const int32_t* class_offsets, int n_classes, int D,
                           int quota, int32_t* out_idx, int32_t* out_count, void* workspace, void* stream);
+
+/* continuum.rehearsal.herd_closest_to_cluster (--herding_method cluster, template.py:34,214): per class the `quota`
+ * samples whose feature is closest (L2) to the class mean, nearest first.  Same argument layout as
+ * wacil_herd_barycenter; bit-exact with oracle/herding.c:herd_cluster.  workspace: n * 4 bytes. */
+int wacil_herd_cluster(const float* features, int64_t n, const int32_t* class_offsets, int n_classes, int D, int quota,
+                       int32_t* out_idx, int32_t* out_count, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Device data path  (the CIFAR transform of utils.py:210-251 without the 10-worker host loader, template.py:236-239)
+ * store: uint8 [n][H][W][3] raw samples resident in HBM (what dataset.get_raw_samples() / memory.get() hold,
+ * template.py:231,301); idx: int64 [B] sample of each batch row (NULL: rows 0..B-1); aug: int32 [B] packed
+ * dy | dx << 8 | flip << 16 with 0 <= dy, dx <= 2*pad (NULL: centre crop, no flip = the eval transform).
+ *   out[b][c][y][x] = (padded(store[idx[b]])[y + dy][(flip ? W-1-x : x) + dx][c] / 255 - mean[c]) / std[c]
+ * i.e. RandomCrop(W, padding=pad) with zero fill, RandomHorizontalFlip, ToTensor, Normalize in torchvision's order
+ * and rounding (IEEE fp32 division): bit-exact with the CPU restatement.  out: fp32 NCHW [B][3][H][W] — the tensor
+ * wacil_net_forward consumes.  mean3/std3 are HOST arrays of 3 floats. */
+int wacil_augment_u8(const uint8_t* store, const int64_t* idx, const int32_t* aug, int B, int H, int W, int pad,
+                     const float* mean3, const float* std3, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * The ResNet engine  (CifarResNet + CilClassifier forward/backward: resnet.py:107-116, template.py:99-123,270)

@@ -95,3 +95,52 @@ int64_t herd_barycenter_c(const float* features, const int64_t* y, int64_t n, in
   free(ci); free(D); free(mu); free(w); free(rank);
   return written;
 }
+
+/* herd_cluster_c — continuum.rehearsal.herd_closest_to_cluster (--herding_method cluster, template.py:34,214):
+ * per class, the nb_per_class samples whose feature is closest (L2) to the class mean, nearest first.
+ * Same conventions as above (PARITY UNPINNED against continuum; fixed float32 order: the mean sums sequentially over
+ * the samples, the squared distance sequentially over the feature dimension, separate multiply and add; ties keep
+ * the lower index = a stable ascending sort). */
+int64_t herd_cluster_c(const float* features, const int64_t* y, int64_t n, int d, int nb_per_class, int64_t* out_idx) {
+  if (n <= 0 || d <= 0 || nb_per_class < 0) return -1;
+  int64_t ymin = y[0], ymax = y[0];
+  for (int64_t i = 1; i < n; ++i) {
+    if (y[i] < ymin) ymin = y[i];
+    if (y[i] > ymax) ymax = y[i];
+  }
+  int64_t written = 0;
+  int64_t* ci = (int64_t*)malloc(sizeof(int64_t) * n);
+  float* mean = (float*)malloc(sizeof(float) * d);
+  float* dist = (float*)malloc(sizeof(float) * n);
+  for (int64_t c = ymin; c <= ymax; ++c) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (y[i] == c) ci[m++] = i;
+    if (m == 0) continue;
+    for (int k = 0; k < d; ++k) {
+      float s = 0.f;
+      for (int64_t i = 0; i < m; ++i) s = s + features[ci[i] * d + k];
+      mean[k] = s / (float)m;
+    }
+    for (int64_t i = 0; i < m; ++i) {
+      const float* f = features + ci[i] * d;
+      float ss = 0.f;
+      for (int k = 0; k < d; ++k) {
+        float df = mean[k] - f[k];
+        float sq = df * df;
+        ss = ss + sq;
+      }
+      dist[i] = sqrtf(ss);
+    }
+    int64_t take = nb_per_class < m ? nb_per_class : m;
+    for (int64_t i = 0; i < m; ++i) {
+      int64_t r = 0;
+      for (int64_t j = 0; j < m; ++j)
+        if (dist[j] < dist[i] || (dist[j] == dist[i] && j < i)) ++r;
+      if (r < take) out_idx[written + r] = ci[i];
+    }
+    written += take;
+  }
+  free(ci); free(mean); free(dist);
+  return written;
+}

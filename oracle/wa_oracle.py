@@ -338,6 +338,83 @@ def herd_barycenter_seq(features: np.ndarray, y: np.ndarray, nb_per_class: int) 
     return np.concatenate(out)
 
 
+def herd_cluster_np(x, y, t, features: np.ndarray, nb_per_class: int):
+    """continuum.rehearsal.herd_closest_to_cluster (--herding_method cluster, template.py:34,214; continuum==1.2.2 is
+    not vendored: PARITY UNPINNED): per class the samples closest to the class-mean feature, nearest first."""
+    if features.ndim != 2:
+        raise ValueError(f"Expected features to have 2 dimensions, not {features.ndim}d.")
+    indexes = []
+    for class_id in np.unique(y):
+        class_indexes = np.where(y == class_id)[0]
+        class_features = features[class_indexes]
+        class_mean = np.mean(class_features, axis=0, keepdims=True)
+        dist_to_mean = np.linalg.norm(class_mean - class_features, axis=1)
+        tmp_indexes = dist_to_mean.argsort(kind="stable")[:nb_per_class]
+        indexes.append(class_indexes[tmp_indexes])
+    indexes = np.concatenate(indexes)
+    return x[indexes], y[indexes], t[indexes], indexes
+
+
+def herd_random_np(x, y, t, features, nb_per_class: int, rng=np.random):
+    """continuum.rehearsal.herd_random (--herding_method random): nb_per_class samples per class, uniformly without
+    replacement, from NumPy's global RNG (the reference seeds it, template.py:54)."""
+    indexes = []
+    for class_id in np.unique(y):
+        class_indexes = np.where(y == class_id)[0]
+        indexes.append(rng.choice(class_indexes, size=min(nb_per_class, len(class_indexes)), replace=False))
+    indexes = np.concatenate(indexes)
+    return x[indexes], y[indexes], t[indexes], indexes
+
+
+# ---------------------------------------------------------------------------------------------------- data path
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+CIFAR_MEAN, CIFAR_STD = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)
+
+
+def transform_stats(data_set: str, input_size: int = 32):
+    """The Normalize() the reference ends up with (utils.py:228-230,246-251): the CIFAR statistics only when
+    args.data_set == 'CIFAR' (upper case) — with the default --data_set cifar the ImageNet defaults stay in place."""
+    if input_size == 32 and data_set == "CIFAR":
+        return CIFAR_MEAN, CIFAR_STD
+    return IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+
+
+def augment_u8_np(store: np.ndarray, idx, aug, mean, std, pad: int = 4) -> np.ndarray:
+    """CPU restatement of the CIFAR transform chain of utils.py:210-251 for explicit random draws:
+    RandomCrop(32, padding=4) (zero fill; top-left corner (dy, dx) in the padded image), RandomHorizontalFlip,
+    ToTensor (uint8 -> float32 / 255), Normalize ((x - mean) / std, float32).  store uint8 [n,H,W,3]; idx [B] or None;
+    aug int32 [B] = dy | dx << 8 | flip << 16 or None (centre crop, no flip = the eval transform, utils.py:245-251).
+    RandAugment / colour jitter of timm's create_transform are host-side PIL operations outside this path."""
+    n, H, W, _ = store.shape
+    idx = np.arange(n) if idx is None else np.asarray(idx)
+    B = len(idx)
+    aug = np.full(B, pad | (pad << 8), dtype=np.int32) if aug is None else np.asarray(aug)
+    out = np.empty((B, 3, H, W), dtype=np.float32)
+    m = np.asarray(mean, dtype=np.float32).reshape(3, 1, 1)
+    s = np.asarray(std, dtype=np.float32).reshape(3, 1, 1)
+    for b in range(B):
+        dy, dx, flip = int(aug[b]) & 0xFF, (int(aug[b]) >> 8) & 0xFF, (int(aug[b]) >> 16) & 1
+        padded = np.zeros((H + 2 * pad, W + 2 * pad, 3), dtype=np.uint8)
+        padded[pad:pad + H, pad:pad + W] = store[idx[b]]
+        crop = padded[dy:dy + H, dx:dx + W]
+        if flip:
+            crop = crop[:, ::-1]
+        ten = crop.transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+        out[b] = (ten - m) / s
+    return out
+
+
+def eval_meter(logits: torch.Tensor, target: torch.Tensor, topk: int = 5) -> List[float]:
+    """What one iteration of eval() adds to its meters (template.py:174-184; utils.py:77-86): [samples, batches, batch
+    mean CrossEntropy, top-1 hits, top-min(topk, C) hits]; acc = 100 * hits / samples at the end (global_avg)."""
+    b, c = logits.shape
+    k = min(topk, c)
+    loss = F.cross_entropy(logits, target)
+    a1, ak = accuracy(logits, target, topk=(1, k))
+    return [float(b), 1.0, float(loss), float(a1) * b / 100.0, float(ak) * b / 100.0]
+
+
 class RehearsalMemoryOracle:
     """continuum.rehearsal.RehearsalMemory restated (ctor template.py:212-216; get :231; add :300-302)."""
 

@@ -318,3 +318,15 @@ def test_mini_class_incremental_run(w):
     xt, yt = task_data([0, 1, 2, 3], n=32)
     acc = (model(xt)[0].argmax(1) == yt).float().mean().item()
     assert acc > 0.7, acc
+
+
+def test_pixel_pair_form_stays_under_parity():
+    """The pixel-pair form of the 32x32 layers (WACIL_PAIR=7; the default is the plain form) runs the layer-by-layer
+    parity tests in a subprocess (the switch is read once per process)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, WACIL_PAIR="7")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "train_forward_backward or two_training_steps or infer_forward or fused_trainer"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -110,6 +110,8 @@ def test_rehearsal_memory_bookkeeping_with_callable_herding(w):
     ora.add(np.arange(60), np.repeat(np.arange(2), 30), np.zeros(60, int), None)
     assert len(ora) == 40
     with pytest.raises(NotImplementedError):
-        w.RehearsalMemory(10, "cluster")
+        w.RehearsalMemory(10, "kmeans")
+    for name in ("barycenter", "cluster", "random"):  # the three methods continuum ships (template.py:34)
+        assert callable(w.RehearsalMemory(10, name).herding_method)
     with pytest.raises(ValueError):
         w.RehearsalMemory(10, "barycenter", fixed_memory=True)

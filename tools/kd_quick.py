@@ -25,4 +25,4 @@ for dtype, code, esz in ((torch.float32, 0, 4), (torch.bfloat16, 1, 2)):
         torch.cuda.synchronize()
         best = min(best, 1e3 * e0.elapsed_time(e1) / 40)
     nbytes = 3 * B * C * esz + 4 * B
-    print(f"WACIL_KD_MATH={os.environ.get('WACIL_KD_MATH', '1')} {dtype}: {best:.2f} us  {nbytes / best / 1e3:.0f} GB/s  loss {loss.item():.6f}")
+    print(f"STREAM={os.environ.get('WACIL_KD_STREAM', '1')} MATH={os.environ.get('WACIL_KD_MATH', '-')} {dtype}: {best:.2f} us  {nbytes / best / 1e3:.0f} GB/s  loss {loss.item():.6f}")
