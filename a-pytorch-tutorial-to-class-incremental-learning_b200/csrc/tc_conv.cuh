@@ -204,7 +204,12 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [13*64] per-channel scratch
 
-  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc));
+  // Fused modes keep a second TMEM region beside the accumulators (same tile/column indexing, offset stash_col): what the
+  // post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: x-hat) is staged there in phase 1,
+  // while the main loop still runs, so that phase 2 touches no global memory but its stores.
+  const bool stash = (p.epi == EPI_BNBWD) || (p.epi == EPI_BN_TRAIN && p.res != nullptr);
+  const uint32_t stash_col = static_cast<uint32_t>(nacc * p.nc);
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 2u : 1u));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -342,16 +347,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN)
+    // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN); stages phase 2's operands
     int as = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
-      mbar_wait(&accfull[as], 0);
-      tc_fence_after();
-      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
       const __nv_bfloat16* gres_ptr = nullptr;
+      const __nv_bfloat16* res_ptr = nullptr;
       if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
         if (p.gres_mode == 1) {
           gres_ptr = p.g_res + base;
@@ -364,8 +367,29 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           }
         }
       }
+      if (p.epi == EPI_BN_TRAIN && p.res != nullptr && valid) {
+        if (p.res_stride == 1) {
+          res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
+        } else {
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+        }
+      }
+      if (p.epi == EPI_BN_TRAIN && stash) {
+        // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
+        for (int c0 = 0; c0 < p.nc; c0 += 16) {
+          float r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = 0.f;
+          if (res_ptr != nullptr && c0 < p.res_c) load16_bf16(res_ptr + c0, r);
+          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
+        }
+      }
+      mbar_wait(&accfull[as], 0);
+      tc_fence_after();
+      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
-        float v[16], s1[16], s2[16];
+        float v[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
           __align__(16) __nv_bfloat16 ob[16];
@@ -379,11 +403,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float r = valid ? __bfloat162float(ob[i]) : 0.f;
-            s1[i] = r;
+            v[i] = r;
             s2[i] = r * r;
           }
         } else {
           float a[16], yv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { a[i] = 0.f; yv[i] = 0.f; }
           if (valid) {
             load16_bf16(p.act_in + base + c0, a);
             load16_bf16(p.y_in + base + c0, yv);
@@ -396,12 +422,16 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float gzv = (valid && a[i] > 0.f) ? v[i] : 0.f;
-            s1[i] = gzv;
-            s2[i] = valid ? gzv * (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;
+            v[i] = (valid && a[i] > 0.f) ? v[i] : 0.f;                             // gz (masked gradient)
+            yv[i] = valid ? (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;       // x-hat
           }
+          // phase 2 reads both back from TMEM: gz replaces the accumulator, x-hat goes to the stash region
+          tmem_st16(tmem_base + lane_base + as * p.nc + c0, v);
+          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, yv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s2[i] = v[i] * yv[i];
         }
-        const float t1 = warp_colsum16(s1, lane);
+        const float t1 = warp_colsum16(v, lane);
         const float t2 = warp_colsum16(s2, lane);
         if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
           const int c = c0 + warp_colsum16_col(lane);
@@ -447,64 +477,43 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    // ---------------- phase 2: normalise (forward) / BN backward, from the accumulators still in TMEM
+    // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash)
     as = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-      const __nv_bfloat16* res_ptr = nullptr;
-      const __nv_bfloat16* gres_ptr = nullptr;
-      if (valid && p.epi == EPI_BN_TRAIN && p.res != nullptr) {
-        res_ptr = p.res_stride == 1
-                      ? p.res + static_cast<size_t>(pix) * p.res_c
-                      : p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
-      }
-      if (valid && p.epi == EPI_BNBWD && p.g_res != nullptr) {
-        if (p.gres_mode == 1) gres_ptr = p.g_res + base;
-        else if (p.fold) {
-          if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
-        } else if (((w | h) & 1) == 0)
-          gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+      size_t up_base = 0;
+      if (p.epi == EPI_BNBWD && p.gy_up != nullptr) {
+        const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+        up_base = ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc;
       }
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (!valid) continue;
         if (p.epi == EPI_BN_TRAIN) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
-          if (res_ptr != nullptr && c0 < p.res_c) {
+          if (stash) {
             float r[16];
-            load16_bf16(res_ptr + c0, r);
+            tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          store16_bf16(p.act_out + base + c0, v);
+          if (valid) store16_bf16(p.act_out + base + c0, v);
         } else {
-          float a[16], yv[16], o[16];
-          load16_bf16(p.act_in + base + c0, a);
-          load16_bf16(p.y_in + base + c0, yv);
-          if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {
-            float r[16];
-            load16_bf16(gres_ptr + c0, r);
+          float xh[16], o[16];
+          tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, xh);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          for (int i = 0; i < 16; ++i) o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xh[i] * s_c2[c0 + i]);
+          if (valid) {
+            store16_bf16(p.gy + base + c0, o);
+            if (p.gy_up != nullptr) store16_bf16(p.gy_up + up_base + c0, o);
+            if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = (a[i] > 0.f) ? v[i] : 0.f;  // gz
-            const float xhat = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
-            o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xhat * s_c2[c0 + i]);
-          }
-          store16_bf16(p.gy + base + c0, o);
-          if (p.gy_up != nullptr)
-            store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
-          if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
         }
       }
     }

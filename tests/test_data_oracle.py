@@ -32,7 +32,8 @@ def aug_cases(seed, n_store=12, B=9, pad=4):
     idx = rs.randint(0, n_store, size=B).astype(np.int64)
     dy, dx, fl = rs.randint(0, 2 * pad + 1, B), rs.randint(0, 2 * pad + 1, B), rs.randint(0, 2, B)
     dy[0], dx[0], fl[0] = 0, 0, 1          # top-left corner: 4 rows / columns of padding visible
-    dy[1], dx[1], fl[1] = 2 * pad, 2 * pad, 0  # bottom-right corner
+    if B > 1:
+        dy[1], dx[1], fl[1] = 2 * pad, 2 * pad, 0  # bottom-right corner
     aug = (dy | (dx << 8) | (fl << 16)).astype(np.int32)
     return store, idx, aug
 
