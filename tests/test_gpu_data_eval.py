@@ -152,13 +152,15 @@ def _runner_args(w, tmp, extra=()):
     p = argparse.ArgumentParser(parents=[w.get_args_parser()])
     w.train.add_runner_args(p)
     return p.parse_args(["--data_set", "synthetic", "--nb_classes", "6", "--num_bases", "2", "--increment", "2",
-                         "--backbone", "resnet20", "--batch_size", "64", "--num_epochs", "8", "--lr", "0.05",
-                         "--memory_size", "60", "--synthetic_per_class", "96", "--synthetic_val_per_class", "32",
+                         "--backbone", "resnet20", "--batch_size", "32", "--num_epochs", "10", "--lr", "0.05",
+                         "--memory_size", "60", "--synthetic_per_class", "128", "--synthetic_val_per_class", "32",
                          "--eval_every_epoch", "100", "--checkpoint_dir", str(tmp), *extra])
 
 
 def test_runner_end_to_end_and_resume(w, tmp_path):
-    """template.main on a 3-task synthetic protocol: learns (accuracy far above chance), writes checkpoints, and a run
+    """template.main on a 3-task synthetic protocol (>= 80 optimisation steps per task, the last ones at a small cosine
+    learning rate, so that the BatchNorm running statistics the evaluation uses have caught up with the weights):
+    learns (accuracy far above chance), writes checkpoints, and a run
     resumed from the task-0 checkpoint reproduces the uninterrupted run bit for bit (deterministic kernels apart from
     the weight-gradient atomics, so accuracies are compared with a small tolerance and the memory exactly)."""
     logs = []
