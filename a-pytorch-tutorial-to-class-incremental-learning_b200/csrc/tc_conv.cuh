@@ -75,6 +75,9 @@ struct ConvGemmParams {
   int fold;                     // pixel-pair form: the nc columns are 2 x (nc/2) real channels (column c -> channel c % (nc/2))
   int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
   int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
+  int wstream;                  // weights travel with the activations, one tap tile per pipeline slot, instead of staying
+                                // resident: a CTA that owns a single tile never reuses a resident copy, and without it
+                                // the 64-channel layers get a 4-deep ring inside the 113 KB footprint instead of 2
 };
 
 // Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
@@ -187,13 +190,16 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   if (threadIdx.x == 0) WACIL_STAMP(0);  // kernel entry
   const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
   const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
-  const uint32_t stage_bytes = p.tps * a_bytes;  // one pipeline stage = tps tap tiles
   const int groups = (p.taps + p.tps - 1) / p.tps;
   const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
   const uint32_t w_bytes = p.taps * w_tap_bytes;
+  const bool ws = p.wstream != 0;
+  // one pipeline stage = tps activation tap tiles (+ their tps weight tap tiles when the weights are streamed)
+  const uint32_t stage_w_off = p.tps * a_bytes;
+  const uint32_t stage_bytes = stage_w_off + (ws ? p.tps * w_tap_bytes : 0u);
 
   uint8_t* smem_w = smem;
-  uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023u);
+  uint8_t* smem_a = smem + (ws ? 0u : ((w_bytes + 1023) & ~1023u));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * stage_bytes);
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + p.stages;      // [stages]
@@ -204,12 +210,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [13*64] per-channel scratch
 
-  // Fused modes keep a second TMEM region beside the accumulators (same tile/column indexing, offset stash_col): what the
-  // post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: x-hat) is staged there in phase 1,
-  // while the main loop still runs, so that phase 2 touches no global memory but its stores.
+  // Fused modes keep a second TMEM region beside the accumulators (offset stash_col, 8 columns of packed bf16 pairs per
+  // 16-channel chunk): what the post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: y, for
+  // x-hat) is staged there in phase 1, exactly as it was read from HBM, so that phase 2 touches no global memory but
+  // its stores.
   const bool stash = (p.epi == EPI_BNBWD) || (p.epi == EPI_BN_TRAIN && p.res != nullptr);
   const uint32_t stash_col = static_cast<uint32_t>(nacc * p.nc);
-  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 2u : 1u));
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 3u : 2u) / 2u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 
   // Programmatic dependent launch: everything above (and the weight TMA when the weights are older than the upstream
   // grid) overlaps the tail of the previous kernel; its outputs are only touched after griddepcontrol.wait.
-  if (p.pdl && p.w_early && warp == 0 && lane == 0) {
+  if (p.pdl && p.w_early && !ws && warp == 0 && lane == 0) {
     mbar_expect_tx(wfull, w_bytes);
     for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
   }
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      if (!(p.pdl && p.w_early)) {
+      if (!ws && !(p.pdl && p.w_early)) {
         mbar_expect_tx(wfull, w_bytes);
         for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
       }
@@ -260,11 +267,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           const int tap_lo = g * p.tps;
           const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], ntap * a_bytes);
+          mbar_expect_tx(&full[stage], ntap * (a_bytes + (ws ? w_tap_bytes : 0u)));
           for (int j = 0; j < ntap; ++j) {
             int c0, c1, c2, c3, c4;
             tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
             tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+            if (ws)
+              tma_load_2d(smem_a + stage * stage_bytes + stage_w_off + j * w_tap_bytes, &mapW, &full[stage], 0,
+                          (tap_lo + j) * p.nc);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -284,8 +294,10 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       const uint64_t desc_hi = umma_smem_desc(0, 16, sbo, layout);
       const uint32_t a_ring_addr = smem_u32(smem_a);
       const uint32_t w_base_addr = smem_u32(smem_w);
-      mbar_wait(wfull, 0);
-      tc_fence_after();
+      if (!ws) {
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+      }
       WACIL_STAMP(3);  // weights landed
       int stage = 0;
       uint32_t phase = 0;
@@ -303,7 +315,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
           // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
           uint64_t adesc = desc_hi | ((a_ring_addr + stage * stage_bytes) >> 4);
-          uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
+          uint64_t bdesc = desc_hi | ((ws ? a_ring_addr + stage * stage_bytes + stage_w_off
+                                             : w_base_addr + tap_lo * w_tap_bytes) >> 4);
           for (int j = 0; j < ntap; ++j) {
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k)
@@ -347,56 +360,61 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    // The CTA's tiles t = 0 .. ntl-1 (tile blockIdx + t * gridDim) x their nc/16 column chunks form one sequence of
+    // chunks q: accumulator columns q*16 .. q*16+15, stash columns stash_col + q*8 .. +7.
+    const int cpt = p.nc >> 4;                                  // chunks per tile: 1, 2 or 4 (nc = 16, 32, 64)
+    const int cshift = cpt == 4 ? 2 : (cpt == 2 ? 1 : 0);
+    const int ntl = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int Q = ntl << cshift;
+    const uint32_t acc_t = tmem_base + lane_base;
+    const uint32_t sta_t = tmem_base + lane_base + stash_col;
+    auto chunk_pix = [&](int q, int& c0) {
+      c0 = (q & (cpt - 1)) << 4;
+      return (static_cast<int>(blockIdx.x) + (q >> cshift) * static_cast<int>(gridDim.x)) * 128 + m;
+    };
     // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN); stages phase 2's operands
-    int as = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
-      const int pix = tile * 128 + m;
-      const bool valid = pix < p.num_pixels;
-      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      const __nv_bfloat16* gres_ptr = nullptr;
-      const __nv_bfloat16* res_ptr = nullptr;
-      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
-        if (p.gres_mode == 1) {
-          gres_ptr = p.g_res + base;
-        } else {
-          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
-            if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
-          } else if (((w | h) & 1) == 0) {
-            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+    if (p.epi == EPI_BN_TRAIN) {
+      int q = 0;
+      for (int t = 0; t < ntl; ++t) {
+        int c0;
+        const int pix = chunk_pix(q, c0);
+        const bool valid = pix < p.num_pixels;
+        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+        if (stash) {
+          // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
+          const __nv_bfloat16* res_ptr = nullptr;
+          if (valid) {
+            if (p.res_stride == 1) {
+              res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
+            } else {
+              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+              res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+            }
+          }
+          for (int cc = 0; cc < cpt; ++cc) {
+            uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (res_ptr != nullptr && cc * 16 < p.res_c) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res_ptr + cc * 16);
+              const uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
+              r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+            }
+            tmem_st8(sta_t + (q + cc) * 8, r);
           }
         }
-      }
-      if (p.epi == EPI_BN_TRAIN && p.res != nullptr && valid) {
-        if (p.res_stride == 1) {
-          res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
-        } else {
-          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
-        }
-      }
-      if (p.epi == EPI_BN_TRAIN && stash) {
-        // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
-        for (int c0 = 0; c0 < p.nc; c0 += 16) {
-          float r[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = 0.f;
-          if (res_ptr != nullptr && c0 < p.res_c) load16_bf16(res_ptr + c0, r);
-          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
-        }
-      }
-      mbar_wait(&accfull[as], 0);
-      tc_fence_after();
-      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
-      for (int c0 = 0; c0 < p.nc; c0 += 16) {
-        float v[16], s2[16];
-        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (p.epi == EPI_BN_TRAIN) {
+        mbar_wait(&accfull[t], 0);
+        tc_fence_after();
+        if (tid128 == 0 && t == 0) WACIL_STAMP(6);  // first accumulator complete
+        uint32_t A[16], An[16];
+        tmem_ld16_issue(acc_t + q * 16, A);
+        tmem_ld_wait16(A);
+        for (int cc = 0; cc < cpt; ++cc) {
+          if (cc + 1 < cpt) tmem_ld16_issue(acc_t + (q + cc + 1) * 16, An);  // next chunk's accumulator under this one's math
+          float v[16], s2[16];
           __align__(16) __nv_bfloat16 ob[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(__uint_as_float(A[i]));
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + base + c0);
+            uint4* op = reinterpret_cast<uint4*>(p.out + base + cc * 16);
             op[0] = reinterpret_cast<const uint4*>(ob)[0];
             op[1] = reinterpret_cast<const uint4*>(ob)[1];
           }
@@ -406,38 +424,96 @@ __global__ void __launch_bounds__(kConvThreads, 2)
             v[i] = r;
             s2[i] = r * r;
           }
+          const float t1 = warp_colsum16(v, lane);
+          const float t2 = warp_colsum16(s2, lane);
+          if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
+            const int c = cc * 16 + warp_colsum16_col(lane);
+            s_part[(quarter * 2 + 0) * 64 + c] += t1;
+            s_part[(quarter * 2 + 1) * 64 + c] += t2;
+          }
+          if (cc + 1 < cpt) {
+            tmem_ld_wait16(An);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) A[i] = An[i];
+          }
+        }
+        q += cpt;
+      }
+    } else {
+      // BNBWD: the global operands of chunk q+1 (ReLU mask source a, conv output y, shortcut gradient) are requested
+      // before chunk q is processed, across tile boundaries and ahead of the accumulators they will meet.
+      struct Raw { uint4 a0, a1, y0, y1, g0, g1; };
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      auto gl_issue = [&](int q, Raw& R) {
+        int c0;
+        const int pix = chunk_pix(q, c0);
+        R.a0 = R.a1 = R.y0 = R.y1 = R.g0 = R.g1 = z4;
+        if (pix >= p.num_pixels) return;
+        const size_t off = static_cast<size_t>(pix) * p.nc + c0;
+        const uint4* ap = reinterpret_cast<const uint4*>(p.act_in + off);
+        const uint4* yp = reinterpret_cast<const uint4*>(p.y_in + off);
+        R.a0 = __ldg(ap); R.a1 = __ldg(ap + 1);
+        R.y0 = __ldg(yp); R.y1 = __ldg(yp + 1);
+        if (p.g_res == nullptr) return;
+        const __nv_bfloat16* gp = nullptr;
+        if (p.gres_mode == 1) {
+          gp = p.g_res + off;
         } else {
-          float a[16], yv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { a[i] = 0.f; yv[i] = 0.f; }
-          if (valid) {
-            load16_bf16(p.act_in + base + c0, a);
-            load16_bf16(p.y_in + base + c0, yv);
-            if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {  // fold: only the even pixel's half
-              float r[16];
-              load16_bf16(gres_ptr + c0, r);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += r[i];
-            }
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
+            if ((h & 1) == 0 && c0 < ncr)
+              gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr) + c0;
+          } else if (((w | h) & 1) == 0) {
+            gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc) + c0;
           }
+        }
+        if (gp != nullptr) {
+          const uint4* gq = reinterpret_cast<const uint4*>(gp);
+          R.g0 = __ldg(gq); R.g1 = __ldg(gq + 1);
+        }
+      };
+      Raw Rc, Rn;
+      if (Q > 0) gl_issue(0, Rc);
+      for (int q = 0; q < Q; ++q) {
+        const int c0 = (q & (cpt - 1)) << 4;
+        if (c0 == 0) {
+          mbar_wait(&accfull[q >> cshift], 0);
+          tc_fence_after();
+          if (tid128 == 0 && q == 0) WACIL_STAMP(6);  // first accumulator complete
+        }
+        uint32_t A[16];
+        tmem_ld16_issue(acc_t + q * 16, A);
+        if (q + 1 < Q) gl_issue(q + 1, Rn);
+        tmem_ld_wait16(A);
+        float v[16], s2[16];
+        {
+          const uint32_t aw[8] = {Rc.a0.x, Rc.a0.y, Rc.a0.z, Rc.a0.w, Rc.a1.x, Rc.a1.y, Rc.a1.z, Rc.a1.w};
+          const uint32_t yw[8] = {Rc.y0.x, Rc.y0.y, Rc.y0.z, Rc.y0.w, Rc.y1.x, Rc.y1.y, Rc.y1.z, Rc.y1.w};
+          const uint32_t gw[8] = {Rc.g0.x, Rc.g0.y, Rc.g0.z, Rc.g0.w, Rc.g1.x, Rc.g1.y, Rc.g1.z, Rc.g1.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = (valid && a[i] > 0.f) ? v[i] : 0.f;                             // gz (masked gradient)
-            yv[i] = valid ? (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;       // x-hat
+          for (int i = 0; i < 8; ++i) {  // bf16 -> fp32 is a 16-bit shift; an all-zero (invalid) row masks itself
+            const float a_lo = __uint_as_float(aw[i] << 16), a_hi = __uint_as_float(aw[i] & 0xffff0000u);
+            const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
+            const float g_lo = __uint_as_float(gw[i] << 16), g_hi = __uint_as_float(gw[i] & 0xffff0000u);
+            const float gz_lo = (a_lo > 0.f) ? __uint_as_float(A[2 * i]) + g_lo : 0.f;       // gz (masked gradient)
+            const float gz_hi = (a_hi > 0.f) ? __uint_as_float(A[2 * i + 1]) + g_hi : 0.f;
+            v[2 * i] = gz_lo;
+            v[2 * i + 1] = gz_hi;
+            s2[2 * i] = gz_lo * ((y_lo - s_mean[c0 + 2 * i]) * s_rstd[c0 + 2 * i]);           // gz * x-hat
+            s2[2 * i + 1] = gz_hi * ((y_hi - s_mean[c0 + 2 * i + 1]) * s_rstd[c0 + 2 * i + 1]);
           }
-          // phase 2 reads both back from TMEM: gz replaces the accumulator, x-hat goes to the stash region
-          tmem_st16(tmem_base + lane_base + as * p.nc + c0, v);
-          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, yv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s2[i] = v[i] * yv[i];
+          // phase 2 reads both back from TMEM: gz replaces the accumulator, y (as loaded) goes to the stash region
+          tmem_st16(acc_t + q * 16, v);
+          tmem_st8(sta_t + q * 8, yw);
         }
         const float t1 = warp_colsum16(v, lane);
         const float t2 = warp_colsum16(s2, lane);
-        if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
+        if ((lane & 1) == 0) {
           const int c = c0 + warp_colsum16_col(lane);
           s_part[(quarter * 2 + 0) * 64 + c] += t1;
           s_part[(quarter * 2 + 1) * 64 + c] += t2;
         }
+        Rc = Rn;
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -477,43 +553,69 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash)
-    as = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
-      const int pix = tile * 128 + m;
-      const bool valid = pix < p.num_pixels;
-      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      size_t up_base = 0;
-      if (p.epi == EPI_BNBWD && p.gy_up != nullptr) {
-        const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-        up_base = ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc;
+    // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash);
+    //                  the TMEM loads of chunk q+1 are issued before chunk q is processed
+    {
+      uint32_t A[16], An[16], S[8], Sn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) S[i] = Sn[i] = 0u;
+      if (Q > 0) {
+        tmem_ld16_issue(acc_t, A);
+        if (stash) tmem_ld8_issue(sta_t, S);
+        tmem_ld_wait16(A);
+        tmem_ld_wait8(S);
       }
-      for (int c0 = 0; c0 < p.nc; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
+      for (int q = 0; q < Q; ++q) {
+        if (q + 1 < Q) {
+          tmem_ld16_issue(acc_t + (q + 1) * 16, An);
+          if (stash) tmem_ld8_issue(sta_t + (q + 1) * 8, Sn);
+        }
+        int c0;
+        const int pix = chunk_pix(q, c0);
+        const bool valid = pix < p.num_pixels;
+        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc + c0;
+        float o[16];
         if (p.epi == EPI_BN_TRAIN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
-          if (stash) {
-            float r[16];
-            tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          for (int i = 0; i < 8; ++i) {
+            const float r_lo = __uint_as_float(S[i] << 16), r_hi = __uint_as_float(S[i] & 0xffff0000u);  // 0 when no stash
+            const float v_lo = __bfloat162float(__float2bfloat16_rn(__uint_as_float(A[2 * i])));
+            const float v_hi = __bfloat162float(__float2bfloat16_rn(__uint_as_float(A[2 * i + 1])));
+            o[2 * i] = fmaxf(v_lo * s_c0[c0 + 2 * i] + s_c1[c0 + 2 * i] + r_lo, 0.f);
+            o[2 * i + 1] = fmaxf(v_hi * s_c0[c0 + 2 * i + 1] + s_c1[c0 + 2 * i + 1] + r_hi, 0.f);
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          if (valid) store16_bf16(p.act_out + base + c0, v);
+          if (valid) store16_bf16(p.act_out + base, o);
         } else {
-          float xh[16], o[16];
-          tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, xh);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xh[i] * s_c2[c0 + i]);
-          if (valid) {
-            store16_bf16(p.gy + base + c0, o);
-            if (p.gy_up != nullptr) store16_bf16(p.gy_up + up_base + c0, o);
-            if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
+          for (int i = 0; i < 8; ++i) {
+            const float y_lo = __uint_as_float(S[i] << 16), y_hi = __uint_as_float(S[i] & 0xffff0000u);
+            const float xh_lo = (y_lo - s_mean[c0 + 2 * i]) * s_rstd[c0 + 2 * i];
+            const float xh_hi = (y_hi - s_mean[c0 + 2 * i + 1]) * s_rstd[c0 + 2 * i + 1];
+            o[2 * i] = s_c0[c0 + 2 * i] * (__uint_as_float(A[2 * i]) - s_c1[c0 + 2 * i] - xh_lo * s_c2[c0 + 2 * i]);
+            o[2 * i + 1] = s_c0[c0 + 2 * i + 1] *
+                           (__uint_as_float(A[2 * i + 1]) - s_c1[c0 + 2 * i + 1] - xh_hi * s_c2[c0 + 2 * i + 1]);
           }
+          if (valid) {
+            store16_bf16(p.gy + base, o);
+            if (p.gy_up != nullptr) {
+              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+              store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
+            }
+            if (p.gz != nullptr) {
+              float gzv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) gzv[i] = __uint_as_float(A[i]);
+              store16_bf16(p.gz + base, gzv);
+            }
+          }
+        }
+        if (q + 1 < Q) {
+          tmem_ld_wait16(An);
+          tmem_ld_wait8(Sn);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) A[i] = An[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) S[i] = Sn[i];
         }
       }
     }
@@ -862,9 +964,9 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 }
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
-  const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
-  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
-         13 * 64 * 4 + 64;
+  const size_t w = p.wstream ? 0 : (((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023));
+  const size_t stage = (size_t)p.tps * (128 * p.kc * 2 + (p.wstream ? p.nc * p.kc * 2 : 0));
+  return 1024 + w + (size_t)p.stages * stage + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 + 13 * 64 * 4 + 64;
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
@@ -875,10 +977,11 @@ inline size_t conv_smem_bytes(const ConvGemmParams& p) {
 // those variants are as fast or faster in isolation: the kernels are latency-bound, a second resident CTA hides it.
 // (The occupancy API reports 1 CTA/SM for any tcgen05 kernel — csrc/occ_probe.cu — so a cooperative grid is <= #SMs.)
 constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
-inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
-  const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
+inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax,
+                               bool wstream = false) {
+  const size_t w = wstream ? 0 : (((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023));
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch
-  const size_t tap_bytes = (size_t)128 * kc * 2;
+  const size_t tap_bytes = (size_t)128 * kc * 2 + (wstream ? (size_t)nc * kc * 2 : 0);
   const int cand[3] = {9, 3, 1};
   tps = 1;
   stages = 2;

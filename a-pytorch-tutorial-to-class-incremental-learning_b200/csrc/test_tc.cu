@@ -115,7 +115,12 @@ static int run_conv(const Case& c) {
   p.num_pixels = (int)npix;
   p.num_tiles = (int)((npix + 127) / 128);
   p.Ho = Ho; p.Wo = Wo;
-  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
+  {
+    const char* ev = getenv("WACIL_WSTREAM");
+    const bool on = !(ev && ev[0] == '0');
+    p.wstream = (on && (size_t)c.taps * c.nc * c.kc * 2 > 48 * 1024 && p.num_tiles <= 148 && (c.nc * c.kc * 2) % 1024 == 0) ? 1 : 0;
+  }
+  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages, kConvSmemMax, p.wstream != 0);
   if (g_stages > 0) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
   p.epi = c.epi;
   p.acc_stages = 2;

@@ -250,7 +250,15 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.num_tiles = (p.num_pixels + 127) / 128;
   p.Ho = Ho;
   p.Wo = Wo;
-  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
+  // Weight streaming (WACIL_WSTREAM=0 disables): when every CTA owns a single tile a resident weight copy is never
+  // reused; for the 64-channel layers (72 KB of taps) streaming them beside the activations doubles the ring depth.
+  {
+    static int ws_env = -2;
+    if (ws_env == -2) { const char* ev = getenv("WACIL_WSTREAM"); ws_env = ev ? (ev[0] == '0' ? 0 : 1) : 1; }
+    const size_t wbytes = static_cast<size_t>(taps) * nc * kc * 2;
+    p.wstream = (ws_env && wbytes > 48 * 1024 && p.num_tiles <= num_sms() && (nc * kc * 2) % 1024 == 0) ? 1 : 0;
+  }
+  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages, kConvSmemMax, p.wstream != 0);
   p.epi = epi;
   p.acc_stages = 2;
   p.res_stride = 1;
