@@ -45,7 +45,10 @@ struct ConvGemmParams {
   int tps;        // taps per pipeline stage (one mbarrier round trip per stage)
   int epi;
   __nv_bfloat16* out;        // [num_pixels][nc]
-  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics)
+  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics).  Fused modes: [stat_reps][2*ncr] replicas of
+                             // the per-channel sums (BN_TRAIN: sum, sumsq; BNBWD: d-beta, d-gamma), zero before the launch
+  int stat_reps;             // CTA b adds into replica b % stat_reps (each replica its own 128-byte lines): the 2*nc*grid
+                             // reductions of a layer no longer queue on one L2 atomic unit
   const float* bias;         // [nc] (EPI_INFER)
   const __nv_bfloat16* res;  // residual (EPI_INFER) or nullptr
   int res_stride;            // 1: same geometry as out; 2: residual is [N][2Ho][2Wo][res_c] sampled at even pixels
@@ -75,15 +78,13 @@ struct ConvGemmParams {
   int fold;                     // pixel-pair form: the nc columns are 2 x (nc/2) real channels (column c -> channel c % (nc/2))
   int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
   int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
-  int wstream;                  // weights travel with the activations, one tap tile per pipeline slot, instead of staying
-                                // resident: a CTA that owns a single tile never reuses a resident copy, and without it
-                                // the 64-channel layers get a 4-deep ring inside the 113 KB footprint instead of 2
 };
 
 // Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
 // cooperative launch (all CTAs co-resident).  bar[0], bar[1] are zero at rest; bounded spin (a bug must trap, not hang).
+template <int ET>
 __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
   if (tid128 == 0) {
     // arrive with release semantics (cumulative over the partner threads' writes ordered by the bar.sync above),
     // then poll with acquire loads: two L2 round trips instead of fence + atomic + atomic polling
@@ -98,7 +99,7 @@ __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
       }
     } while (seen < gridDim.x);
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
   if (tid128 == 0) {
     // self-reset, off the critical path: the last CTA to check out knows every CTA has left the polling loop
     if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
@@ -178,10 +179,14 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
 }
 
 constexpr int kConvThreads = 192;
+constexpr int kConvThreadsW8 = 320;  // the fused modes may run with 8 epilogue warps (two per TMEM lane quarter)
 
-__global__ void __launch_bounds__(kConvThreads, 2)
-    conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                     const ConvGemmParams p) {
+// EW epilogue warps (4 or 8).  With 8, warps 2..5 and 6..9 share the four lane quarters and take alternate 16-column
+// chunks of the fused epilogues: the phases are issue-bound with one warp per scheduler.
+template <int EW>
+__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CUtensorMap& mapW, const ConvGemmParams& p) {
+  constexpr int ET = EW * 32;  // epilogue threads
+  constexpr int NH = EW / 4;   // warps per lane quarter
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -190,16 +195,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   if (threadIdx.x == 0) WACIL_STAMP(0);  // kernel entry
   const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
   const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
+  const uint32_t stage_bytes = p.tps * a_bytes;  // one pipeline stage = tps tap tiles
   const int groups = (p.taps + p.tps - 1) / p.tps;
   const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
   const uint32_t w_bytes = p.taps * w_tap_bytes;
-  const bool ws = p.wstream != 0;
-  // one pipeline stage = tps activation tap tiles (+ their tps weight tap tiles when the weights are streamed)
-  const uint32_t stage_w_off = p.tps * a_bytes;
-  const uint32_t stage_bytes = stage_w_off + (ws ? p.tps * w_tap_bytes : 0u);
 
   uint8_t* smem_w = smem;
-  uint8_t* smem_a = smem + (ws ? 0u : ((w_bytes + 1023) & ~1023u));
+  uint8_t* smem_a = smem + ((w_bytes + 1023) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + p.stages * stage_bytes);
   uint64_t* full = bars;                  // [stages]
   uint64_t* empty = bars + p.stages;      // [stages]
@@ -208,15 +210,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   uint64_t* accfull = wfull + 1;          // [nacc]
   uint64_t* accempty = accfull + nacc;    // [nacc]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [13*64] per-channel scratch
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [(2*EW+5)*64] per-channel scratch
 
-  // Fused modes keep a second TMEM region beside the accumulators (offset stash_col, 8 columns of packed bf16 pairs per
-  // 16-channel chunk): what the post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: y, for
-  // x-hat) is staged there in phase 1, exactly as it was read from HBM, so that phase 2 touches no global memory but
-  // its stores.
+  // Fused modes keep a second TMEM region beside the accumulators (same tile/column indexing, offset stash_col): what the
+  // post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: x-hat) is staged there in phase 1,
+  // while the main loop still runs, so that phase 2 touches no global memory but its stores.
   const bool stash = (p.epi == EPI_BNBWD) || (p.epi == EPI_BN_TRAIN && p.res != nullptr);
   const uint32_t stash_col = static_cast<uint32_t>(nacc * p.nc);
-  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 3u : 2u) / 2u);
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 2u : 1u));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 13 * 64; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < (2 * EW + 5) * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
 
   // Programmatic dependent launch: everything above (and the weight TMA when the weights are older than the upstream
   // grid) overlaps the tail of the previous kernel; its outputs are only touched after griddepcontrol.wait.
-  if (p.pdl && p.w_early && !ws && warp == 0 && lane == 0) {
+  if (p.pdl && p.w_early && warp == 0 && lane == 0) {
     mbar_expect_tx(wfull, w_bytes);
     for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
   }
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      if (!ws && !(p.pdl && p.w_early)) {
+      if (!(p.pdl && p.w_early)) {
         mbar_expect_tx(wfull, w_bytes);
         for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
       }
@@ -267,14 +268,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           const int tap_lo = g * p.tps;
           const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], ntap * (a_bytes + (ws ? w_tap_bytes : 0u)));
+          mbar_expect_tx(&full[stage], ntap * a_bytes);
           for (int j = 0; j < ntap; ++j) {
             int c0, c1, c2, c3, c4;
             tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
             tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
-            if (ws)
-              tma_load_2d(smem_a + stage * stage_bytes + stage_w_off + j * w_tap_bytes, &mapW, &full[stage], 0,
-                          (tap_lo + j) * p.nc);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -294,10 +292,8 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       const uint64_t desc_hi = umma_smem_desc(0, 16, sbo, layout);
       const uint32_t a_ring_addr = smem_u32(smem_a);
       const uint32_t w_base_addr = smem_u32(smem_w);
-      if (!ws) {
-        mbar_wait(wfull, 0);
-        tc_fence_after();
-      }
+      mbar_wait(wfull, 0);
+      tc_fence_after();
       WACIL_STAMP(3);  // weights landed
       int stage = 0;
       uint32_t phase = 0;
@@ -315,8 +311,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
           if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
           // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
           uint64_t adesc = desc_hi | ((a_ring_addr + stage * stage_bytes) >> 4);
-          uint64_t bdesc = desc_hi | ((ws ? a_ring_addr + stage * stage_bytes + stage_w_off
-                                             : w_base_addr + tap_lo * w_tap_bytes) >> 4);
+          uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
           for (int j = 0; j < ntap; ++j) {
 #pragma unroll 4
             for (int k = 0; k < ksteps; ++k)
@@ -341,80 +336,79 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   } else if (p.epi >= EPI_BN_TRAIN) {
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
     const int quarter = warp & 3;
+    const int ew = warp - 2;          // epilogue warp index
+    const int half = ew >> 2;         // which of the NH warps of this lane quarter
     const int m = quarter * 32 + lane;
-    const int tid128 = threadIdx.x - 64;
+    const int tid128 = threadIdx.x - 64;  // index among the ET epilogue threads
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    float* s_part = s_stats;          // [4 warps][2][64] private per-warp partial sums (zeroed at kernel start)
-    float* s_c0 = s_stats + 512;      // [nc] scale    | k = gamma * rstd
-    float* s_c1 = s_stats + 576;      // [nc] shift    | d-beta / M
-    float* s_c2 = s_stats + 640;      // [nc]          | d-gamma / M
-    float* s_mean = s_stats + 704;    // [nc]
-    float* s_rstd = s_stats + 768;    // [nc]
+    float* s_part = s_stats;                    // [EW warps][2][64] private per-warp partial sums (zeroed at kernel start)
+    float* s_c0 = s_stats + EW * 128;           // [nc] scale    | k = gamma * rstd
+    float* s_c1 = s_stats + EW * 128 + 64;      // [nc] shift    | d-beta / M
+    float* s_c2 = s_stats + EW * 128 + 128;     // [nc]          | d-gamma / M
+    float* s_mean = s_stats + EW * 128 + 192;   // [nc]
+    float* s_rstd = s_stats + EW * 128 + 256;   // [nc]
     // Pixel-pair ("fold") form: a row is two horizontally adjacent pixels, its nc columns are (pixel parity, channel);
     // BatchNorm parameters and statistics belong to the ncr = nc/2 real channels, a row counts as two pixels.
     const int ncr = p.fold ? p.nc / 2 : p.nc;
     if (p.epi == EPI_BNBWD) {
-      for (int c = tid128; c < p.nc; c += 128) {
+      for (int c = tid128; c < p.nc; c += ET) {
         s_mean[c] = p.saved[c % ncr];
         s_rstd[c] = p.saved[ncr + c % ncr];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     }
-    // The CTA's tiles t = 0 .. ntl-1 (tile blockIdx + t * gridDim) x their nc/16 column chunks form one sequence of
-    // chunks q: accumulator columns q*16 .. q*16+15, stash columns stash_col + q*8 .. +7.
-    const int cpt = p.nc >> 4;                                  // chunks per tile: 1, 2 or 4 (nc = 16, 32, 64)
-    const int cshift = cpt == 4 ? 2 : (cpt == 2 ? 1 : 0);
-    const int ntl = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    const int Q = ntl << cshift;
-    const uint32_t acc_t = tmem_base + lane_base;
-    const uint32_t sta_t = tmem_base + lane_base + stash_col;
-    auto chunk_pix = [&](int q, int& c0) {
-      c0 = (q & (cpt - 1)) << 4;
-      return (static_cast<int>(blockIdx.x) + (q >> cshift) * static_cast<int>(gridDim.x)) * 128 + m;
-    };
     // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN); stages phase 2's operands
-    if (p.epi == EPI_BN_TRAIN) {
-      int q = 0;
-      for (int t = 0; t < ntl; ++t) {
-        int c0;
-        const int pix = chunk_pix(q, c0);
-        const bool valid = pix < p.num_pixels;
-        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-        if (stash) {
-          // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
-          const __nv_bfloat16* res_ptr = nullptr;
-          if (valid) {
-            if (p.res_stride == 1) {
-              res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
-            } else {
-              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-              res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
-            }
-          }
-          for (int cc = 0; cc < cpt; ++cc) {
-            uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            if (res_ptr != nullptr && cc * 16 < p.res_c) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res_ptr + cc * 16);
-              const uint4 lo = __ldg(rp), hi = __ldg(rp + 1);
-              r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
-            }
-            tmem_st8(sta_t + (q + cc) * 8, r);
+    int as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      const __nv_bfloat16* gres_ptr = nullptr;
+      const __nv_bfloat16* res_ptr = nullptr;
+      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
+        if (p.gres_mode == 1) {
+          gres_ptr = p.g_res + base;
+        } else {
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
+            if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
+          } else if (((w | h) & 1) == 0) {
+            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
           }
         }
-        mbar_wait(&accfull[t], 0);
-        tc_fence_after();
-        if (tid128 == 0 && t == 0) WACIL_STAMP(6);  // first accumulator complete
-        uint32_t A[16], An[16];
-        tmem_ld16_issue(acc_t + q * 16, A);
-        tmem_ld_wait16(A);
-        for (int cc = 0; cc < cpt; ++cc) {
-          if (cc + 1 < cpt) tmem_ld16_issue(acc_t + (q + cc + 1) * 16, An);  // next chunk's accumulator under this one's math
-          float v[16], s2[16];
+      }
+      if (p.epi == EPI_BN_TRAIN && p.res != nullptr && valid) {
+        if (p.res_stride == 1) {
+          res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
+        } else {
+          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+          res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
+        }
+      }
+      if (p.epi == EPI_BN_TRAIN && stash) {
+        // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
+        for (int c0 = 0; c0 < p.nc; c0 += 16) {
+          if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
+          float r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = 0.f;
+          if (res_ptr != nullptr && c0 < p.res_c) load16_bf16(res_ptr + c0, r);
+          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
+        }
+      }
+      mbar_wait(&accfull[as], 0);
+      tc_fence_after();
+      if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
+        float v[16], s2[16];
+        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
+        if (p.epi == EPI_BN_TRAIN) {
           __align__(16) __nv_bfloat16 ob[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(__uint_as_float(A[i]));
+          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
           if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + base + cc * 16);
+            uint4* op = reinterpret_cast<uint4*>(p.out + base + c0);
             op[0] = reinterpret_cast<const uint4*>(ob)[0];
             op[1] = reinterpret_cast<const uint4*>(ob)[1];
           }
@@ -424,203 +418,146 @@ __global__ void __launch_bounds__(kConvThreads, 2)
             v[i] = r;
             s2[i] = r * r;
           }
-          const float t1 = warp_colsum16(v, lane);
-          const float t2 = warp_colsum16(s2, lane);
-          if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
-            const int c = cc * 16 + warp_colsum16_col(lane);
-            s_part[(quarter * 2 + 0) * 64 + c] += t1;
-            s_part[(quarter * 2 + 1) * 64 + c] += t2;
-          }
-          if (cc + 1 < cpt) {
-            tmem_ld_wait16(An);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) A[i] = An[i];
-          }
-        }
-        q += cpt;
-      }
-    } else {
-      // BNBWD: the global operands of chunk q+1 (ReLU mask source a, conv output y, shortcut gradient) are requested
-      // before chunk q is processed, across tile boundaries and ahead of the accumulators they will meet.
-      struct Raw { uint4 a0, a1, y0, y1, g0, g1; };
-      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-      auto gl_issue = [&](int q, Raw& R) {
-        int c0;
-        const int pix = chunk_pix(q, c0);
-        R.a0 = R.a1 = R.y0 = R.y1 = R.g0 = R.g1 = z4;
-        if (pix >= p.num_pixels) return;
-        const size_t off = static_cast<size_t>(pix) * p.nc + c0;
-        const uint4* ap = reinterpret_cast<const uint4*>(p.act_in + off);
-        const uint4* yp = reinterpret_cast<const uint4*>(p.y_in + off);
-        R.a0 = __ldg(ap); R.a1 = __ldg(ap + 1);
-        R.y0 = __ldg(yp); R.y1 = __ldg(yp + 1);
-        if (p.g_res == nullptr) return;
-        const __nv_bfloat16* gp = nullptr;
-        if (p.gres_mode == 1) {
-          gp = p.g_res + off;
         } else {
-          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
-            if ((h & 1) == 0 && c0 < ncr)
-              gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr) + c0;
-          } else if (((w | h) & 1) == 0) {
-            gp = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc) + c0;
-          }
-        }
-        if (gp != nullptr) {
-          const uint4* gq = reinterpret_cast<const uint4*>(gp);
-          R.g0 = __ldg(gq); R.g1 = __ldg(gq + 1);
-        }
-      };
-      Raw Rc, Rn;
-      if (Q > 0) gl_issue(0, Rc);
-      for (int q = 0; q < Q; ++q) {
-        const int c0 = (q & (cpt - 1)) << 4;
-        if (c0 == 0) {
-          mbar_wait(&accfull[q >> cshift], 0);
-          tc_fence_after();
-          if (tid128 == 0 && q == 0) WACIL_STAMP(6);  // first accumulator complete
-        }
-        uint32_t A[16];
-        tmem_ld16_issue(acc_t + q * 16, A);
-        if (q + 1 < Q) gl_issue(q + 1, Rn);
-        tmem_ld_wait16(A);
-        float v[16], s2[16];
-        {
-          const uint32_t aw[8] = {Rc.a0.x, Rc.a0.y, Rc.a0.z, Rc.a0.w, Rc.a1.x, Rc.a1.y, Rc.a1.z, Rc.a1.w};
-          const uint32_t yw[8] = {Rc.y0.x, Rc.y0.y, Rc.y0.z, Rc.y0.w, Rc.y1.x, Rc.y1.y, Rc.y1.z, Rc.y1.w};
-          const uint32_t gw[8] = {Rc.g0.x, Rc.g0.y, Rc.g0.z, Rc.g0.w, Rc.g1.x, Rc.g1.y, Rc.g1.z, Rc.g1.w};
+          float a[16], yv[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {  // bf16 -> fp32 is a 16-bit shift; an all-zero (invalid) row masks itself
-            const float a_lo = __uint_as_float(aw[i] << 16), a_hi = __uint_as_float(aw[i] & 0xffff0000u);
-            const float y_lo = __uint_as_float(yw[i] << 16), y_hi = __uint_as_float(yw[i] & 0xffff0000u);
-            const float g_lo = __uint_as_float(gw[i] << 16), g_hi = __uint_as_float(gw[i] & 0xffff0000u);
-            const float gz_lo = (a_lo > 0.f) ? __uint_as_float(A[2 * i]) + g_lo : 0.f;       // gz (masked gradient)
-            const float gz_hi = (a_hi > 0.f) ? __uint_as_float(A[2 * i + 1]) + g_hi : 0.f;
-            v[2 * i] = gz_lo;
-            v[2 * i + 1] = gz_hi;
-            s2[2 * i] = gz_lo * ((y_lo - s_mean[c0 + 2 * i]) * s_rstd[c0 + 2 * i]);           // gz * x-hat
-            s2[2 * i + 1] = gz_hi * ((y_hi - s_mean[c0 + 2 * i + 1]) * s_rstd[c0 + 2 * i + 1]);
+          for (int i = 0; i < 16; ++i) { a[i] = 0.f; yv[i] = 0.f; }
+          if (valid) {
+            load16_bf16(p.act_in + base + c0, a);
+            load16_bf16(p.y_in + base + c0, yv);
+            if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {  // fold: only the even pixel's half
+              float r[16];
+              load16_bf16(gres_ptr + c0, r);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
           }
-          // phase 2 reads both back from TMEM: gz replaces the accumulator, y (as loaded) goes to the stash region
-          tmem_st16(acc_t + q * 16, v);
-          tmem_st8(sta_t + q * 8, yw);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = (valid && a[i] > 0.f) ? v[i] : 0.f;                             // gz (masked gradient)
+            yv[i] = valid ? (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;       // x-hat
+          }
+          // phase 2 reads both back from TMEM: gz replaces the accumulator, x-hat goes to the stash region
+          tmem_st16(tmem_base + lane_base + as * p.nc + c0, v);
+          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, yv);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s2[i] = v[i] * yv[i];
         }
         const float t1 = warp_colsum16(v, lane);
         const float t2 = warp_colsum16(s2, lane);
-        if ((lane & 1) == 0) {
+        if ((lane & 1) == 0) {  // this lane owns column c of this warp's private partial row: plain read-modify-write
           const int c = c0 + warp_colsum16_col(lane);
-          s_part[(quarter * 2 + 0) * 64 + c] += t1;
-          s_part[(quarter * 2 + 1) * 64 + c] += t2;
+          s_part[(ew * 2 + 0) * 64 + c] += t1;
+          s_part[(ew * 2 + 1) * 64 + c] += t2;
         }
-        Rc = Rn;
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
+    const int reps = p.stat_reps > 0 ? p.stat_reps : 1;
     {
-      float* g0 = p.epi == EPI_BN_TRAIN ? p.stats : p.dbeta;
-      float* g1 = p.epi == EPI_BN_TRAIN ? p.stats + ncr : p.dgamma;
-      for (int c = tid128; c < p.nc; c += 128) {
-        atomicAdd(g0 + c % ncr, s_part[0 * 64 + c] + s_part[2 * 64 + c] + s_part[4 * 64 + c] + s_part[6 * 64 + c]);
-        atomicAdd(g1 + c % ncr, s_part[1 * 64 + c] + s_part[3 * 64 + c] + s_part[5 * 64 + c] + s_part[7 * 64 + c]);
+      float* g0 = p.stats + static_cast<size_t>(blockIdx.x % reps) * (2 * ncr);
+      float* g1 = g0 + ncr;
+      for (int c = tid128; c < p.nc; c += ET) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < EW; ++wv) {
+          a0 += s_part[(2 * wv + 0) * 64 + c];
+          a1 += s_part[(2 * wv + 1) * 64 + c];
+        }
+        atomicAdd(g0 + c % ncr, a0);
+        atomicAdd(g1 + c % ncr, a1);
       }
     }
-    grid_barrier_epi(p.grid_bar, tid128);
+    // what the per-channel constants need besides the grid-wide sums is fetched before the barrier (nc <= 64 <= 128
+    // threads: one channel per thread)
+    const int myc = tid128 < p.nc ? tid128 : 0;
+    const float gam = p.gamma[myc % ncr];
+    const float bet = p.epi == EPI_BN_TRAIN ? p.beta[myc % ncr] : 0.f;
+    float rmean = 0.f, rvar = 0.f;
+    if (p.epi == EPI_BN_TRAIN && blockIdx.x == 0 && tid128 < ncr) {
+      rmean = p.running_mean[tid128];
+      rvar = p.running_var[tid128];
+    }
+    grid_barrier_epi<ET>(p.grid_bar, tid128);
     if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels) * (p.fold ? 2.f : 1.f);
-    for (int c = tid128; c < p.nc; c += 128) {
-      const int cc = c % ncr;
+    if (tid128 < p.nc) {
+      const int c = tid128, cc = c % ncr;
+      float t0 = 0.f, t1 = 0.f;  // replicas in fixed order
+      for (int r = 0; r < reps; ++r) {
+        t0 += __ldcg(p.stats + static_cast<size_t>(r) * (2 * ncr) + cc);
+        t1 += __ldcg(p.stats + static_cast<size_t>(r) * (2 * ncr) + ncr + cc);
+      }
       if (p.epi == EPI_BN_TRAIN) {
-        const float mean = __ldcg(p.stats + cc) / cnt;
-        float var = __ldcg(p.stats + ncr + cc) / cnt - mean * mean;
+        const float mean = t0 / cnt;
+        float var = t1 / cnt - mean * mean;
         var = fmaxf(var, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        const float sc = p.gamma[cc] * rstd;
+        const float sc = gam * rstd;
         s_c0[c] = sc;
-        s_c1[c] = p.beta[cc] - mean * sc;
+        s_c1[c] = bet - mean * sc;
         if (blockIdx.x == 0 && c < ncr) {
           p.saved[c] = mean;
           p.saved[ncr + c] = rstd;
-          p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-          p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (cnt / (cnt - 1.f));
+          p.running_mean[c] = (1.f - p.momentum) * rmean + p.momentum * mean;
+          p.running_var[c] = (1.f - p.momentum) * rvar + p.momentum * var * (cnt / (cnt - 1.f));
         }
       } else {
-        s_c0[c] = p.gamma[cc] * s_rstd[c];
-        s_c1[c] = __ldcg(p.dbeta + cc) / cnt;
-        s_c2[c] = __ldcg(p.dgamma + cc) / cnt;
+        s_c0[c] = gam * s_rstd[c];
+        s_c1[c] = t0 / cnt;
+        s_c2[c] = t1 / cnt;
+        if (blockIdx.x == 0 && c < ncr) {  // the parameter gradients of this BatchNorm
+          p.dbeta[c] = t0;
+          p.dgamma[c] = t1;
+        }
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash);
-    //                  the TMEM loads of chunk q+1 are issued before chunk q is processed
-    {
-      uint32_t A[16], An[16], S[8], Sn[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) S[i] = Sn[i] = 0u;
-      if (Q > 0) {
-        tmem_ld16_issue(acc_t, A);
-        if (stash) tmem_ld8_issue(sta_t, S);
-        tmem_ld_wait16(A);
-        tmem_ld_wait8(S);
+    asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+    // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash)
+    as = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+      const int pix = tile * 128 + m;
+      const bool valid = pix < p.num_pixels;
+      const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
+      size_t up_base = 0;
+      if (p.epi == EPI_BNBWD && p.gy_up != nullptr) {
+        const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+        up_base = ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc;
       }
-      for (int q = 0; q < Q; ++q) {
-        if (q + 1 < Q) {
-          tmem_ld16_issue(acc_t + (q + 1) * 16, An);
-          if (stash) tmem_ld8_issue(sta_t + (q + 1) * 8, Sn);
-        }
-        int c0;
-        const int pix = chunk_pix(q, c0);
-        const bool valid = pix < p.num_pixels;
-        const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc + c0;
-        float o[16];
+      for (int c0 = 0; c0 < p.nc; c0 += 16) {
+        if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
+        float v[16];
+        tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float r_lo = __uint_as_float(S[i] << 16), r_hi = __uint_as_float(S[i] & 0xffff0000u);  // 0 when no stash
-            const float v_lo = __bfloat162float(__float2bfloat16_rn(__uint_as_float(A[2 * i])));
-            const float v_hi = __bfloat162float(__float2bfloat16_rn(__uint_as_float(A[2 * i + 1])));
-            o[2 * i] = fmaxf(v_lo * s_c0[c0 + 2 * i] + s_c1[c0 + 2 * i] + r_lo, 0.f);
-            o[2 * i + 1] = fmaxf(v_hi * s_c0[c0 + 2 * i + 1] + s_c1[c0 + 2 * i + 1] + r_hi, 0.f);
+          for (int i = 0; i < 16; ++i)
+            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
+          if (stash) {
+            float r[16];
+            tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
-          if (valid) store16_bf16(p.act_out + base, o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          if (valid) store16_bf16(p.act_out + base + c0, v);
         } else {
+          float xh[16], o[16];
+          tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, xh);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y_lo = __uint_as_float(S[i] << 16), y_hi = __uint_as_float(S[i] & 0xffff0000u);
-            const float xh_lo = (y_lo - s_mean[c0 + 2 * i]) * s_rstd[c0 + 2 * i];
-            const float xh_hi = (y_hi - s_mean[c0 + 2 * i + 1]) * s_rstd[c0 + 2 * i + 1];
-            o[2 * i] = s_c0[c0 + 2 * i] * (__uint_as_float(A[2 * i]) - s_c1[c0 + 2 * i] - xh_lo * s_c2[c0 + 2 * i]);
-            o[2 * i + 1] = s_c0[c0 + 2 * i + 1] *
-                           (__uint_as_float(A[2 * i + 1]) - s_c1[c0 + 2 * i + 1] - xh_hi * s_c2[c0 + 2 * i + 1]);
-          }
+          for (int i = 0; i < 16; ++i) o[i] = s_c0[c0 + i] * (v[i] - s_c1[c0 + i] - xh[i] * s_c2[c0 + i]);
           if (valid) {
-            store16_bf16(p.gy + base, o);
-            if (p.gy_up != nullptr) {
-              const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-              store16_bf16(p.gy_up + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc + c0, o);
-            }
-            if (p.gz != nullptr) {
-              float gzv[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) gzv[i] = __uint_as_float(A[i]);
-              store16_bf16(p.gz + base, gzv);
-            }
+            store16_bf16(p.gy + base + c0, o);
+            if (p.gy_up != nullptr) store16_bf16(p.gy_up + up_base + c0, o);
+            if (p.gz != nullptr) store16_bf16(p.gz + base + c0, v);
           }
-        }
-        if (q + 1 < Q) {
-          tmem_ld_wait16(An);
-          tmem_ld_wait8(Sn);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) A[i] = An[i];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) S[i] = Sn[i];
         }
       }
     }
     if (tid128 == 0) WACIL_STAMP(9);  // phase 2 done
-  } else {
+  } else if (warp < 6) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
@@ -712,6 +649,17 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     tmem_dealloc(tmem_base, tmem_cols);
   }
   if (threadIdx.x == 0) WACIL_STAMP(10);  // teardown done
+}
+
+__global__ void __launch_bounds__(kConvThreads, 2)
+    conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                     const ConvGemmParams p) {
+  conv_gemm_body<4>(mapA, mapW, p);
+}
+__global__ void __launch_bounds__(kConvThreadsW8, 2)
+    conv_gemm_kernel_w8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                        const ConvGemmParams p) {
+  conv_gemm_body<8>(mapA, mapW, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -964,9 +912,9 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 }
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
-  const size_t w = p.wstream ? 0 : (((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023));
-  const size_t stage = (size_t)p.tps * (128 * p.kc * 2 + (p.wstream ? p.nc * p.kc * 2 : 0));
-  return 1024 + w + (size_t)p.stages * stage + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 + 13 * 64 * 4 + 64;
+  const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
+  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
+         21 * 64 * 4 + 64;  // per-channel scratch sized for 8 epilogue warps
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
@@ -977,11 +925,10 @@ inline size_t conv_smem_bytes(const ConvGemmParams& p) {
 // those variants are as fast or faster in isolation: the kernels are latency-bound, a second resident CTA hides it.
 // (The occupancy API reports 1 CTA/SM for any tcgen05 kernel — csrc/occ_probe.cu — so a cooperative grid is <= #SMs.)
 constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
-inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax,
-                               bool wstream = false) {
-  const size_t w = wstream ? 0 : (((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023));
+inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
+  const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch
-  const size_t tap_bytes = (size_t)128 * kc * 2 + (wstream ? (size_t)nc * kc * 2 : 0);
+  const size_t tap_bytes = (size_t)128 * kc * 2;
   const int cand[3] = {9, 3, 1};
   tps = 1;
   stages = 2;

@@ -97,13 +97,13 @@ static int run_conv(const Case& c) {
   CK(cudaMalloc(&dx, nx * 2));
   CK(cudaMalloc(&dw, nw * 2));
   CK(cudaMalloc(&dy, ny * 2));
-  CK(cudaMalloc(&dstats, 2 * c.nc * 4));
+  CK(cudaMalloc(&dstats, 16 * 2 * c.nc * 4));  // room for the fused kernels' replicas
   CK(cudaMalloc(&dbias, c.nc * 4));
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, wb.data(), nw * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, bias.data(), c.nc * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dy, 0xFF, ny * 2));
-  CK(cudaMemset(dstats, 0, 2 * c.nc * 4));
+  CK(cudaMemset(dstats, 0, 16 * 2 * c.nc * 4));
   if (c.res_mode) {
     CK(cudaMalloc(&dres, rb.size() * 2));
     CK(cudaMemcpy(dres, rb.data(), rb.size() * 2, cudaMemcpyHostToDevice));
@@ -115,12 +115,7 @@ static int run_conv(const Case& c) {
   p.num_pixels = (int)npix;
   p.num_tiles = (int)((npix + 127) / 128);
   p.Ho = Ho; p.Wo = Wo;
-  {
-    const char* ev = getenv("WACIL_WSTREAM");
-    const bool on = !(ev && ev[0] == '0');
-    p.wstream = (on && (size_t)c.taps * c.nc * c.kc * 2 > 48 * 1024 && p.num_tiles <= 148 && (c.nc * c.kc * 2) % 1024 == 0) ? 1 : 0;
-  }
-  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages, kConvSmemMax, p.wstream != 0);
+  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
   if (g_stages > 0) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
   p.epi = c.epi;
   p.acc_stages = 2;
@@ -150,11 +145,18 @@ static int run_conv(const Case& c) {
     p.grid_bar = dbar; p.act_out = dact; p.gamma = dbias; p.beta = dbias; p.running_mean = dscratch;
     p.running_var = dscratch + 128; p.saved = dscratch + 256; p.eps = 1e-5f; p.momentum = 0.1f;
     if (!c.res_mode) p.res = nullptr;
+    const char* ev = getenv("WACIL_STAT_REPS");
+    p.stat_reps = ev ? atoi(ev) : 1;
   }
   if (fused) p.acc_stages = (p.num_tiles + 147) / 148;  // upper bound for the shared-memory size
   const size_t smem = conv_smem_bytes(p);
+  const char* ewv = getenv("WACIL_EPI_WARPS");
+  const bool w8 = fused && ewv && atoi(ewv) == 8;
+  const int nthreads = w8 ? kConvThreadsW8 : kConvThreads;
   CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem));
@@ -165,7 +167,8 @@ static int run_conv(const Case& c) {
   auto launch = [&]() {
     if (fused) {
       void* args[] = {&mapA, &mapW, &p};
-      CK(cudaLaunchCooperativeKernel((void*)conv_gemm_kernel, dim3(grid), dim3(kConvThreads), args, smem, 0));
+      CK(cudaLaunchCooperativeKernel(w8 ? (void*)conv_gemm_kernel_w8 : (void*)conv_gemm_kernel, dim3(grid), dim3(nthreads),
+                                     args, smem, 0));
     } else {
       conv_gemm_kernel<<<grid, kConvThreads, smem>>>(mapA, mapW, p);
     }

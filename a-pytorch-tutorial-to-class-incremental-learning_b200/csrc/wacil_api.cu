@@ -59,6 +59,20 @@ int pair_mask() {
   return v;
 }
 
+// Replicas of the per-channel BatchNorm sum accumulators of the fused kernels (WACIL_STAT_REPS).  Default 1: spreading
+// the 2*nc*grid reductions of a layer over 8 replicas was measured neutral-to-slower (1.254 vs 1.232 ms/step,
+// profiles/r01_epilogue_experiments.md) — the grid barrier is bound by L2 round trips, not by the atomic unit.
+int stat_reps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WACIL_STAT_REPS");
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+    if (v > 16) v = 16;
+  }
+  return v;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -162,7 +176,7 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wscr, which;
+  size_t table, wbuf, bias, stats, bstats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wscr, which;
   size_t wscr_elems = 0;
   int n_sup_w = 0;
   std::vector<size_t> y, a, gyup;
@@ -188,7 +202,8 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.bias = c.take(sel * 4);  // <= 2*cout floats per layer (pixel-pair layers duplicate the bias)
   o.wscr = c.take(scr * 4 + 16);
   o.which = c.take(static_cast<size_t>(nsw + 1) * 4);
-  o.stats = c.take(sel * 4);
+  o.stats = c.take(sel * 4 * stat_reps());   // forward: per layer [reps][2*cout] sum / sumsq replicas
+  o.bstats = c.take(sel * 4 * stat_reps());  // backward: per layer [reps][2*cout] d-beta / d-gamma replicas
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
@@ -226,7 +241,20 @@ struct ConvLaunch {
   ConvGemmParams p;
   int grid;
   size_t smem;
+  int ew = 4;  // epilogue warps: 4 (conv_gemm_kernel) or 8 (conv_gemm_kernel_w8, fused modes)
 };
+
+// Epilogue warps of the fused (BatchNorm) launches: WACIL_EPI_WARPS = 4 (default) | 8.  Two warps per TMEM lane quarter
+// were measured slower both in isolation (22.5 vs 20.9 us for the fused stage-1 layer) and on the step graph (1.234 vs
+// 1.194 ms): the post-barrier phase is not issue-bound, and the wider CTA crowds the co-resident branch.
+int fused_epi_warps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WACIL_EPI_WARPS");
+    v = (e && atoi(e) == 8) ? 8 : 4;
+  }
+  return v;
+}
 struct WgradLaunch {
   CUtensorMap mapX, mapDY;
   WgradParams p;
@@ -250,15 +278,7 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.num_tiles = (p.num_pixels + 127) / 128;
   p.Ho = Ho;
   p.Wo = Wo;
-  // Weight streaming (WACIL_WSTREAM=0 disables): when every CTA owns a single tile a resident weight copy is never
-  // reused; for the 64-channel layers (72 KB of taps) streaming them beside the activations doubles the ring depth.
-  {
-    static int ws_env = -2;
-    if (ws_env == -2) { const char* ev = getenv("WACIL_WSTREAM"); ws_env = ev ? (ev[0] == '0' ? 0 : 1) : 1; }
-    const size_t wbytes = static_cast<size_t>(taps) * nc * kc * 2;
-    p.wstream = (ws_env && wbytes > 48 * 1024 && p.num_tiles <= num_sms() && (nc * kc * 2) % 1024 == 0) ? 1 : 0;
-  }
-  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages, kConvSmemMax, p.wstream != 0);
+  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
   p.epi = epi;
   p.acc_stages = 2;
   p.res_stride = 1;
@@ -281,6 +301,12 @@ int conv_attrs() {
                                        static_cast<int>(kConvSmemMax));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kConvSmemMax));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -308,7 +334,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(c.ew == 8 ? kConvThreadsW8 : kConvThreads);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -325,7 +351,8 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
+  cudaError_t e = c.ew == 8 ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel_w8, c.mapA, c.mapW, c.p)
+                            : cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel");
   return 0;
 }
@@ -333,6 +360,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
 // Switch a prepared launch to a fused mode: one TMEM accumulator stage per tile of a CTA.
 int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
   c.p.epi = epi;
+  c.ew = fused_epi_warps();
   c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
   if (c.p.acc_stages * c.p.nc > 512)
     return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path: %d tiles x %d channels per CTA > 512 TMEM "
@@ -516,7 +544,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       c.p.w_early = l > 0 ? 1 : 0;  // layer 0 is launched right after cast_weights
       c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
       c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
-      c.p.stats = stats + so[l];
+      c.p.stats = stats + so[l] * stat_reps();
+      c.p.stat_reps = stat_reps();
       c.p.saved = saved + so[l];
       c.p.gamma = n->params + d.gamma_off;
       c.p.beta = n->params + d.beta_off;
@@ -568,6 +597,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         g.p.gamma = n->params + pd.gamma_off;
         g.p.dgamma = n->grads + pd.gamma_off;
         g.p.dbeta = n->grads + pd.beta_off;
+        g.p.stats = n->at<float>(n->off.bstats) + so[pl] * stat_reps();
+        g.p.stat_reps = stat_reps();
         g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 3]);
         g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
         g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
@@ -697,7 +728,7 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
   ++launches;
   const __nv_bfloat16* last = nullptr;
   if (n->mode == WACIL_NET_TRAIN) {
-    cudaError_t ce = cudaMemsetAsync(n->ws + n->off.stats, 0, n->off.stat_elems * 4, st);
+    cudaError_t ce = cudaMemsetAsync(n->ws + n->off.stats, 0, n->off.stat_elems * 4 * stat_reps(), st);
     if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
     dim3 grid(36, static_cast<unsigned>(nl));  // <= 4 elements per thread for the largest (64x64x9) layers
     cast_weights_kernel<<<grid, 256, 0, st>>>(n->params, n->at<__nv_bfloat16>(n->off.wbuf),
@@ -741,6 +772,8 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     ce = cudaMemsetAsync(n->ws + n->off.wscr, 0, n->off.wscr_elems * 4, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "weight-gradient scratch clear");
   }
+  ce = cudaMemsetAsync(n->ws + n->off.bstats, 0, n->off.stat_elems * 4 * stat_reps(), st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "BatchNorm-backward sums clear");
   float* dfeats = n->at<float>(n->off.dfeats);
   fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
                                                   C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
@@ -1114,7 +1147,9 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
   return launch_conv(c, S(stream));
 }
 
-size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout) { return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8; }
+size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout) {
+  return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8 * stat_reps();
+}
 
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
                           int res_mode, void* y, void* a, float* mean_rstd, float* running_mean, float* running_var,
@@ -1128,7 +1163,7 @@ int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, cons
                 res_mode);
   unsigned* gbar = static_cast<unsigned*>(workspace);
   float* stats = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 64);
-  cudaError_t ce = cudaMemsetAsync(stats, 0, static_cast<size_t>(cout) * 8, S(stream));
+  cudaError_t ce = cudaMemsetAsync(stats, 0, static_cast<size_t>(cout) * 8 * stat_reps(), S(stream));
   if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
   ConvLaunch c;
   int e = setup_conv(c, x, N, H, W, cin, cout, stride, 9, w, EPI_STATS);
@@ -1137,6 +1172,7 @@ int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, cons
   c.p.out = static_cast<__nv_bfloat16*>(y);
   c.p.act_out = static_cast<__nv_bfloat16*>(a);
   c.p.stats = stats;
+  c.p.stat_reps = stat_reps();
   c.p.saved = mean_rstd;
   c.p.gamma = gamma;
   c.p.beta = beta;

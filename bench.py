@@ -254,7 +254,8 @@ def kernel_rooflines(w, pk):
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / reps
     bytes_alg = 3 * B * C * 4 + 4 * B
-    out["kd"] = {"kernel": "kd_rows_kernel fp32 B=1024 C=8192 T=2", "us": us, "gbs": bytes_alg / us / 1e3,
+    out["kd"] = {"kernel": "kd_stream_kernel fp32 B=1024 C=8192 T=2 (TMA-streamed, 60 back-to-back launches over 6 "
+                           "rotating buffer sets, PDL)", "us": us, "gbs": bytes_alg / us / 1e3,
                  "frac": bytes_alg / us / 1e3 / pk["hbm_gbs"], "bytes": bytes_alg}
     return out
 
