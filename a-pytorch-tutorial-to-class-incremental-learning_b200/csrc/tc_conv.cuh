@@ -78,6 +78,10 @@ struct ConvGemmParams {
   int fold;                     // pixel-pair form: the nc columns are 2 x (nc/2) real channels (column c -> channel c % (nc/2))
   int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
   int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
+  int rmerge;                   // row-merged activation loads (stride 1, 3x3, tile inside one image): ONE box of Ht+2 image
+                                // rows per horizontal tap offset s; the three vertical taps r are M-windows of that box
+                                // shifted by r*Wo rows (= r KB: whole swizzle atoms).  3 loads of (Ht+2) rows instead of 9
+                                // loads of Ht rows: the L2->SM traffic of the main loop halves (stage 1) / drops 2.4x (stage 2)
 };
 
 // Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
@@ -195,8 +199,12 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   if (threadIdx.x == 0) WACIL_STAMP(0);  // kernel entry
   const int rowbytes = p.kc * 2;                 // bytes per K row of A and W tiles
   const uint32_t a_bytes = 128u * rowbytes;      // one tap tile of A
-  const uint32_t stage_bytes = p.tps * a_bytes;  // one pipeline stage = tps tap tiles
-  const int groups = (p.taps + p.tps - 1) / p.tps;
+  const bool rm = p.rmerge != 0;
+  const uint32_t win_bytes = static_cast<uint32_t>(p.Wo) * rowbytes;          // one image row of the tile (rmerge)
+  const uint32_t box_bytes = static_cast<uint32_t>(p.Ht + 2) * win_bytes;      // rmerge: Ht+2 image rows per load
+  // one pipeline stage = tps tap tiles, or (row-merged) one box holding the three vertical taps of one s
+  const uint32_t stage_bytes = rm ? box_bytes : p.tps * a_bytes;
+  const int groups = rm ? 3 : (p.taps + p.tps - 1) / p.tps;
   const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
   const uint32_t w_bytes = p.taps * w_tap_bytes;
 
@@ -268,11 +276,16 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           const int tap_lo = g * p.tps;
           const int ntap = min(p.tps, p.taps - tap_lo);
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], ntap * a_bytes);
-          for (int j = 0; j < ntap; ++j) {
-            int c0, c1, c2, c3, c4;
-            tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
-            tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+          if (rm) {  // g = horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
+            mbar_expect_tx(&full[stage], box_bytes);
+            tma_load_5d(smem_a + stage * stage_bytes, &mapA, &full[stage], 0, g - 1, h0 - 1, n0, 0);
+          } else {
+            mbar_expect_tx(&full[stage], ntap * a_bytes);
+            for (int j = 0; j < ntap; ++j) {
+              int c0, c1, c2, c3, c4;
+              tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
+              tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -311,13 +324,24 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
           // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
           uint64_t adesc = desc_hi | ((a_ring_addr + stage * stage_bytes) >> 4);
-          uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
-          for (int j = 0; j < ntap; ++j) {
+          if (rm) {  // taps (r, s = g), r = 0..2: M-window of the box shifted by r image rows; weight tap 3r + g
+            uint64_t bdesc = desc_hi | ((w_base_addr + g * w_tap_bytes) >> 4);
+            for (int r = 0; r < 3; ++r) {
 #pragma unroll 4
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap_lo + j + k) != 0);
-            adesc += a_bytes >> 4;
-            bdesc += w_tap_bytes >> 4;
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g + r + k) != 0);
+              adesc += win_bytes >> 4;
+              bdesc += (3 * w_tap_bytes) >> 4;
+            }
+          } else {
+            uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
+            for (int j = 0; j < ntap; ++j) {
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap_lo + j + k) != 0);
+              adesc += a_bytes >> 4;
+              bdesc += w_tap_bytes >> 4;
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == p.stages) {
@@ -864,7 +888,7 @@ inline CUtensorMapSwizzle swizzle_for_rowbytes(int rowbytes) {
 // Nt images x Ht rows x (full output width).  stride 1: dims {C, W, H, N, 1}; stride 2: the parity-plane
 // view {2C, W/2, 2, H/2, N} so that every tap is a unit-stride box.  Returns 0 on success.
 inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int stride, int Ht,
-                        int Nt) {
+                        int Nt, int box_rows = 0) {  // box_rows > 0 (stride 1): rows per box instead of Ht (row-merged loads)
   PFN_tmapEncodeTiled enc = get_tmap_encode();
   if (!enc) return -100;
   cuuint64_t dims[5], strides[4];
@@ -874,7 +898,7 @@ inline int make_act_map(CUtensorMap* map, const void* base, int N, int H, int W,
     dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 1;
     strides[0] = C * e; strides[1] = W * C * e; strides[2] = (cuuint64_t)H * W * C * e;
     strides[3] = (cuuint64_t)N * H * W * C * e;
-    box[0] = C; box[1] = W; box[2] = Ht; box[3] = Nt; box[4] = 1;
+    box[0] = C; box[1] = W; box[2] = box_rows > 0 ? box_rows : Ht; box[3] = Nt; box[4] = 1;
   } else {
     dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
     strides[0] = 2 * C * e; strides[1] = W * C * e; strides[2] = 2 * (cuuint64_t)W * C * e;
@@ -913,8 +937,23 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
-  return 1024 + w + (size_t)p.stages * p.tps * 128 * p.kc * 2 + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
+  const size_t stage = p.rmerge ? (size_t)(p.Ht + 2) * p.Wo * p.kc * 2 : (size_t)p.tps * 128 * p.kc * 2;
+  return 1024 + w + (size_t)p.stages * stage + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
          21 * 64 * 4 + 64;  // per-channel scratch sized for 8 epilogue warps
+}
+// Row-merged loads apply to stride-1 3x3 convolutions whose 128-pixel tile lies inside one image (32x32 and 16x16
+// maps) and whose image row is a whole number of 1 KB swizzle spans (so that the r-shifted windows stay atom-aligned).
+inline bool conv_can_rmerge(int kc, int taps, int stride, int Ho, int Wo) {
+  return stride == 1 && taps == 9 && Ho * Wo >= 128 && (Wo * kc * 2) % 1024 == 0;
+}
+inline void conv_pick_rmerge_pipeline(int kc, int nc, int Ht, int Wo, int& tps, int& stages,
+                                      size_t total_budget = 113 * 1024) {
+  const size_t w = ((size_t)9 * nc * kc * 2 + 1023) & ~size_t(1023);
+  const size_t budget = total_budget - 6144 - w;
+  const size_t box = (size_t)(Ht + 2) * Wo * kc * 2;
+  tps = 3;  // taps per stage (one box = the three vertical taps)
+  int st = (int)(budget / box);
+  stages = st > 6 ? 6 : (st < 2 ? 2 : st);
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).

@@ -115,13 +115,18 @@ static int run_conv(const Case& c) {
   p.num_pixels = (int)npix;
   p.num_tiles = (int)((npix + 127) / 128);
   p.Ho = Ho; p.Wo = Wo;
-  conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
-  if (g_stages > 0) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
+  {
+    const char* ev = getenv("WACIL_RMERGE");
+    p.rmerge = (!(ev && ev[0] == '0') && conv_can_rmerge(c.kc, c.taps, c.stride, Ho, Wo)) ? 1 : 0;
+  }
+  if (p.rmerge) conv_pick_rmerge_pipeline(c.kc, c.nc, p.Ht, Wo, p.tps, p.stages);
+  else conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
+  if (g_stages > 0 && !p.rmerge) { p.tps = g_stages / 100; p.stages = g_stages % 100; }  // e.g. 904 = 9 taps/stage, 4 stages
   p.epi = c.epi;
   p.acc_stages = 2;
   p.out = dy; p.stats = dstats; p.bias = dbias; p.res = dres; p.res_stride = rs; p.res_c = rC;
   CUtensorMap mapA, mapW;
-  int e1 = make_act_map(&mapA, dx, c.N, c.H, c.W, c.kc, c.stride, p.Ht, p.Nt);
+  int e1 = make_act_map(&mapA, dx, c.N, c.H, c.W, c.kc, c.stride, p.Ht, p.Nt, p.rmerge ? p.Ht + 2 : 0);
   int e2 = make_mat_map(&mapW, dw, (long long)c.taps * c.nc, c.kc, c.nc);
   if (e1 || e2) { printf("  tensor map encode failed: %d %d\n", e1, e2); return 1; }
   int grid = p.num_tiles < 296 ? p.num_tiles : 296;

@@ -278,12 +278,18 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.num_tiles = (p.num_pixels + 127) / 128;
   p.Ho = Ho;
   p.Wo = Wo;
-  conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
+  {
+    static int rm_env = -2;  // WACIL_RMERGE=0 restores one box per tap
+    if (rm_env == -2) { const char* ev = getenv("WACIL_RMERGE"); rm_env = ev ? (ev[0] == '0' ? 0 : 1) : 1; }
+    p.rmerge = (rm_env && conv_can_rmerge(kc, taps, stride, Ho, Wo)) ? 1 : 0;
+  }
+  if (p.rmerge) conv_pick_rmerge_pipeline(kc, nc, p.Ht, Wo, p.tps, p.stages);
+  else conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
   p.epi = epi;
   p.acc_stages = 2;
   p.res_stride = 1;
   p.res_c = nc;
-  int e = make_act_map(&c.mapA, in, N, H, W, kc, stride, p.Ht, p.Nt);
+  int e = make_act_map(&c.mapA, in, N, H, W, kc, stride, p.Ht, p.Nt, p.rmerge ? p.Ht + 2 : 0);
   if (e) return fail(WACIL_E_DRIVER, "activation tensor map (N=%d H=%d C=%d s=%d): %d", N, H, kc, stride, e);
   e = make_mat_map(&c.mapW, wts, static_cast<long long>(taps) * nc, kc, nc);
   if (e) return fail(WACIL_E_DRIVER, "weight tensor map (%dx%d): %d", nc, kc, e);
