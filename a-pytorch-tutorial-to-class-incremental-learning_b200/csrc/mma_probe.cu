@@ -7,13 +7,14 @@
 #include "tc_prims.cuh"
 using namespace wacil;
 
-__global__ void __launch_bounds__(128) probe_kernel(int n, int rowbytes, int count, int chains, long long* out) {
+__global__ void __launch_bounds__(128) probe_kernel(int n, int rowbytes, int count, int chains, int walk, int commit_every,
+                                                      long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_slot;
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_mbar_init(); }
   if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -24,15 +25,24 @@ __global__ void __launch_bounds__(128) probe_kernel(int n, int rowbytes, int cou
     const uint64_t desc_hi = umma_smem_desc(0, 16, 8u * rowbytes, layout);
     const uint32_t idesc = umma_idesc_bf16(128, n, 0, 0);
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 32 * 1024);
-    const int ksteps = rowbytes / 32;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int rep = 0; rep < 2; ++rep) {  // rep 0 warms up
       const long long t0 = clock64();
+      const uint64_t adesc = desc_hi | (a_addr >> 4), bdesc = desc_hi | (b_addr >> 4);
+      // no integer division in the timed loop: the chain index advances by compare-and-reset
+      int c = 0, wk = 0, ce = 0;
+      uint32_t d = tmem_base;
+      uint64_t ad = adesc, bd = bdesc;
       for (int i = 0; i < count; ++i) {
-        const int c = i % chains;
-        const uint64_t adesc = (desc_hi | (a_addr >> 4)) + 2 * (i % ksteps);
-        const uint64_t bdesc = (desc_hi | (b_addr >> 4)) + 2 * (i % ksteps);
-        umma_bf16(tmem_base + c * n, adesc, bdesc, idesc, i >= chains);
+        umma_bf16(d, ad, bd, idesc, i >= chains);
+        d += n;
+        if (++c == chains) { c = 0; d = tmem_base; }
+        if (walk) {  // a different 4 KB activation tile and weight tile per MMA (7 tiles, then wrap)
+          ad += 4096 >> 4;
+          bd += 1024 >> 4;
+          if (++wk == 7) { wk = 0; ad = adesc; bd = bdesc; }
+        }
+        if (commit_every > 0 && ++ce == commit_every) { ce = 0; umma_commit(&bar2); }
       }
       const long long t1 = clock64();
       umma_commit(&bar);
@@ -50,20 +60,19 @@ int main() {
   long long* d;
   cudaMalloc(&d, 148 * 2 * sizeof(long long));
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  printf("%5s %8s %6s %6s %6s | %12s %12s\n", "N", "rowbytes", "count", "chains", "grid", "issue cyc/mma", "total cyc/mma");
-  const int ns[] = {16, 32, 64, 128, 256};
-  for (int grid : {1, 148})
-    for (int rb : {32, 128})
-      for (int n : ns)
-        for (int chains : {1, 2, 4}) {
-          if (chains * n > 512) continue;
-          const int count = 64;
-          probe_kernel<<<grid, 128, 64 * 1024>>>(n, rb, count, chains, d);
+  printf("%5s %8s %6s %6s %5s %7s | %12s %12s\n", "N", "rowbytes", "count", "chains", "walk", "commit/", "issue cyc/mma", "total cyc/mma");
+  const int ns[] = {16, 64};
+  for (int rb : {32, 128})
+    for (int n : ns)
+      for (int walk : {0, 1})
+        for (int ce : {0, 9, 3, 1}) {
+          const int count = 63, chains = 1;
+          probe_kernel<<<148, 128, 64 * 1024>>>(n, rb, count, chains, walk, ce, d);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
           long long h[2];
           cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-          printf("%5d %8d %6d %6d %6d | %12.1f %12.1f\n", n, rb, count, chains, grid, (double)h[0] / count, (double)h[1] / count);
+          printf("%5d %8d %6d %6d %5d %7d | %12.1f %12.1f\n", n, rb, count, chains, walk, ce, (double)h[0] / count, (double)h[1] / count);
         }
   return 0;
 }

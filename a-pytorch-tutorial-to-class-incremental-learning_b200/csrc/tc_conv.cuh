@@ -182,6 +182,54 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// ---- MMA issue loops.  One thread issues every tcgen05.mma of the CTA, and at these channel counts an MMA is cheap
+// (mma_probe.cu: 64 cycles per instruction in a minimal loop, independent of N <= 128) while every scalar instruction
+// of that lone thread costs ~6 cycles of dependent-issue latency: a loop with runtime trip counts, flag arithmetic
+// and descriptor rebuilding spent ~250-300 cycles per MMA — the main loop was bound by this thread, not by TMA or the
+// tensor core.  These loops are fully unrolled per (K steps, taps per stage): per MMA one predicate set, the MMA, and
+// immediate-offset descriptor adds.
+template <int KS>
+__device__ __forceinline__ void issue_rmerge_group(bool leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                   uint32_t idesc, uint32_t win16, uint32_t wtap16, bool first_of_tile) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      if (r == 0 && k == 0) { if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, first_of_tile ? 0u : 1u); }
+      else if (leader) umma_bf16_acc(d_tmem, adesc + (r * win16 + 2 * k), bdesc + (3 * r * wtap16 + 2 * k), idesc);
+    }
+  }
+}
+// Row-merged tile: the three boxes (s = 0..2) of a stage, each feeding the three vertical taps.
+template <int KS>
+__device__ __forceinline__ void issue_rmerge_tile(bool leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                  uint32_t idesc, uint32_t box16, uint32_t win16, uint32_t wtap16) {
+#pragma unroll
+  for (int sft = 0; sft < 3; ++sft) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        if (sft == 0 && r == 0 && k == 0) { if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, 0u); }
+        else if (leader)
+          umma_bf16_acc(d_tmem, adesc + (sft * box16 + r * win16 + 2 * k), bdesc + ((3 * r + sft) * wtap16 + 2 * k), idesc);
+      }
+    }
+  }
+}
+template <int KS, int NTAP>
+__device__ __forceinline__ void issue_tap_group(bool leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t a16, uint32_t wtap16, bool first_of_tile) {
+#pragma unroll
+  for (int j = 0; j < NTAP; ++j) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      if (j == 0 && k == 0) { if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, first_of_tile ? 0u : 1u); }
+      else if (leader) umma_bf16_acc(d_tmem, adesc + (j * a16 + 2 * k), bdesc + (j * wtap16 + 2 * k), idesc);
+    }
+  }
+}
+
 constexpr int kConvThreads = 192;
 constexpr int kConvThreadsW8 = 320;  // the fused modes may run with 8 epilogue warps (two per TMEM lane quarter)
 
@@ -203,8 +251,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   const uint32_t win_bytes = static_cast<uint32_t>(p.Wo) * rowbytes;          // one image row of the tile (rmerge)
   const uint32_t box_bytes = static_cast<uint32_t>(p.Ht + 2) * win_bytes;      // rmerge: Ht+2 image rows per load
   // one pipeline stage = tps tap tiles, or (row-merged) one box holding the three vertical taps of one s
-  const uint32_t stage_bytes = rm ? box_bytes : p.tps * a_bytes;
-  const int groups = rm ? 3 : (p.taps + p.tps - 1) / p.tps;
+  const uint32_t stage_bytes = rm ? 3 * box_bytes : p.tps * a_bytes;  // row-merged: the whole tile (s = 0, 1, 2) per stage
+  const int groups = rm ? 1 : (p.taps + p.tps - 1) / p.tps;
   const uint32_t w_tap_bytes = p.nc * rowbytes;  // one tap tile of W
   const uint32_t w_bytes = p.taps * w_tap_bytes;
 
@@ -262,100 +310,131 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if (!(p.pdl && p.w_early)) {
+    // (whole warp in the loop, lane 0 issues: see the MMA issuer)
+    {
+      const bool leader = elect_one_sync();
+      const bool timing = p.dbg != nullptr;
+      if (leader && !(p.pdl && p.w_early)) {
         mbar_expect_tx(wfull, w_bytes);
         for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long dbg_wait = 0, dbg_t = 0;  // profiling only (p.dbg): cycles blocked on a free slot
+      const int nstages = p.stages, ntiles = p.num_tiles, tstride = gridDim.x, tps = p.tps, taps = p.taps;
+      for (int tile = blockIdx.x; tile < ntiles; tile += tstride) {
         const int n0 = (tile / p.tiles_h) * p.Nt;
         const int h0 = (tile % p.tiles_h) * p.Ht;
         for (int g = 0; g < groups; ++g) {
-          const int tap_lo = g * p.tps;
-          const int ntap = min(p.tps, p.taps - tap_lo);
+          if (timing) dbg_t = clock64();
           mbar_wait(&empty[stage], phase ^ 1);
-          if (rm) {  // g = horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
-            mbar_expect_tx(&full[stage], box_bytes);
-            tma_load_5d(smem_a + stage * stage_bytes, &mapA, &full[stage], 0, g - 1, h0 - 1, n0, 0);
+          if (timing) dbg_wait += clock64() - dbg_t;
+          uint8_t* dst = smem_a + stage * stage_bytes;
+          if (rm) {  // per horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
+            if (leader) {
+              mbar_expect_tx(&full[stage], 3 * box_bytes);
+              tma_load_5d(dst, &mapA, &full[stage], 0, -1, h0 - 1, n0, 0);
+              tma_load_5d(dst + box_bytes, &mapA, &full[stage], 0, 0, h0 - 1, n0, 0);
+              tma_load_5d(dst + 2 * box_bytes, &mapA, &full[stage], 0, 1, h0 - 1, n0, 0);
+            }
           } else {
-            mbar_expect_tx(&full[stage], ntap * a_bytes);
+            const int tap_lo = g * tps;
+            const int ntap = min(tps, taps - tap_lo);
+            if (leader) mbar_expect_tx(&full[stage], ntap * a_bytes);
             for (int j = 0; j < ntap; ++j) {
               int c0, c1, c2, c3, c4;
-              tap_coords(p.taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
-              tma_load_5d(smem_a + stage * stage_bytes + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+              tap_coords(taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
+              if (leader) tma_load_5d(dst + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
             }
           }
-          if (++stage == p.stages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
-      WACIL_STAMP(2);  // producer: every TMA load issued
+      if (leader) {
+        WACIL_STAMP(2);  // producer: every TMA load issued
+        if (timing) p.dbg[blockIdx.x * 16 + 11] = dbg_wait;
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop (warp-uniform control flow keeps the descriptor arithmetic in uniform registers, where
+    // UTCHMMA wants its operands); only the tcgen05 instructions themselves are predicated on the leader lane.
+    {
+      const bool leader = elect_one_sync();
       const uint32_t layout = umma_layout_for_rowbytes(rowbytes);
       const uint32_t sbo = 8u * rowbytes;
       const uint32_t idesc = umma_idesc_bf16(128, p.nc, 0, 0);
       const int ksteps = p.kc / 16;
       const uint64_t desc_hi = umma_smem_desc(0, 16, sbo, layout);
-      const uint32_t a_ring_addr = smem_u32(smem_a);
-      const uint32_t w_base_addr = smem_u32(smem_w);
+      // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
+      const uint64_t a_ring_desc = desc_hi | (smem_u32(smem_a) >> 4);
+      const uint64_t w_desc = desc_hi | (smem_u32(smem_w) >> 4);
+      const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4, win16 = win_bytes >> 4, wtap16 = w_tap_bytes >> 4;
+      const uint32_t box16 = box_bytes >> 4;
+      const int nstages = p.stages, ntiles = p.num_tiles, tstride = gridDim.x, nc = p.nc, tps = p.tps, taps = p.taps;
+      const bool timing = p.dbg != nullptr;
       mbar_wait(wfull, 0);
       tc_fence_after();
-      WACIL_STAMP(3);  // weights landed
+      if (leader) WACIL_STAMP(3);  // weights landed
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long dbg_wait = 0, dbg_t = 0;  // profiling only (p.dbg): cycles blocked on operands
+      bool first_stage = true;
+      for (int tile = blockIdx.x; tile < ntiles; tile += tstride) {
         mbar_wait(&accempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.nc;
+        const uint32_t d_tmem = tmem_base + as * nc;
         for (int g = 0; g < groups; ++g) {
-          const int tap_lo = g * p.tps;
-          const int ntap = min(p.tps, p.taps - tap_lo);
+          if (timing) dbg_t = clock64();
           mbar_wait(&full[stage], phase);
+          if (timing) dbg_wait += clock64() - dbg_t;
           tc_fence_after();
-          if (tile == static_cast<int>(blockIdx.x) && g == 0) WACIL_STAMP(4);  // first activation stage landed
-          // descriptors differ only in the start-address field ((addr >> 4) in the low bits): add, don't rebuild
-          uint64_t adesc = desc_hi | ((a_ring_addr + stage * stage_bytes) >> 4);
-          if (rm) {  // taps (r, s = g), r = 0..2: M-window of the box shifted by r image rows; weight tap 3r + g
-            uint64_t bdesc = desc_hi | ((w_base_addr + g * w_tap_bytes) >> 4);
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (g + r + k) != 0);
-              adesc += win_bytes >> 4;
-              bdesc += (3 * w_tap_bytes) >> 4;
-            }
+          if (first_stage) { if (leader) WACIL_STAMP(4); first_stage = false; }  // first activation stage landed
+          const uint64_t adesc = a_ring_desc + stage * stage16;
+          if (rm) {  // taps (r, s): M-window of box s shifted by r image rows; weight tap 3r + s
+            if (ksteps == 1) issue_rmerge_tile<1>(leader, d_tmem, adesc, w_desc, idesc, box16, win16, wtap16);
+            else if (ksteps == 2) issue_rmerge_tile<2>(leader, d_tmem, adesc, w_desc, idesc, box16, win16, wtap16);
+            else issue_rmerge_tile<4>(leader, d_tmem, adesc, w_desc, idesc, box16, win16, wtap16);
           } else {
-            uint64_t bdesc = desc_hi | ((w_base_addr + tap_lo * w_tap_bytes) >> 4);
-            for (int j = 0; j < ntap; ++j) {
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap_lo + j + k) != 0);
-              adesc += a_bytes >> 4;
-              bdesc += w_tap_bytes >> 4;
+            const int tap_lo = g * tps;
+            const uint64_t bdesc = w_desc + tap_lo * wtap16;
+            const bool first = g == 0;
+            const int ntap = min(tps, taps - tap_lo);
+            if (ntap == 9) {
+              if (ksteps == 1) issue_tap_group<1, 9>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else if (ksteps == 2) issue_tap_group<2, 9>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else issue_tap_group<4, 9>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+            } else if (ntap == 3) {
+              if (ksteps == 1) issue_tap_group<1, 3>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else if (ksteps == 2) issue_tap_group<2, 3>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else issue_tap_group<4, 3>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+            } else {
+              if (ksteps == 1) issue_tap_group<1, 1>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else if (ksteps == 2) issue_tap_group<2, 1>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
+              else issue_tap_group<4, 1>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
             }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == p.stages) {
+          if (leader) umma_commit(&empty[stage]);
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&accfull[as]);
+        if (leader) umma_commit(&accfull[as]);
         if (++as == nacc) {
           as = 0;
           aphase ^= 1;
         }
       }
-      WACIL_STAMP(5);  // every MMA issued
+      if (leader) {
+        WACIL_STAMP(5);  // every MMA issued
+        if (timing) p.dbg[blockIdx.x * 16 + 12] = dbg_wait;
+      }
     }
   } else if (p.epi >= EPI_BN_TRAIN) {
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
@@ -763,73 +842,83 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
 
+  // Producer and MMA warps run their loops with all 32 lanes (uniform control flow: the descriptor arithmetic stays in
+  // uniform registers); the TMA / tcgen05 instructions are issued by the elect.sync leader (see conv_gemm_body).
   if (warp == 0) {
-    if (lane == 0) {
-      int gs = 0, ys = 0;
-      uint32_t gphase = 0, yphase = 0;
-      for (int tile = t_begin; tile < t_end; ++tile) {
-        const int n0 = (tile / p.tiles_h) * p.Nt;
-        const int h0 = (tile % p.tiles_h) * p.Ht;
-        mbar_wait(&yempty[ys], yphase ^ 1);
+    const bool leader = elect_one_sync();
+    int gs = 0, ys = 0;
+    uint32_t gphase = 0, yphase = 0;
+    const int ring = p.ring, taps = p.taps;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int n0 = (tile / p.tiles_h) * p.Nt;
+      const int h0 = (tile % p.tiles_h) * p.Ht;
+      mbar_wait(&yempty[ys], yphase ^ 1);
+      if (leader) {
         mbar_expect_tx(&yfull[ys], y_bytes);
         tma_load_2d(smem_y + ys * y_stride, &mapDY, &yfull[ys], 0, tile * 128);
-        if (++ys == 2) {
-          ys = 0;
-          yphase ^= 1;
+      }
+      if (++ys == 2) {
+        ys = 0;
+        yphase ^= 1;
+      }
+      for (int g = 0; g < groups; ++g) {
+        const int tap_lo = g * tpg;
+        const int ntap = min(tpg, taps - tap_lo);
+        mbar_wait(&gempty[gs], gphase ^ 1);
+        if (leader) mbar_expect_tx(&gfull[gs], ntap * slot_bytes);
+        for (int j = 0; j < ntap; ++j) {
+          int c0, c1, c2, c3, c4;
+          tap_coords(taps, p.stride, tap_lo + j, p.cin, h0, n0, c0, c1, c2, c3, c4);
+          if (leader) tma_load_5d(smem_g + gs * group_bytes + j * slot_bytes, &mapX, &gfull[gs], c0, c1, c2, c3, c4);
         }
-        for (int g = 0; g < groups; ++g) {
-          const int tap_lo = g * tpg;
-          const int ntap = min(tpg, p.taps - tap_lo);
-          mbar_wait(&gempty[gs], gphase ^ 1);
-          mbar_expect_tx(&gfull[gs], ntap * slot_bytes);
-          for (int j = 0; j < ntap; ++j) {
-            int c0, c1, c2, c3, c4;
-            tap_coords(p.taps, p.stride, tap_lo + j, p.cin, h0, n0, c0, c1, c2, c3, c4);
-            tma_load_5d(smem_g + gs * group_bytes + j * slot_bytes, &mapX, &gfull[gs], c0, c1, c2, c3, c4);
-          }
-          if (++gs == p.ring) {
-            gs = 0;
-            gphase ^= 1;
-          }
+        if (++gs == ring) {
+          gs = 0;
+          gphase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && t_begin < t_end) {
+    if (t_begin < t_end) {
+      const bool leader = elect_one_sync();
       const uint32_t xlayout = umma_layout_for_rowbytes(xrow);
       const uint32_t ylayout = umma_layout_for_rowbytes(yrow);
       const uint32_t idesc = umma_idesc_bf16(128, p.cout, 1, 1);
+      // MN-major: LBO = stride between MN atoms (tap slots), SBO = stride between 8-pixel K groups; the 8 K-steps of
+      // 16 pixels of a tile differ in the start-address field only
+      const uint64_t a_hi = umma_smem_desc(0, slot_bytes, 8u * xrow, xlayout);
+      const uint64_t b_hi = umma_smem_desc(0, y_bytes, 8u * yrow, ylayout);
+      const uint32_t ka16 = (16u * xrow) >> 4, kb16 = (16u * yrow) >> 4;
+      const int ring = p.ring, cout = p.cout;
       int gs = 0, ys = 0;
       uint32_t gphase = 0, yphase = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(&yfull[ys], yphase);
         tc_fence_after();
-        const uint32_t y_addr = smem_u32(smem_y + ys * y_stride);
+        const uint64_t b0 = b_hi | (smem_u32(smem_y + ys * y_stride) >> 4);
+        const bool first_tile = tile == t_begin;
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&gfull[gs], gphase);
           tc_fence_after();
-          const uint32_t g_addr = smem_u32(smem_g + gs * group_bytes);
-          const uint32_t d_tmem = tmem_base + g * p.cout;
-#pragma unroll 1
+          const uint64_t a0 = a_hi | (smem_u32(smem_g + gs * group_bytes) >> 4);
+          const uint32_t d_tmem = tmem_base + g * cout;
+#pragma unroll
           for (int j = 0; j < 8; ++j) {  // 8 K-steps of 16 pixels
-            // MN-major: LBO = stride between MN atoms (tap slots), SBO = stride between 8-pixel K groups
-            const uint64_t adesc = umma_smem_desc(g_addr + j * 16 * xrow, slot_bytes, 8u * xrow, xlayout);
-            const uint64_t bdesc = umma_smem_desc(y_addr + j * 16 * yrow, y_bytes, 8u * yrow, ylayout);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (tile != t_begin) || (j != 0));
+            if (j == 0) { if (leader) umma_bf16(d_tmem, a0, b0, idesc, first_tile ? 0u : 1u); }
+            else if (leader) umma_bf16_acc(d_tmem, a0 + j * ka16, b0 + j * kb16, idesc);
           }
-          umma_commit(&gempty[gs]);
-          if (++gs == p.ring) {
+          if (leader) umma_commit(&gempty[gs]);
+          if (++gs == ring) {
             gs = 0;
             gphase ^= 1;
           }
         }
-        umma_commit(&yempty[ys]);
+        if (leader) umma_commit(&yempty[ys]);
         if (++ys == 2) {
           ys = 0;
           yphase ^= 1;
         }
       }
-      umma_commit(accfull);
+      if (leader) umma_commit(accfull);
     }
   } else if (t_begin < t_end) {
     const int quarter = warp & 3;
@@ -937,23 +1026,26 @@ inline void conv_tile_shape(int Ho, int Wo, int& Ht, int& Nt, int& tiles_h) {
 
 inline size_t conv_smem_bytes(const ConvGemmParams& p) {
   const size_t w = ((size_t)p.taps * p.nc * p.kc * 2 + 1023) & ~size_t(1023);
-  const size_t stage = p.rmerge ? (size_t)(p.Ht + 2) * p.Wo * p.kc * 2 : (size_t)p.tps * 128 * p.kc * 2;
+  const size_t stage = p.rmerge ? (size_t)3 * (p.Ht + 2) * p.Wo * p.kc * 2 : (size_t)p.tps * 128 * p.kc * 2;
   return 1024 + w + (size_t)p.stages * stage + (2 * p.stages + 1 + 2 * p.acc_stages) * 8 + 16 +
          21 * 64 * 4 + 64;  // per-channel scratch sized for 8 epilogue warps
 }
 // Row-merged loads apply to stride-1 3x3 convolutions whose 128-pixel tile lies inside one image (32x32 and 16x16
 // maps) and whose image row is a whole number of 1 KB swizzle spans (so that the r-shifted windows stay atom-aligned).
-inline bool conv_can_rmerge(int kc, int taps, int stride, int Ho, int Wo) {
-  return stride == 1 && taps == 9 && Ho * Wo >= 128 && (Wo * kc * 2) % 1024 == 0;
+inline bool conv_can_rmerge(int kc, int nc, int taps, int stride, int Ho, int Wo, size_t total_budget = 113 * 1024) {
+  if (!(stride == 1 && taps == 9 && Ho * Wo >= 128 && (Wo * kc * 2) % 1024 == 0)) return false;
+  const size_t w = ((size_t)9 * nc * kc * 2 + 1023) & ~size_t(1023);
+  const size_t tile = (size_t)3 * (128 / Wo + 2) * Wo * kc * 2;  // three boxes of Ht+2 image rows
+  return w + 6144 + 2 * tile <= total_budget;                    // at least a double buffer inside the footprint
 }
 inline void conv_pick_rmerge_pipeline(int kc, int nc, int Ht, int Wo, int& tps, int& stages,
                                       size_t total_budget = 113 * 1024) {
   const size_t w = ((size_t)9 * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;
-  const size_t box = (size_t)(Ht + 2) * Wo * kc * 2;
-  tps = 3;  // taps per stage (one box = the three vertical taps)
-  int st = (int)(budget / box);
-  stages = st > 6 ? 6 : (st < 2 ? 2 : st);
+  const size_t tile = (size_t)3 * (Ht + 2) * Wo * kc * 2;  // three boxes
+  tps = 9;  // taps per stage: the whole tile
+  int st = (int)(budget / tile);
+  stages = st > 4 ? 4 : (st < 2 ? 2 : st);
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).

@@ -117,7 +117,7 @@ static int run_conv(const Case& c) {
   p.Ho = Ho; p.Wo = Wo;
   {
     const char* ev = getenv("WACIL_RMERGE");
-    p.rmerge = (!(ev && ev[0] == '0') && conv_can_rmerge(c.kc, c.taps, c.stride, Ho, Wo)) ? 1 : 0;
+    p.rmerge = (!(ev && ev[0] == '0') && conv_can_rmerge(c.kc, c.nc, c.taps, c.stride, Ho, Wo)) ? 1 : 0;
   }
   if (p.rmerge) conv_pick_rmerge_pipeline(c.kc, c.nc, p.Ht, Wo, p.tps, p.stages);
   else conv_pick_pipeline(c.kc, c.nc, c.taps, p.tps, p.stages);
@@ -203,7 +203,8 @@ static int run_conv(const Case& c) {
         printf("   cta %3d:", b);
         for (int k = 1; k <= 10; ++k)
           if (h[b * 16 + k]) printf(" %s %lld", names[k], h[b * 16 + k] - h[b * 16]);
-        printf("  (cycles)\n");
+        printf("  | producer blocked on free slots %lld, MMA thread blocked on operands %lld  (cycles)\n", h[b * 16 + 11],
+               h[b * 16 + 12]);
       }
     }
     printf("%-34s conv  tps %d stages %2d grid %3d smem %6zu : %7.2f us/launch (warm L2, back-to-back)\n", c.name, p.tps, p.stages, grid,

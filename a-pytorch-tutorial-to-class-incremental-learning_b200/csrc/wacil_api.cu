@@ -281,7 +281,7 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   {
     static int rm_env = -2;  // WACIL_RMERGE=0 restores one box per tap
     if (rm_env == -2) { const char* ev = getenv("WACIL_RMERGE"); rm_env = ev ? (ev[0] == '0' ? 0 : 1) : 1; }
-    p.rmerge = (rm_env && conv_can_rmerge(kc, taps, stride, Ho, Wo)) ? 1 : 0;
+    p.rmerge = (rm_env && conv_can_rmerge(kc, nc, taps, stride, Ho, Wo)) ? 1 : 0;
   }
   if (p.rmerge) conv_pick_rmerge_pipeline(kc, nc, p.Ht, Wo, p.tps, p.stages);
   else conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
