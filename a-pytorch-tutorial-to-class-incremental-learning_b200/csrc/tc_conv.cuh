@@ -119,20 +119,37 @@ __device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
     if (p.dbg != nullptr) p.dbg[blockIdx.x * 16 + (slot)] = clock64();           \
   } while (0)
 
+// bf16 <-> fp32 in registers: a bf16 is the upper half of its fp32 (shift / mask to widen), and two floats round to a
+// packed pair with one cvt.rn.bf16x2.f32 — no per-element conversions, no local-memory staging arrays.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);  // .x (low half) = lo
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void unpack16_bf16(const uint4& a, const uint4& b, float (&v)[16]) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[2 * i] = bf16_lo(w[i]);
+    v[2 * i + 1] = bf16_hi(w[i]);
+  }
+}
+__device__ __forceinline__ void pack16_bf16(const float (&v)[16], uint4& a, uint4& b) {
+  a = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  b = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
 __device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&v)[16]) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 r4[2] = {__ldg(q), __ldg(q + 1)};
-  const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(r4);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __bfloat162float(rb[i]);
+  const uint4 a = __ldg(q), b = __ldg(q + 1);
+  unpack16_bf16(a, b, v);
 }
 __device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&v)[16]) {
-  __align__(16) __nv_bfloat16 ob[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+  uint4 a, b;
+  pack16_bf16(v, a, b);
   uint4* op = reinterpret_cast<uint4*>(p);
-  op[0] = reinterpret_cast<const uint4*>(ob)[0];
-  op[1] = reinterpret_cast<const uint4*>(ob)[1];
+  op[0] = a;
+  op[1] = b;
 }
 
 __device__ __forceinline__ void tap_coords(int taps, int stride, int tap, int kc, int h0, int n0, int& c0, int& c1,
@@ -266,7 +283,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   uint64_t* accfull = wfull + 1;          // [nacc]
   uint64_t* accempty = accfull + nacc;    // [nacc]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + nacc);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [(2*EW+5)*64] per-channel scratch
+  // [(2*EW+5)*64] per-channel scratch, 16-byte aligned (read with 128-bit loads; the size budget has 64 bytes of slack)
+  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   // Fused modes keep a second TMEM region beside the accumulators (same tile/column indexing, offset stash_col): what the
   // post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: x-hat) is staged there in phase 1,
@@ -507,20 +525,18 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         float v[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
-          __align__(16) __nv_bfloat16 ob[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+          uint4 oa, ob;
+          pack16_bf16(v, oa, ob);  // y as stored (bf16); the statistics are taken over the rounded values
           if (valid) {
             uint4* op = reinterpret_cast<uint4*>(p.out + base + c0);
-            op[0] = reinterpret_cast<const uint4*>(ob)[0];
-            op[1] = reinterpret_cast<const uint4*>(ob)[1];
+            op[0] = oa;
+            op[1] = ob;
+          } else {
+            oa = ob = make_uint4(0u, 0u, 0u, 0u);
           }
+          unpack16_bf16(oa, ob, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float r = valid ? __bfloat162float(ob[i]) : 0.f;
-            v[i] = r;
-            s2[i] = r * r;
-          }
+          for (int i = 0; i < 16; ++i) s2[i] = v[i] * v[i];
         } else {
           float a[16], yv[16];
 #pragma unroll
@@ -634,9 +650,21 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
+          {
+            uint4 ya, yb;
+            pack16_bf16(v, ya, yb);  // the stored (rounded) conv output is what gets normalised
+            unpack16_bf16(ya, yb, v);
+            const float4* k0 = reinterpret_cast<const float4*>(s_c0 + c0);
+            const float4* k1 = reinterpret_cast<const float4*>(s_c1 + c0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = __bfloat162float(__float2bfloat16_rn(v[i])) * s_c0[c0 + i] + s_c1[c0 + i];
+            for (int i = 0; i < 4; ++i) {
+              const float4 sc = k0[i], sh = k1[i];
+              v[4 * i] = v[4 * i] * sc.x + sh.x;
+              v[4 * i + 1] = v[4 * i + 1] * sc.y + sh.y;
+              v[4 * i + 2] = v[4 * i + 2] * sc.z + sh.z;
+              v[4 * i + 3] = v[4 * i + 3] * sc.w + sh.w;
+            }
+          }
           if (stash) {
             float r[16];
             tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, r);
@@ -690,31 +718,28 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
           if (res_ptr != nullptr && c0 < p.res_c) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res_ptr + c0);
-            uint4 r4[2] = {__ldg(rp), __ldg(rp + 1)};
-            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(r4);
+            float r[16];
+            load16_bf16(res_ptr + c0, r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(rb[i]);
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        __align__(16) __nv_bfloat16 ob[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) ob[i] = __float2bfloat16_rn(v[i]);
+        uint4 oa, ob;
+        pack16_bf16(v, oa, ob);
         if (valid) {
           uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(pix) * p.nc + c0);
-          op[0] = reinterpret_cast<const uint4*>(ob)[0];
-          op[1] = reinterpret_cast<const uint4*>(ob)[1];
+          op[0] = oa;
+          op[1] = ob;
+        } else {
+          oa = ob = make_uint4(0u, 0u, 0u, 0u);
         }
         if (p.epi == EPI_STATS) {
           float s1[16], s2[16];
+          unpack16_bf16(oa, ob, s1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float r = valid ? __bfloat162float(ob[i]) : 0.f;
-            s1[i] = r;
-            s2[i] = r * r;
-          }
+          for (int i = 0; i < 16; ++i) s2[i] = s1[i] * s1[i];
           const float t1 = warp_colsum16(s1, lane);
           const float t2 = warp_colsum16(s2, lane);
           if ((lane & 1) == 0) {
