@@ -180,7 +180,9 @@ def test_two_training_steps_match_reference_golden(w, name, golden_dir):
     sd = m.state_dict()
     for k in gi.FULL_PARAM_KEYS(case["depth"]):
         ref = g["param/" + k]
-        assert np.abs(sd[k].cpu().numpy() - ref).max() <= 3e-2 * max(np.abs(ref).max(), 1e-3), k
+        # bf16 activations + atomically reduced weight gradients: the worst tensor (the first conv) lands 1.0-2.6 % from
+        # the fp32 reference and varies run to run (tools/two_steps_probe.py: 16 runs, 0.010-0.026) -> 5 % bound
+        assert np.abs(sd[k].cpu().numpy() - ref).max() <= 5e-2 * max(np.abs(ref).max(), 1e-3), k
     m.eval()
     lg, ft = m(gi.batch(case, 0)[0].cuda())
     assert np.abs(ft.cpu().numpy() - g["eval_feats"]).max() <= 5e-2 * np.abs(g["eval_feats"]).max()
