@@ -205,18 +205,6 @@ __device__ __forceinline__ int warp_colsum16_col(int lane) {
 // and descriptor rebuilding spent ~250-300 cycles per MMA — the main loop was bound by this thread, not by TMA or the
 // tensor core.  These loops are fully unrolled per (K steps, taps per stage): per MMA one predicate set, the MMA, and
 // immediate-offset descriptor adds.
-template <int KS>
-__device__ __forceinline__ void issue_rmerge_group(bool leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                                   uint32_t idesc, uint32_t win16, uint32_t wtap16, bool first_of_tile) {
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      if (r == 0 && k == 0) { if (leader) umma_bf16(d_tmem, adesc, bdesc, idesc, first_of_tile ? 0u : 1u); }
-      else if (leader) umma_bf16_acc(d_tmem, adesc + (r * win16 + 2 * k), bdesc + (3 * r * wtap16 + 2 * k), idesc);
-    }
-  }
-}
 // Row-merged tile: the three boxes (s = 0..2) of a stage, each feeding the three vertical taps.
 template <int KS>
 __device__ __forceinline__ void issue_rmerge_tile(bool leader, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
