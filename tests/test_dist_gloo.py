@@ -50,7 +50,14 @@ def _worker(rank, world, port, q):
     # per-epoch statistics
     acc = torch.tensor([1.0 + rank, 0.5, 1.5 + rank, 30.0 + rank])
     stats = w.train.reduce_epoch_stats(acc, steps=2, n_samples=200, world_size=world)
-    q.put((rank, same_init, covered, mean_ok, abs(scale - 1.0 / world) < 1e-12, stats))
+    # evaluation: DistributedSampler(shuffle=False) shards + the packed float64 meter reduced once (template.py:185)
+    ev_idx = w.train.sampler_indices(101, 0, rank, world, shuffle=False)
+    ev_all = [torch.zeros_like(ev_idx) for _ in range(world)]
+    dist.all_gather(ev_all, ev_idx)
+    ev_cover = (torch.cat(ev_all).unique().numel(), torch.cat(ev_all).numel())  # 101 samples, 102 with the padding duplicate
+    meter = torch.tensor([51.0, 2.0, 1.0 + rank, 40.0 + rank, 50.0, 0, 0, 0], dtype=torch.float64)
+    acc1, acc5, loss = w.train._finish_meter(meter, log=None)
+    q.put((rank, same_init, covered, mean_ok, abs(scale - 1.0 / world) < 1e-12, stats, ev_cover, (acc1, acc5, loss)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,6 +74,9 @@ def test_two_rank_gloo_host_logic():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, same_init, covered, mean_ok, scale_ok, stats in results:
+    for rank, same_init, covered, mean_ok, scale_ok, stats, ev_cover, ev in results:
         assert same_init and covered == 7000 and mean_ok and scale_ok
         assert abs(stats["ce"] - (1.0 + 2.0) / 4) < 1e-9 and abs(stats["acc1"] - 100 * 61 / 200) < 1e-9
+        assert ev_cover == (101, 102)
+        # every rank ends with the same global averages: 81 top-1 hits of 102 samples, loss 3 / 4 batches
+        assert abs(ev[0] - 100 * 81 / 102) < 1e-9 and abs(ev[1] - 100 * 100 / 102) < 1e-9 and abs(ev[2] - 0.75) < 1e-12
