@@ -1062,7 +1062,7 @@ inline void conv_pick_rmerge_pipeline(int kc, int nc, int Ht, int Wo, int& tps, 
 }
 // Pipeline shape: a stage carries `tps` tap tiles so the producer / MMA threads pay one mbarrier round trip per
 // stage instead of per tap (the MMAs themselves are only 8..32 cycles each at these channel counts).
-// Per-CTA footprint is kept under half an SM in BOTH shared memory (<= 113 KB) and registers (192 threads x 160 regs =
+// Per-CTA footprint is kept under half an SM in BOTH shared memory (<= 113 KB) and registers (192 threads x <= 160 regs =
 // 30.7 K) so that CTAs of the two concurrently running graph branches (teacher || student forward, weight gradients ||
 // data-gradient chain) can share an SM.  Measured on the overlapped step graph (profiles/r01_footprint_experiments.md):
 // 1.48 ms with this footprint vs 1.78 ms with 194 KB pipelines and 1.71 ms with 320 threads x 168 regs, although
