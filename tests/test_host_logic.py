@@ -115,3 +115,52 @@ def test_rehearsal_memory_bookkeeping_with_callable_herding(w):
         assert callable(w.RehearsalMemory(10, name).herding_method)
     with pytest.raises(ValueError):
         w.RehearsalMemory(10, "barycenter", fixed_memory=True)
+
+
+def test_checkpoint_round_trip_on_the_host(tmp_path):
+    """checkpoint.py is host logic (torch.save of reference-keyed state dicts + numpy memory): the round trip is exact
+    without a GPU."""
+    import argparse
+    import wacil_b200 as w
+    torch.manual_seed(1)
+    model = w.CilModel("resnet20", max_classes=12)
+    model.prev_model_adaption(5)
+    model.prev_model_adaption(4)
+    mem = w.RehearsalMemory(18, "barycenter")
+    mem._x, mem._y, mem._t = np.arange(18).reshape(18, 1), np.repeat(np.arange(9), 2), np.zeros(18, int)
+    mem.seen_classes = set(range(9))
+    args = argparse.Namespace(known_classes=9)
+    path = w.checkpoint.save_checkpoint(str(tmp_path / "t.pt"), model, mem, args, 1, [88.0, 70.25])
+    assert not os.path.exists(path + ".tmp")
+    mem2, args2 = w.RehearsalMemory(18, "barycenter"), argparse.Namespace(known_classes=0)
+    m2, teacher, task_id, acc1s = w.checkpoint.load_checkpoint(path, mem2, args2, device=None, restore_rng=False)
+    assert (task_id, acc1s, args2.known_classes, mem2.seen_classes) == (1, [88.0, 70.25], 9, set(range(9)))
+    assert np.array_equal(mem2.get()[0], mem.get()[0]) and len(m2.fc) == 2 and m2.num_classes == 9
+    sd1, sd2, sdt = model.state_dict(), m2.state_dict(), teacher.state_dict()
+    assert list(sd1) == list(sd2) and all(torch.equal(sd1[k], sd2[k]) and torch.equal(sd1[k], sdt[k]) for k in sd1)
+    assert not teacher.arena.requires_grad and not teacher.training and m2.arena.requires_grad
+
+
+def test_device_taskset_draws_and_runner_flags_on_the_host():
+    import argparse
+    import wacil_b200 as w
+    x, y = w.data.synthetic_cifar(nb_classes=3, per_class=4, seed=2)
+    ts = w.DeviceTaskSet(x, y, device="cpu", pad=4)
+    a, b = ts.draw_aug(50, seed=1, epoch=2, rank=0), ts.draw_aug(50, seed=1, epoch=2, rank=1)
+    assert torch.equal(a, ts.draw_aug(50, seed=1, epoch=2, rank=0)) and not torch.equal(a, b)
+    an = a.numpy()
+    assert ((an & 0xFF) <= 8).all() and (((an >> 8) & 0xFF) <= 8).all() and ((an >> 16) <= 1).all() and (an >= 0).all()
+    # the Normalize() statistics follow the reference's data_set == 'CIFAR' quirk (utils.py:228-230)
+    ns = argparse.Namespace(input_size=32, data_set="cifar")
+    assert w.data.transform_stats(ns) == (w.data.IMAGENET_DEFAULT_MEAN, w.data.IMAGENET_DEFAULT_STD)
+    ns.data_set = "CIFAR"
+    assert w.data.transform_stats(ns) == (w.data.CIFAR_MEAN, w.data.CIFAR_STD)
+    p = argparse.ArgumentParser(parents=[w.get_args_parser()])
+    w.train.add_runner_args(p)
+    args = p.parse_args(["--data_set", "synthetic", "--dynamic_lambda_kd", "--herding_method", "cluster"])
+    assert args.lambda_kd == 0.5 and args.memory_size == 2000 and args.num_bases == 50 and args.batch_size == 128
+    from wacil_b200.train import kd_weights
+    assert kd_weights(args, 50, 10, True) == (1 - 50 / 60, 50 / 60) and kd_weights(args, 0, 50, False) == (1.0, 0.5)
+    with pytest.raises(FileNotFoundError):
+        args.data_set, args.data_path = "cifar", "/nonexistent"
+        w.build_dataset(True, args, device="cpu")
