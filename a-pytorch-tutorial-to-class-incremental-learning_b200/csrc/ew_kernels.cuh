@@ -19,13 +19,6 @@ namespace wacil {
 
 struct LayerDesc {
   int cin, cin_pad, cout, stride, H_in, H_out;
-  // pixel-pair ("super-pixel") form of the 32x32-resolution convolutions: [N,32,32,C] is read as [N,32,16,2C] (same
-  // memory), the 3x3 taps become 3x3 taps over pixel pairs with expanded 2cout x 2cin weights (zero where a tap falls
-  // outside), so TMA rows are >= 64 bytes and the tile count halves
-  int sup_f;  // forward conv (output 32x32)
-  int sup_d;  // data gradient (its output, the layer input, is 32x32)
-  int sup_w;  // weight gradient (stride-1 layer on 32x32)
-  long long wscr_off;                    // fp32 scratch [9][2cin_pad][2cout] for the pixel-pair weight gradient
   long long w_off, gamma_off, beta_off;  // params arena (fp32 elements)
   long long rmean_off, rvar_off;         // bn_running arena
   long long wf_off, wd_off;              // bf16 weight buffer (elements)
@@ -61,42 +54,21 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------------ weights
-// Source weight (fp32 master [tap = 3r+s][ci][co]) of one element of an operand copy.
-//   forward, [tap][n][k]:   plain  n = co, k = ci, tap = (r, s)
-//                           pairs  n = o*cout + co, k = i*cin + ci, tap = (r, ds): s = 2*ds - 1 + i - o
-//   dgrad,   [tap'][n][k]:  plain  n = ci, k = co, tap' = 8 - tap
-//                           pairs  n = o*cin + ci, k = i*cout + co, tap' = (r', ds'): r = 2 - r', s = 3 - 2*ds' - i + o
-// Returns -1 for a structural zero.
-__device__ __forceinline__ int wsrc_fwd(const LayerDesc& L, int t, int n, int k) {
-  if (!L.sup_f) return (t * L.cin_pad + k) * L.cout + n;
-  const int o = n / L.cout, co = n - o * L.cout, i = k / L.cin_pad, ci = k - i * L.cin_pad;
-  const int r = t / 3, ds = t - 3 * r, s = 2 * ds - 1 + i - o;
-  return (s < 0 || s > 2) ? -1 : ((3 * r + s) * L.cin_pad + ci) * L.cout + co;
-}
-__device__ __forceinline__ int wsrc_bwd(const LayerDesc& L, int t, int n, int k) {
-  if (!L.sup_d) return ((8 - t) * L.cin_pad + n) * L.cout + k;
-  const int o = n / L.cin_pad, ci = n - o * L.cin_pad, i = k / L.cout, co = k - i * L.cout;
-  const int rp = t / 3, dsp = t - 3 * rp, r = 2 - rp, s = 3 - 2 * dsp - i + o;
-  return (s < 0 || s > 2) ? -1 : ((3 * r + s) * L.cin_pad + ci) * L.cout + co;
-}
-
+// Operand copies of the fp32 master weights [tap = 3r+s][ci][co]:
+//   forward [tap][n = co][k = ci];   dgrad [tap' = 8 - tap][n = ci][k = co]  (the flipped taps of the transposed conv)
 __global__ void cast_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wbuf,
                                     const LayerDesc* __restrict__ layers) {
   const LayerDesc L = layers[blockIdx.y];
   const float* w = params + L.w_off;
-  const int nf = L.sup_f ? 2 * L.cout : L.cout, kf = L.sup_f ? 2 * L.cin_pad : L.cin_pad;
-  const int nd = L.sup_d ? 2 * L.cin_pad : L.cin_pad, kd = L.sup_d ? 2 * L.cout : L.cout;
-  const int tot_f = 9 * nf * kf, tot_d = 9 * nd * kd;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot_f + tot_d; e += gridDim.x * blockDim.x) {
-    if (e < tot_f) {
-      const int k = e % kf, n = (e / kf) % nf, t = e / (kf * nf);
-      const int src = wsrc_fwd(L, t, n, k);
-      wbuf[L.wf_off + e] = __float2bfloat16_rn(src < 0 ? 0.f : w[src]);
+  const int tot = 9 * L.cout * L.cin_pad;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * tot; e += gridDim.x * blockDim.x) {
+    if (e < tot) {
+      const int k = e % L.cin_pad, n = (e / L.cin_pad) % L.cout, t = e / (L.cin_pad * L.cout);
+      wbuf[L.wf_off + e] = __float2bfloat16_rn(w[(t * L.cin_pad + k) * L.cout + n]);
     } else {
-      const int f = e - tot_f;
-      const int k = f % kd, n = (f / kd) % nd, t = f / (kd * nd);
-      const int src = wsrc_bwd(L, t, n, k);
-      wbuf[L.wd_off + f] = __float2bfloat16_rn(src < 0 ? 0.f : w[src]);
+      const int f = e - tot;
+      const int k = f % L.cout, n = (f / L.cout) % L.cin_pad, t = f / (L.cout * L.cin_pad);
+      wbuf[L.wd_off + f] = __float2bfloat16_rn(w[((8 - t) * L.cin_pad + n) * L.cout + k]);
     }
   }
 }
@@ -110,43 +82,15 @@ __global__ void fold_bn_kernel(const float* __restrict__ params, const float* __
   const float* b = params + L.beta_off;
   const float* rm = bn_running + L.rmean_off;
   const float* rv = bn_running + L.rvar_off;
-  const int nf = L.sup_f ? 2 * L.cout : L.cout, kf = L.sup_f ? 2 * L.cin_pad : L.cin_pad;
-  const int tot_f = 9 * nf * kf;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot_f; e += gridDim.x * blockDim.x) {
-    const int k = e % kf, n = (e / kf) % nf, t = e / (kf * nf);
-    const int co = n % L.cout;
-    const int src = wsrc_fwd(L, t, n, k);
-    const float sc = g[co] * rsqrtf(rv[co] + eps);
-    wbuf[L.wf_off + e] = __float2bfloat16_rn(src < 0 ? 0.f : w[src] * sc);
-    if (e < nf) {
-      const int c2 = e % L.cout;
-      const float s2 = g[c2] * rsqrtf(rv[c2] + eps);
-      bias[L.bias_off + e] = b[c2] - rm[c2] * s2;
+  const int tot = 9 * L.cout * L.cin_pad;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+    const int k = e % L.cin_pad, n = (e / L.cin_pad) % L.cout, t = e / (L.cin_pad * L.cout);
+    const float sc = g[n] * rsqrtf(rv[n] + eps);
+    wbuf[L.wf_off + e] = __float2bfloat16_rn(w[(t * L.cin_pad + k) * L.cout + n] * sc);
+    if (e < L.cout) {
+      const float s2 = g[e] * rsqrtf(rv[e] + eps);
+      bias[L.bias_off + e] = b[e] - rm[e] * s2;
     }
-  }
-}
-
-// Pixel-pair weight gradients -> the real [9][cin][cout] gradient (accumulated; the arena was zeroed at step start):
-//   dW[3r+s][ci][co] = sum over (ds, i, o) with 2*ds - 1 + i - o == s of dWs[3r+ds][i*cin+ci][o*cout+co]
-__global__ void wgrad_fold_kernel(const float* __restrict__ wscr, float* __restrict__ grads,
-                                  const LayerDesc* __restrict__ layers, const int* __restrict__ which, int n_sup) {
-  if (static_cast<int>(blockIdx.y) >= n_sup) return;
-  const LayerDesc L = layers[which[blockIdx.y]];
-  const float* src = wscr + L.wscr_off;
-  const int cin = L.cin_pad, cout = L.cout, n = 9 * cin * cout;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int co = e % cout, ci = (e / cout) % cin, t = e / (cout * cin);
-    const int r = t / 3, s = t - 3 * r;
-    float acc = 0.f;
-#pragma unroll
-    for (int ds = 0; ds < 3; ++ds)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int o = 2 * ds - 1 + i - s;
-        if (o == 0 || o == 1)
-          acc += src[(static_cast<long long>(3 * r + ds) * (2 * cin) + i * cin + ci) * (2 * cout) + o * cout + co];
-      }
-    grads[L.w_off + e] += acc;
   }
 }
 
@@ -161,8 +105,10 @@ struct BnBwdParams {
   const __nv_bfloat16* y;       // raw conv output
   const float* saved;           // mean, rstd
   const float* gamma;
-  float* dgamma;                // grads arena (accumulated by the reduce kernel, read by the apply kernel)
+  float* dgamma;                // grads arena (written by block 0 of the apply kernel)
   float* dbeta;
+  float* part;                  // [nparts][2*C] per-block partial sums of the reduce kernel (plain stores, fixed order)
+  int nparts;                   // blocks of the reduce kernel
   __nv_bfloat16* gy;            // out: gradient wrt the conv output [pix][C]
   __nv_bfloat16* gy_up;         // optional: same, scattered to even pixels of [N][2Ho][2Wo][C] (stride-2 dgrad input)
   __nv_bfloat16* gz;            // optional: masked gradient (before BN backward) for the previous block's shortcut
@@ -231,8 +177,8 @@ __device__ __forceinline__ void bn_bwd_decode(const BnBwdParams& p, const BnBwdR
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  __shared__ float s_acc[128];
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  __shared__ float s_acc[8][128];  // per-warp sums, combined in warp order (no atomics: bit-reproducible)
+  for (int i = threadIdx.x; i < 8 * 128; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
   __syncthreads();
   constexpr int kU = 2;
   const int cv = p.C / 8;                 // channel vectors per pixel (2 / 4 / 8)
@@ -279,30 +225,47 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p)
       sx[i] += __shfl_xor_sync(0xffffffffu, sx[i], o);
     }
   }
-  if ((threadIdx.x & 31) < cv) {
+  if ((threadIdx.x & 31) < cv) {  // lanes 0..cv-1 of every warp own distinct channel vectors
+    float* mine = s_acc[threadIdx.x >> 5];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[c0 + i], sg[i]);
-      atomicAdd(&s_acc[p.C + c0 + i], sx[i]);
+      mine[c0 + i] = sg[i];
+      mine[p.C + c0 + i] = sx[i];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
-    atomicAdd(p.dbeta + i, s_acc[i]);
-    atomicAdd(p.dgamma + i, s_acc[p.C + i]);
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += s_acc[wv][i];
+    p.part[static_cast<long long>(blockIdx.x) * 2 * p.C + i] = t;
   }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
-  __shared__ float s_k[64], s_a[64], s_b[64], s_mean[64], s_rstd[64];
+  __shared__ float s_k[64], s_a[64], s_b[64], s_mean[64], s_rstd[64], s_sum[2][128];
   const float inv_m = 1.f / static_cast<float>(p.num_pixels);
+  {
+    // every block adds the reduce kernel's per-block partial rows in the same fixed order (two interleaved halves)
+    const int V = 2 * p.C, half = threadIdx.x / 128, v = threadIdx.x % 128;
+    float t = 0.f;
+    if (v < V)
+      for (int r = half; r < p.nparts; r += 2) t += __ldcg(p.part + static_cast<long long>(r) * V + v);
+    s_sum[half][v] = t;
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     const float rstd = p.saved[p.C + c];
+    const float db = s_sum[0][c] + s_sum[1][c], dg = s_sum[0][p.C + c] + s_sum[1][p.C + c];
     s_mean[c] = p.saved[c];
     s_rstd[c] = rstd;
     s_k[c] = p.gamma[c] * rstd;          // dL/dy = k * (gz - a - xhat * b)
-    s_a[c] = p.dbeta[c] * inv_m;
-    s_b[c] = p.dgamma[c] * inv_m;
+    s_a[c] = db * inv_m;
+    s_b[c] = dg * inv_m;
+    if (blockIdx.x == 0) {  // the parameter gradients of this BatchNorm
+      p.dbeta[c] = db;
+      p.dgamma[c] = dg;
+    }
   }
   __syncthreads();
   constexpr int kU = 2;

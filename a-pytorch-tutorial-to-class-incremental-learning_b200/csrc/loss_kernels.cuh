@@ -465,98 +465,6 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (finish_rows<1>(part, counter, B, tot, wrote)) *loss_out = tot[0] * lscale;
 }
 
-// Variant with natural-domain arithmetic and the accurate exp2f (kept for A/B measurement, WACIL_KD_MATH=0).
-template <typename T, int TPR, int kRowCache, bool VEC>
-__global__ void __launch_bounds__(256, 3) kd_rows_kernel_v2(const T* __restrict__ s, int64_t s_ld, const T* __restrict__ t,
-                                                      int64_t t_ld, int B, int C, float invT, float gscale,
-                                                      float lscale, float* __restrict__ loss_out, T* __restrict__ g,
-                                                      int64_t g_ld, int accumulate, float* part, unsigned* counter) {
-  __shared__ float red[64];
-  constexpr int RPB = 256 / TPR;  // rows per block
-  const int tid = threadIdx.x % TPR;
-  const int row = blockIdx.x * RPB + threadIdx.x / TPR;
-  const bool live = row < B;
-  const T* sp = s + static_cast<int64_t>(live ? row : 0) * s_ld;
-  const T* tp = t + static_cast<int64_t>(live ? row : 0) * t_ld;
-
-  float a[kRowCache], b[kRowCache];
-  float ma = -INFINITY, mb = -INFINITY;
-  if (VEC) {
-#pragma unroll
-    for (int i = 0; i < kRowCache / 4; ++i) {
-      const int col = (i * TPR + tid) * 4;
-      float va[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, vb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (live && col < C) { Vec4<T>::load(sp + col, va); Vec4<T>::load(tp + col, vb); }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a[i * 4 + j] = va[j] * invT; b[i * 4 + j] = vb[j] * invT;
-        ma = fmaxf(ma, a[i * 4 + j]); mb = fmaxf(mb, b[i * 4 + j]);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < kRowCache; ++i) {
-      const int col = i * TPR + tid;
-      const bool in = live && col < C;
-      a[i] = in ? Vec4<T>::ld1(sp + col) * invT : -INFINITY;
-      b[i] = in ? Vec4<T>::ld1(tp + col) * invT : -INFINITY;
-      ma = fmaxf(ma, a[i]); mb = fmaxf(mb, b[i]);
-    }
-  }
-  RowReduce<TPR>::max2(ma, mb, red);
-  if (!live) { ma = 0.f; mb = 0.f; }
-  // One exponential per element: the cache is overwritten with e^(x - max); the KL sum is accumulated unnormalised,
-  //   sum_i p_t,i (log p_t,i - log p_s,i) = (sum_i e_b,i (b_i - a_i)) / S_b - log S_b + log S_a     (shifted logits)
-  // with 0 * log 0 := 0 (xlogy semantics of F.kl_div) for underflowed / padded entries.
-  float sa = 0.f, sb = 0.f, acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < kRowCache; ++i) {
-    const float as = a[i] - ma, bs = b[i] - mb;  // <= 0; -inf for padding
-    const float ea = exp2f(as * kLog2e), eb = exp2f(bs * kLog2e);
-    sa += ea;
-    sb += eb;
-    acc += (eb > 0.f) ? eb * (bs - as) : 0.f;
-    a[i] = ea;
-    b[i] = eb;
-  }
-  RowReduce<TPR>::sum2(sa, sb, red);
-  float dummy = 0.f;
-  RowReduce<TPR>::sum2(acc, dummy, red);
-  const float inv_sa = 1.f / sa, inv_sb = 1.f / sb;
-  const float kl = acc * inv_sb - logf(sb) + logf(sa);
-#pragma unroll
-  for (int i = 0; i < kRowCache; ++i) a[i] = (a[i] * inv_sa - b[i] * inv_sb) * gscale;  // gradient, reusing the cache
-  if (g != nullptr && live) {
-    T* gp = g + static_cast<int64_t>(row) * g_ld;
-    if (VEC) {
-#pragma unroll
-      for (int i = 0; i < kRowCache / 4; ++i) {
-        const int col = (i * TPR + tid) * 4;
-        if (col < C) {
-          float v[4] = {a[i * 4], a[i * 4 + 1], a[i * 4 + 2], a[i * 4 + 3]};
-          if (accumulate) {
-            float o[4];
-            Vec4<T>::load(gp + col, o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] += o[j];
-          }
-          Vec4<T>::store(gp + col, v);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < kRowCache; ++i) {
-        const int col = i * TPR + tid;
-        if (col < C) Vec4<T>::st1(gp + col, accumulate ? Vec4<T>::ld1(gp + col) + a[i] : a[i]);
-      }
-    }
-  }
-  if (live && tid == 0) part[row] = kl;
-  float tot[1];
-  if (finish_rows<1>(part, counter, B, tot, live && tid == 0)) *loss_out = tot[0] * lscale;
-}
-
-
 // ------------------------------------------------------------------------------------------------ CE + KD
 // One pass over the student logits of a row: softmax over C_seen (CE) and softmax-T over the first C_known
 // columns (KD) share the loaded values.  fp32 in, fp32 out.

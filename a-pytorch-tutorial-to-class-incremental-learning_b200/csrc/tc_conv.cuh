@@ -45,10 +45,9 @@ struct ConvGemmParams {
   int tps;        // taps per pipeline stage (one mbarrier round trip per stage)
   int epi;
   __nv_bfloat16* out;        // [num_pixels][nc]
-  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics).  Fused modes: [stat_reps][2*ncr] replicas of
-                             // the per-channel sums (BN_TRAIN: sum, sumsq; BNBWD: d-beta, d-gamma), zero before the launch
-  int stat_reps;             // CTA b adds into replica b % stat_reps (each replica its own 128-byte lines): the 2*nc*grid
-                             // reductions of a layer no longer queue on one L2 atomic unit
+  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics, zero before the launch).  Fused modes:
+                             // [gridDim.x][2*nc] per-CTA partial sums (BN_TRAIN: sum, sumsq; BNBWD: d-beta, d-gamma), plain
+                             // stores before the grid barrier, summed in CTA order by every CTA after it (deterministic)
   const float* bias;         // [nc] (EPI_INFER)
   const __nv_bfloat16* res;  // residual (EPI_INFER) or nullptr
   int res_stride;            // 1: same geometry as out; 2: residual is [N][2Ho][2Wo][res_c] sampled at even pixels
@@ -75,7 +74,6 @@ struct ConvGemmParams {
   __nv_bfloat16* gy_up;         // optional zero-upsampled copy (stride-2 layer l)
   __nv_bfloat16* gz;            // optional masked gradient (shortcut of the previous block)
   long long* dbg;               // optional [gridDim.x][16] clock64 timestamps of pipeline milestones (profiling)
-  int fold;                     // pixel-pair form: the nc columns are 2 x (nc/2) real channels (column c -> channel c % (nc/2))
   int pdl;                      // launched with programmatic stream serialization: wait for the upstream grid here
   int w_early;                  // weights were written >= 2 launches upstream: their TMA may precede the wait
   int rmerge;                   // row-merged activation loads (stride 1, 3x3, tile inside one image): ONE box of Ht+2 image
@@ -236,14 +234,10 @@ __device__ __forceinline__ void issue_tap_group(bool leader, uint32_t d_tmem, ui
 }
 
 constexpr int kConvThreads = 192;
-constexpr int kConvThreadsW8 = 320;  // the fused modes may run with 8 epilogue warps (two per TMEM lane quarter)
 
-// EW epilogue warps (4 or 8).  With 8, warps 2..5 and 6..9 share the four lane quarters and take alternate 16-column
-// chunks of the fused epilogues: the phases are issue-bound with one warp per scheduler.
-template <int EW>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CUtensorMap& mapW, const ConvGemmParams& p) {
+  constexpr int EW = 4;        // epilogue warps (one per TMEM lane quarter)
   constexpr int ET = EW * 32;  // epilogue threads
-  constexpr int NH = EW / 4;   // warps per lane quarter
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -446,7 +440,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
     const int quarter = warp & 3;
     const int ew = warp - 2;          // epilogue warp index
-    const int half = ew >> 2;         // which of the NH warps of this lane quarter
     const int m = quarter * 32 + lane;
     const int tid128 = threadIdx.x - 64;  // index among the ET epilogue threads
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
@@ -456,9 +449,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     float* s_c2 = s_stats + EW * 128 + 128;     // [nc]          | d-gamma / M
     float* s_mean = s_stats + EW * 128 + 192;   // [nc]
     float* s_rstd = s_stats + EW * 128 + 256;   // [nc]
-    // Pixel-pair ("fold") form: a row is two horizontally adjacent pixels, its nc columns are (pixel parity, channel);
-    // BatchNorm parameters and statistics belong to the ncr = nc/2 real channels, a row counts as two pixels.
-    const int ncr = p.fold ? p.nc / 2 : p.nc;
+    const int ncr = p.nc;
     if (p.epi == EPI_BNBWD) {
       for (int c = tid128; c < p.nc; c += ET) {
         s_mean[c] = p.saved[c % ncr];
@@ -479,9 +470,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           gres_ptr = p.g_res + base;
         } else {
           const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (p.fold) {  // the even pixel of pair w is pixel (h, 2w): source (h/2, w) of the half-resolution map
-            if ((h & 1) == 0) gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * p.Wo + w) * (2 * ncr);
-          } else if (((w | h) & 1) == 0) {
+          if (((w | h) & 1) == 0) {
             gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
           }
         }
@@ -497,7 +486,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       if (p.epi == EPI_BN_TRAIN && stash) {
         // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
         for (int c0 = 0; c0 < p.nc; c0 += 16) {
-          if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
           float r[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] = 0.f;
@@ -509,7 +497,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       tc_fence_after();
       if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
-        if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
         float v[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
@@ -532,7 +519,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           if (valid) {
             load16_bf16(p.act_in + base + c0, a);
             load16_bf16(p.y_in + base + c0, yv);
-            if (gres_ptr != nullptr && !(p.fold && p.gres_mode == 2 && c0 >= ncr)) {  // fold: only the even pixel's half
+            if (gres_ptr != nullptr) {
               float r[16];
               load16_bf16(gres_ptr + c0, r);
 #pragma unroll
@@ -561,10 +548,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
-    const int reps = p.stat_reps > 0 ? p.stat_reps : 1;
     {
-      float* g0 = p.stats + static_cast<size_t>(blockIdx.x % reps) * (2 * ncr);
-      float* g1 = g0 + ncr;
+      // this CTA's partial sums -> its own row of the [grid][2*nc] table (plain stores, released by the grid barrier):
+      // no atomics anywhere on the BatchNorm sums, so the statistics are bit-reproducible run to run
+      float* g0 = p.stats + static_cast<size_t>(blockIdx.x) * (2 * ncr);
       for (int c = tid128; c < p.nc; c += ET) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -572,8 +559,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           a0 += s_part[(2 * wv + 0) * 64 + c];
           a1 += s_part[(2 * wv + 1) * 64 + c];
         }
-        atomicAdd(g0 + c % ncr, a0);
-        atomicAdd(g1 + c % ncr, a1);
+        g0[c] = a0;
+        g0[ncr + c] = a1;
       }
     }
     // what the per-channel constants need besides the grid-wide sums is fetched before the barrier (nc <= 64 <= 128
@@ -589,13 +576,23 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     grid_barrier_epi<ET>(p.grid_bar, tid128);
     if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
-    const float cnt = static_cast<float>(p.num_pixels) * (p.fold ? 2.f : 1.f);
+    const float cnt = static_cast<float>(p.num_pixels);
+    {
+      // every CTA sums the per-CTA partial rows in the same fixed order: thread (slice, value) takes rows slice,
+      // slice + S, ... (coalesced 4*V-byte rows, all loads independent), the S slice sums are combined in order
+      const int V = 2 * p.nc, S = ET / V;  // 32/64/128 values -> 4/2/1 row slices
+      const int v = tid128 % V, sl = tid128 / V;
+      float acc = 0.f;
+      for (int r = sl; r < static_cast<int>(gridDim.x); r += S) acc += __ldcg(p.stats + static_cast<size_t>(r) * V + v);
+      s_part[sl * 128 + v] = acc;  // the per-warp partials are dead after the stores above
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 < p.nc) {
-      const int c = tid128, cc = c % ncr;
-      float t0 = 0.f, t1 = 0.f;  // replicas in fixed order
-      for (int r = 0; r < reps; ++r) {
-        t0 += __ldcg(p.stats + static_cast<size_t>(r) * (2 * ncr) + cc);
-        t1 += __ldcg(p.stats + static_cast<size_t>(r) * (2 * ncr) + ncr + cc);
+      const int c = tid128;
+      float t0 = 0.f, t1 = 0.f;
+      for (int sl = 0; sl < ET / (2 * p.nc); ++sl) {
+        t0 += s_part[sl * 128 + c];
+        t1 += s_part[sl * 128 + p.nc + c];
       }
       if (p.epi == EPI_BN_TRAIN) {
         const float mean = t0 / cnt;
@@ -634,7 +631,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         up_base = ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc;
       }
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
-        if (NH > 1 && (((as * p.nc + c0) >> 4) & (NH - 1)) != half) continue;  // the partner warp's chunk
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
         if (p.epi == EPI_BN_TRAIN) {
@@ -770,12 +766,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
 __global__ void __launch_bounds__(kConvThreads, 2)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {
-  conv_gemm_body<4>(mapA, mapW, p);
-}
-__global__ void __launch_bounds__(kConvThreadsW8, 2)
-    conv_gemm_kernel_w8(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                        const ConvGemmParams p) {
-  conv_gemm_body<8>(mapA, mapW, p);
+  conv_gemm_body(mapA, mapW, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,13 +779,14 @@ struct WgradParams {
   int tiles_h;
   int num_tiles;      // pixel tiles in total
   int ring;           // group ring depth (32 KB each)
-  float* dw;          // [taps*cin][cout] fp32, accumulated with red.global.add
+  float* part;        // [active CTAs][taps*cin][cout] fp32: every CTA that owns pixel tiles stores ITS partial sum with plain
+                      // stores (no atomics); wgrad_reduce_kernel adds the slots in CTA order -> bit-reproducible gradients
   int pdl;            // launched with programmatic stream serialization
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
+// CTAs of a wgrad launch that own pixel tiles (= partial slots written): contiguous chunks of `per` tiles
+__host__ __device__ inline int wgrad_active_ctas(int num_tiles, int grid) {
+  const int per = (num_tiles + grid - 1) / grid;
+  return (num_tiles + per - 1) / per;
 }
 
 __global__ void __launch_bounds__(kConvThreads, 2)
@@ -944,11 +936,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         float v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * p.cout + c0, v);
         if (row < rows) {
-          float* dst = p.dw + static_cast<size_t>(row) * p.cout + c0;
-          red_add_v4(dst + 0, v[0], v[1], v[2], v[3]);
-          red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
-          red_add_v4(dst + 8, v[8], v[9], v[10], v[11]);
-          red_add_v4(dst + 12, v[12], v[13], v[14], v[15]);
+          float4* dst = reinterpret_cast<float4*>(p.part + (static_cast<size_t>(blockIdx.x) * rows + row) * p.cout + c0);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+          dst[3] = make_float4(v[12], v[13], v[14], v[15]);
         }
       }
     }
@@ -959,6 +951,40 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// Ordered reduction of the per-CTA weight-gradient slots: dst[e] = part[0][e] + part[1][e] + ... in a fixed tree.
+// Eight lanes share one float4 of the result: lane j adds slots j, j+8, ... in order, then a fixed xor-shuffle tree
+// combines the eight sums.  blockIdx.y selects the layer.
+struct WgradReduceDesc {
+  const float* part;
+  float* dst;
+  int nparts;
+  int elems;  // taps*cin*cout, a multiple of 4
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ descs) {
+  const WgradReduceDesc d = descs[blockIdx.y];
+  const int n4 = d.elems >> 2;
+  const int sub = threadIdx.x & 7;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; e < ((n4 + 31) & ~31); e += (gridDim.x * blockDim.x) >> 3) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n4) {
+      const float4* src = reinterpret_cast<const float4*>(d.part) + e;
+#pragma unroll 4
+      for (int r = sub; r < d.nparts; r += 8) {
+        const float4 t = __ldcg(src + static_cast<size_t>(r) * n4);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (sub == 0 && e < n4) reinterpret_cast<float4*>(d.dst)[e] = acc;
   }
 }
 

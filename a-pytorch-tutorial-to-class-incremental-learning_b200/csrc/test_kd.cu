@@ -187,10 +187,6 @@ template <typename T> void sweep(int B, int C, float Tm) {
   CK(cudaMemset(bf.counter, 0, 64));
   const float invT = 1.f / Tm, gs = Tm / B, ls = Tm * Tm / B;
   if (C <= 8192 && C > 4096) {
-    run_variant<T>("rows_v2<256,32> (natural exp2f)", bf, ref, [&](int k) {
-      kd_rows_kernel_v2<T, 256, 32, true><<<B, 256>>>(bf.s[k], C, bf.t[k], C, B, C, invT, gs, ls, bf.loss, bf.g[k], C, 0,
-                                                      bf.part, bf.counter);
-    });
     run_variant<T>("rows<256,32> (log2 domain)", bf, ref, [&](int k) {
       kd_rows_kernel<T, 256, 32, true><<<B, 256>>>(bf.s[k], C, bf.t[k], C, B, C, invT, gs, ls, bf.loss, bf.g[k], C, 0,
                                                    bf.part, bf.counter);

@@ -97,13 +97,13 @@ static int run_conv(const Case& c) {
   CK(cudaMalloc(&dx, nx * 2));
   CK(cudaMalloc(&dw, nw * 2));
   CK(cudaMalloc(&dy, ny * 2));
-  CK(cudaMalloc(&dstats, 16 * 2 * c.nc * 4));  // room for the fused kernels' replicas
+  CK(cudaMalloc(&dstats, 296 * 2 * c.nc * 4));  // room for the fused kernels' per-CTA partial rows
   CK(cudaMalloc(&dbias, c.nc * 4));
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, wb.data(), nw * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, bias.data(), c.nc * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dy, 0xFF, ny * 2));
-  CK(cudaMemset(dstats, 0, 16 * 2 * c.nc * 4));
+  CK(cudaMemset(dstats, 0, 296 * 2 * c.nc * 4));
   if (c.res_mode) {
     CK(cudaMalloc(&dres, rb.size() * 2));
     CK(cudaMemcpy(dres, rb.data(), rb.size() * 2, cudaMemcpyHostToDevice));
@@ -150,18 +150,12 @@ static int run_conv(const Case& c) {
     p.grid_bar = dbar; p.act_out = dact; p.gamma = dbias; p.beta = dbias; p.running_mean = dscratch;
     p.running_var = dscratch + 128; p.saved = dscratch + 256; p.eps = 1e-5f; p.momentum = 0.1f;
     if (!c.res_mode) p.res = nullptr;
-    const char* ev = getenv("WACIL_STAT_REPS");
-    p.stat_reps = ev ? atoi(ev) : 1;
   }
   if (fused) p.acc_stages = (p.num_tiles + 147) / 148;  // upper bound for the shared-memory size
   const size_t smem = conv_smem_bytes(p);
-  const char* ewv = getenv("WACIL_EPI_WARPS");
-  const bool w8 = fused && ewv && atoi(ewv) == 8;
-  const int nthreads = w8 ? kConvThreadsW8 : kConvThreads;
+  const int nthreads = kConvThreads;
   CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem));
@@ -172,8 +166,7 @@ static int run_conv(const Case& c) {
   auto launch = [&]() {
     if (fused) {
       void* args[] = {&mapA, &mapW, &p};
-      CK(cudaLaunchCooperativeKernel(w8 ? (void*)conv_gemm_kernel_w8 : (void*)conv_gemm_kernel, dim3(grid), dim3(nthreads),
-                                     args, smem, 0));
+      CK(cudaLaunchCooperativeKernel((void*)conv_gemm_kernel, dim3(grid), dim3(nthreads), args, smem, 0));
     } else {
       conv_gemm_kernel<<<grid, kConvThreads, smem>>>(mapA, mapW, p);
     }
@@ -267,10 +260,13 @@ static int run_wgrad(const Case& c) {
             for (int co = 0; co < cout; ++co) ref[((size_t)t * cin + ci) * cout + co] += (double)xp[ci] * yp[co];
         }
   __nv_bfloat16 *dx, *ddy;
-  float* ddw;
+  float *ddw, *dpart;
+  WgradReduceDesc* ddesc;
   CK(cudaMalloc(&dx, nx * 2));
   CK(cudaMalloc(&ddy, ny * 2));
   CK(cudaMalloc(&ddw, nw * 4));
+  CK(cudaMalloc(&dpart, 296 * nw * 4));
+  CK(cudaMalloc(&ddesc, sizeof(WgradReduceDesc)));
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ddy, yb.data(), ny * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(ddw, 0, nw * 4));
@@ -279,7 +275,7 @@ static int run_wgrad(const Case& c) {
   conv_tile_shape(Ho, Wo, p.Ht, p.Nt, p.tiles_h);
   p.num_tiles = (int)((npix + 127) / 128);
   p.ring = 2;
-  p.dw = ddw;
+  p.part = dpart;
   CUtensorMap mapX, mapDY;
   int e1 = make_act_map(&mapX, dx, c.N, c.H, c.W, cin, c.stride, p.Ht, p.Nt);
   int e2 = make_mat_map(&mapDY, ddy, (long long)npix, cout, 128);
@@ -290,7 +286,12 @@ static int run_wgrad(const Case& c) {
   int grid = p.num_tiles < 148 ? p.num_tiles : 148;
   if (grid > 3 && !g_timing) grid = (grid + 2) / 3;  // force several tiles per CTA to exercise TMEM accumulation
   if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 296) grid = 296; }
+  {
+    WgradReduceDesc rd{dpart, ddw, wgrad_active_ctas(p.num_tiles, grid), (int)nw};
+    CK(cudaMemcpy(ddesc, &rd, sizeof(rd), cudaMemcpyHostToDevice));
+  }
   wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
+  wgrad_reduce_kernel<<<dim3(48, 1), 256>>>(ddesc);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   if (g_timing) {
@@ -303,7 +304,7 @@ static int run_wgrad(const Case& c) {
     CK(cudaDeviceSynchronize());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     printf("%-34s wgrad grid %3d : %7.2f us/launch (warm L2, back-to-back)\n", c.name, grid, 1e3 * ms / reps);
-    cudaFree(dx); cudaFree(ddy); cudaFree(ddw);
+    cudaFree(dx); cudaFree(ddy); cudaFree(ddw); cudaFree(dpart); cudaFree(ddesc);
     return 0;
   }
   std::vector<float> got(nw);
@@ -323,7 +324,7 @@ static int run_wgrad(const Case& c) {
     printf("   first bad idx %zu (tap %zu ci %zu co %zu): got %g ref %g\n", i, i / ((size_t)cin * cout),
            (i / cout) % cin, i % cout, (double)got[i], ref[i]);
   }
-  cudaFree(dx); cudaFree(ddy); cudaFree(ddw);
+  cudaFree(dx); cudaFree(ddy); cudaFree(ddw); cudaFree(dpart); cudaFree(ddesc);
   return bad ? 1 : 0;
 }
 

@@ -46,33 +46,6 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-// Pixel-pair form of the 32x32-resolution layers: bit 0 fprop, bit 1 dgrad, bit 2 wgrad (WACIL_PAIR).  Off by default:
-// the A/B on one box (profiles/r01_pair_ab.md) shows the plain form 0.9 % faster on the step (the stage-1 main loop is
-// bound by L2->SM bytes, which the pair form does not change, not by TMA row count); tests/test_gpu_engine.py keeps the
-// pair form under parity in a subprocess.
-int pair_mask() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WACIL_PAIR");
-    v = e ? (atoi(e) & 7) : 0;
-  }
-  return v;
-}
-
-// Replicas of the per-channel BatchNorm sum accumulators of the fused kernels (WACIL_STAT_REPS).  Default 1: spreading
-// the 2*nc*grid reductions of a layer over 8 replicas was measured neutral-to-slower (1.254 vs 1.232 ms/step,
-// profiles/r01_epilogue_experiments.md) — the grid barrier is bound by L2 round trips, not by the atomic unit.
-int stat_reps() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WACIL_STAT_REPS");
-    v = e ? atoi(e) : 1;
-    if (v < 1) v = 1;
-    if (v > 16) v = 16;
-  }
-  return v;
-}
-
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -111,10 +84,6 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
     d.stride = stride;
     d.H_in = H_in;
     d.H_out = H_in / stride;
-    const int pm = pair_mask();
-    d.sup_f = ((pm & 1) && d.H_out == 32) ? 1 : 0;
-    d.sup_d = ((pm & 2) && d.H_in == 32 && !L.empty()) ? 1 : 0;  // the first layer has no data gradient
-    d.sup_w = ((pm & 4) && d.H_in == 32 && stride == 1) ? 1 : 0;
     L.push_back(d);
   };
   add(3, 16, 1, 32);
@@ -128,7 +97,7 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
       add(planes[s], planes[s], 1, H);
       inpl = planes[s];
     }
-  long long off = 0, boff = 0, woff = 0, bioff = 0, scroff = 0;
+  long long off = 0, boff = 0, woff = 0, bioff = 0;
   for (auto& d : L) {
     d.w_off = off;
     off += 9LL * d.cin_pad * d.cout;
@@ -143,13 +112,11 @@ int build_layers(int depth, int max_classes, std::vector<LayerDesc>& L, wacil_ne
     d.rvar_off = boff;
     boff += d.cout;
     d.wf_off = woff;
-    woff += 9LL * d.cin_pad * d.cout * (d.sup_f ? 4 : 1);
+    woff += 9LL * d.cin_pad * d.cout;
     d.wd_off = woff;
-    woff += 9LL * d.cin_pad * d.cout * (d.sup_d ? 4 : 1);
+    woff += 9LL * d.cin_pad * d.cout;
     d.bias_off = bioff;
-    bioff += d.cout * (d.sup_f ? 2 : 1);
-    d.wscr_off = scroff;
-    if (d.sup_w) scroff += 36LL * d.cin_pad * d.cout;
+    bioff += d.cout;
   }
   if (lay) {
     lay->depth = depth;
@@ -176,34 +143,35 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, bstats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wscr, which;
-  size_t wscr_elems = 0;
-  int n_sup_w = 0;
-  std::vector<size_t> y, a, gyup;
+  size_t table, wbuf, bias, stats, bstats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wred;
+  std::vector<size_t> y, a, gyup, wpart;
   size_t stat_elems = 0, wbuf_elems = 0, total = 0;
 };
+
+// Grid of the weight-gradient kernel of a layer (pixel tiles are split into contiguous chunks, one per CTA) — also the
+// number of partial-sum slots its workspace holds.
+int wgrad_grid(int num_tiles) {
+  int g = (num_tiles + 1) / 2;
+  if (g > 2 * num_sms()) g = 2 * num_sms();
+  return g < 1 ? 1 : g;
+}
 
 void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offsets& o) {
   Carve c;
   const size_t nl = L.size();
   o.table = c.take(nl * sizeof(LayerDesc));
-  size_t wel = 0, sel = 0, scr = 0;
-  int nsw = 0;
+  size_t wel = 0, sel = 0;
   for (auto& d : L) {
-    wel += 9ull * d.cin_pad * d.cout * ((d.sup_f ? 4 : 1) + (d.sup_d ? 4 : 1));
+    wel += 2ull * 9 * d.cin_pad * d.cout;
     sel += 2ull * d.cout;
-    if (d.sup_w) { scr += 36ull * d.cin_pad * d.cout; ++nsw; }
   }
-  o.wscr_elems = scr;
-  o.n_sup_w = nsw;
   o.wbuf_elems = wel;
   o.stat_elems = sel;
   o.wbuf = c.take(wel * 2);
-  o.bias = c.take(sel * 4);  // <= 2*cout floats per layer (pixel-pair layers duplicate the bias)
-  o.wscr = c.take(scr * 4 + 16);
-  o.which = c.take(static_cast<size_t>(nsw + 1) * 4);
-  o.stats = c.take(sel * 4 * stat_reps());   // forward: per layer [reps][2*cout] sum / sumsq replicas
-  o.bstats = c.take(sel * 4 * stat_reps());  // backward: per layer [reps][2*cout] d-beta / d-gamma replicas
+  o.bias = c.take(sel * 4);
+  // per layer [CTAs][2*cout] partial BatchNorm sums of the fused kernels (forward: sum / sumsq; backward: d-beta / d-gamma)
+  o.stats = c.take(sel * 4 * num_sms());
+  o.bstats = c.take(sel * 4 * num_sms());
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
@@ -218,7 +186,14 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.y.assign(nl, 0);
   o.a.assign(nl, 0);
   o.gyup.assign(nl, 0);
+  o.wpart.assign(nl, 0);
+  o.wred = 0;
   if (mode == WACIL_NET_TRAIN) {
+    o.wred = c.take(nl * sizeof(WgradReduceDesc));
+    for (size_t l = 0; l < nl; ++l) {  // weight-gradient partial slots [CTAs][9*cin][cout] fp32
+      const int tiles = (batch * L[l].H_out * L[l].H_out + 127) / 128;
+      o.wpart[l] = c.take(static_cast<size_t>(wgrad_grid(tiles)) * 9 * L[l].cin_pad * L[l].cout * 4);
+    }
     for (size_t l = 0; l < nl; ++l) {
       const size_t out_b = static_cast<size_t>(batch) * L[l].H_out * L[l].H_out * L[l].cout * 2;
       o.y[l] = c.take(out_b);
@@ -241,20 +216,8 @@ struct ConvLaunch {
   ConvGemmParams p;
   int grid;
   size_t smem;
-  int ew = 4;  // epilogue warps: 4 (conv_gemm_kernel) or 8 (conv_gemm_kernel_w8, fused modes)
 };
 
-// Epilogue warps of the fused (BatchNorm) launches: WACIL_EPI_WARPS = 4 (default) | 8.  Two warps per TMEM lane quarter
-// were measured slower both in isolation (22.5 vs 20.9 us for the fused stage-1 layer) and on the step graph (1.234 vs
-// 1.194 ms): the post-barrier phase is not issue-bound, and the wider CTA crowds the co-resident branch.
-int fused_epi_warps() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WACIL_EPI_WARPS");
-    v = (e && atoi(e) == 8) ? 8 : 4;
-  }
-  return v;
-}
 struct WgradLaunch {
   CUtensorMap mapX, mapDY;
   WgradParams p;
@@ -309,12 +272,6 @@ int conv_attrs() {
     e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(kConvSmemMax));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel_w8, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kConvSmemMax));
   if (e == cudaSuccess)
@@ -340,7 +297,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(c.ew == 8 ? kConvThreadsW8 : kConvThreads);
+  cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -357,8 +314,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = c.ew == 8 ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel_w8, c.mapA, c.mapW, c.p)
-                            : cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel");
   return 0;
 }
@@ -366,7 +322,6 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
 // Switch a prepared launch to a fused mode: one TMEM accumulator stage per tile of a CTA.
 int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
   c.p.epi = epi;
-  c.ew = fused_epi_warps();
   c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
   if (c.p.acc_stages * c.p.nc > 512)
     return fail(WACIL_E_SHAPE, "batch too large for the fused BatchNorm path: %d tiles x %d channels per CTA > 512 TMEM "
@@ -387,7 +342,7 @@ int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
   return 0;
 }
 
-int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout,
+int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* part, int N, int H, int W, int cin, int cout,
                 int stride, int taps) {
   WgradParams& p = w.p;
   memset(&p, 0, sizeof(p));
@@ -400,15 +355,12 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* dw, int N,
   const long long npix = static_cast<long long>(N) * Ho * Wo;
   p.num_tiles = static_cast<int>((npix + 127) / 128);
   p.ring = 2;
-  p.dw = dw;
+  p.part = part;
   int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
   if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
   e = make_mat_map(&w.mapDY, dy, npix, cout, 128);
   if (e) return fail(WACIL_E_DRIVER, "wgrad dY tensor map: %d", e);
-  int g = (p.num_tiles + 1) / 2;
-  if (g > 2 * num_sms()) g = 2 * num_sms();
-  if (g < 1) g = 1;
-  w.grid = g;
+  w.grid = wgrad_grid(p.num_tiles);
   w.smem = wgrad_smem_bytes(p);
   return 0;
 }
@@ -510,14 +462,6 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   const size_t nl = n->L.size();
   cudaError_t ce = cudaMemcpy(n->ws + n->off.table, n->L.data(), nl * sizeof(LayerDesc), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "layer table upload"); }
-  {
-    std::vector<int> which;
-    for (size_t l = 0; l < nl; ++l)
-      if (n->L[l].sup_w) which.push_back(static_cast<int>(l));
-    which.push_back(-1);
-    ce = cudaMemcpy(n->ws + n->off.which, which.data(), which.size() * sizeof(int), cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "pixel-pair layer list upload"); }
-  }
   __nv_bfloat16* wbuf = n->at<__nv_bfloat16>(n->off.wbuf);
   n->fprop.resize(nl);
   if (mode == WACIL_NET_TRAIN) {
@@ -533,25 +477,20 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       size_t o = 0;
       for (size_t l = 0; l < nl; ++l) { so[l] = o; o += 2 * n->L[l].cout; }
     }
+    std::vector<WgradReduceDesc> wred(nl);
     for (size_t l = 0; l < nl; ++l) {
       const LayerDesc& d = n->L[l];
       // ---- forward: conv + batch statistics + BatchNorm + shortcut + ReLU in one cooperative launch
       ConvLaunch& c = n->fprop[l];
-      if (d.sup_f)  // 32x32 output: pixel-pair form, [N,32,32,C] read as [N,32,16,2C]
-        e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9,
-                       wbuf + d.wf_off, EPI_STATS);
-      else
-        e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
-                       wbuf + d.wf_off, EPI_STATS);
+      e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
+                     wbuf + d.wf_off, EPI_STATS);
       if (e) { delete n; return e; }
       if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) { delete n; return e; }
-      c.p.fold = d.sup_f;
       c.p.pdl = pdl_enabled() ? 1 : 0;
       c.p.w_early = l > 0 ? 1 : 0;  // layer 0 is launched right after cast_weights
       c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
       c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
-      c.p.stats = stats + so[l] * stat_reps();
-      c.p.stat_reps = stat_reps();
+      c.p.stats = stats + so[l] * num_sms();  // [grid <= SMs][2*cout] partial sums
       c.p.saved = saved + so[l];
       c.p.gamma = n->params + d.gamma_off;
       c.p.beta = n->params + d.beta_off;
@@ -566,13 +505,13 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         c.p.res_c = ds ? da.cin : c.p.nc;
       }
       // ---- wgrad: X = layer input, dY = GY[l % 3]
-      if (d.sup_w)  // pixel-pair weight gradient into a scratch, folded onto the real gradient by wgrad_fold_kernel
-        e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
-                        n->at<float>(n->off.wscr) + d.wscr_off, batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9);
-      else
-        e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
-                        n->grads + d.w_off, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
+      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
+                      n->at<float>(n->off.wpart[l]), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
+      wred[l].part = n->at<float>(n->off.wpart[l]);
+      wred[l].dst = n->grads + d.w_off;
+      wred[l].nparts = wgrad_active_ctas(n->wgrad[l].p.num_tiles, n->wgrad[l].grid);
+      wred[l].elems = 9 * d.cin_pad * d.cout;
       n->wgrad[l].p.pdl = pdl_enabled() ? 1 : 0;
       if (l > 0) {
         // ---- dgrad of layer l (stride-1 conv over GY or its zero-upsampled copy, flipped [cin][cout] weights)
@@ -580,13 +519,9 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         const LayerDesc& pd = n->L[l - 1];
         const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 3]);
         ConvLaunch& g = n->dgrad[l];
-        if (d.sup_d)
-          e = setup_conv(g, src, batch, 32, 16, 2 * d.cout, 2 * d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
-        else
-          e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
+        e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
         if (e) { delete n; return e; }
         if ((e = make_fused(g, EPI_BNBWD, gbar))) { delete n; return e; }
-        g.p.fold = d.sup_d;
         g.p.pdl = pdl_enabled() ? 1 : 0;
         g.p.w_early = 1;  // operand copies were written by cast_weights in the forward
         const int pl = static_cast<int>(l) - 1;
@@ -603,8 +538,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         g.p.gamma = n->params + pd.gamma_off;
         g.p.dgamma = n->grads + pd.gamma_off;
         g.p.dbeta = n->grads + pd.beta_off;
-        g.p.stats = n->at<float>(n->off.bstats) + so[pl] * stat_reps();
-        g.p.stat_reps = stat_reps();
+        g.p.stats = n->at<float>(n->off.bstats) + so[pl] * num_sms();
         g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 3]);
         g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
         g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
@@ -614,6 +548,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         }
       }
     }
+    ce = cudaMemcpy(n->ws + n->off.wred, wred.data(), nl * sizeof(WgradReduceDesc), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "weight-gradient reduction table upload"); }
   } else {
     // INFER: block input in tmp[cur], conv_a -> tmp[mid], conv_b (+shortcut from tmp[cur]) -> tmp[nxt]
     float* bias = n->at<float>(n->off.bias);
@@ -639,12 +575,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         if (da.stride == 2 || da.cin != da.cout) { res_stride = 2; res_c = da.cin; }
         cur = (cur + 2) % 3;
       }
-      if (d.sup_f) {
-        e = setup_conv(c, in, batch, 32, 16, 2 * d.cin_pad, 2 * d.cout, 1, 9, wbuf + d.wf_off, EPI_INFER);
-        res_c = 2 * d.cout;  // identity shortcut on the pixel-pair view
-      } else {
-        e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
-      }
+      e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
       if (e) { delete n; return e; }
       c.p.pdl = pdl_enabled() ? 1 : 0;
       c.p.w_early = 1;  // folded once per task by wacil_net_fold
@@ -734,8 +665,6 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
   ++launches;
   const __nv_bfloat16* last = nullptr;
   if (n->mode == WACIL_NET_TRAIN) {
-    cudaError_t ce = cudaMemsetAsync(n->ws + n->off.stats, 0, n->off.stat_elems * 4 * stat_reps(), st);
-    if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
     dim3 grid(36, static_cast<unsigned>(nl));  // <= 4 elements per thread for the largest (64x64x9) layers
     cast_weights_kernel<<<grid, 256, 0, st>>>(n->params, n->at<__nv_bfloat16>(n->off.wbuf),
                                               n->at<LayerDesc>(n->off.table));
@@ -774,12 +703,6 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   int launches = 0, e;
   cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
-  if (n->off.wscr_elems) {
-    ce = cudaMemsetAsync(n->ws + n->off.wscr, 0, n->off.wscr_elems * 4, st);
-    if (ce != cudaSuccess) return cuda_fail(ce, "weight-gradient scratch clear");
-  }
-  ce = cudaMemsetAsync(n->ws + n->off.bstats, 0, n->off.stat_elems * 4 * stat_reps(), st);
-  if (ce != cudaSuccess) return cuda_fail(ce, "BatchNorm-backward sums clear");
   float* dfeats = n->at<float>(n->off.dfeats);
   fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
                                                   C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
@@ -814,7 +737,9 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
     const int lanes = 256 / (d.cout / 8);
     int rgrid = static_cast<int>((bp.num_pixels + lanes - 1) / lanes);
-    if (rgrid > num_sms() * 2) rgrid = num_sms() * 2;
+    if (rgrid > num_sms()) rgrid = num_sms();
+    bp.part = n->at<float>(n->off.bstats) + soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no fused launch uses them)
+    bp.nparts = rgrid;
     bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 2), 256, 0, st>>>(bp);
@@ -831,25 +756,25 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
   } while (0)
   if (par) WACIL_EV(cudaEventRecord(n->ev_gy[nl - 1], st), "event record");
+  int pending = 0;  // weight gradients whose partial slots have not been reduced yet (layers l .. l + pending - 1)
   for (int l = nl - 1; l >= 0; --l) {
     if (par) WACIL_EV(cudaStreamWaitEvent(ws, n->ev_gy[l], 0), "event wait");
     if ((e = launch_wgrad(n->wgrad[l], ws))) return e;
-    if (par) WACIL_EV(cudaEventRecord(n->ev_wg[l], ws), "event record");
+    if (par && l > 0) WACIL_EV(cudaEventRecord(n->ev_wg[l], ws), "event record");
     ++launches;
+    if (++pending == 6 || l == 0) {  // ordered sum of the per-CTA slots -> the gradient arena, a few layers per launch
+      wgrad_reduce_kernel<<<dim3(48, static_cast<unsigned>(pending)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l);
+      WACIL_LAUNCH_CHECK("wgrad_reduce_kernel");
+      ++launches;
+      pending = 0;
+    }
+    if (par && l == 0) WACIL_EV(cudaEventRecord(n->ev_wg[0], ws), "event record");
     if (l > 0) {
       if (par && l + 2 <= nl - 1) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[l + 2], 0), "event wait");
       if ((e = launch_conv(n->dgrad[l], st))) return e;
       if (par) WACIL_EV(cudaEventRecord(n->ev_gy[l - 1], st), "event record");
       ++launches;
     }
-  }
-  if (n->off.n_sup_w > 0) {  // pixel-pair weight gradients -> real [9][cin][cout] gradients (after the last wgrad)
-    dim3 fgrid(9, static_cast<unsigned>(n->off.n_sup_w));
-    wgrad_fold_kernel<<<fgrid, 256, 0, ws>>>(n->at<float>(n->off.wscr), n->grads, n->at<LayerDesc>(n->off.table),
-                                             n->at<int>(n->off.which), n->off.n_sup_w);
-    WACIL_LAUNCH_CHECK("wgrad_fold_kernel");
-    ++launches;
-    if (par) WACIL_EV(cudaEventRecord(n->ev_wg[0], ws), "event record");
   }
   if (par) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[0], 0), "event wait");  // join (the side stream is in order)
 #undef WACIL_EV
@@ -940,15 +865,8 @@ int kd_dispatch(const void* s, int64_t s_ld, const void* t, int64_t t_ld, int B,
   } else if (C <= 4096) {
     if (vec) KD_LAUNCH(512, 8, true); else KD_LAUNCH(512, 8, false);
   } else if (C <= 8192) {
-    // A/B on B200 at B=1024, C=8192 (profiles/r01_kd_variants.log): natural-domain exp2f variant 24.2 us fp32 /
-    // 24.7 us bf16; log2-domain ex2.approx variant 32.4 us fp32 / 21.3 us bf16 -> pick per dtype (env override).
-    static int math_env = -2;
-    if (math_env == -2) { const char* ev = getenv("WACIL_KD_MATH"); math_env = ev ? (ev[0] == '0' ? 0 : 1) : -1; }
-    const int math = math_env >= 0 ? math_env : (sizeof(T) == 4 ? 0 : 1);
-    if (math == 0 && vec) {
-      kd_rows_kernel_v2<T, 256, 32, true><<<B, 256, 0, st>>>(sp, s_ld, tp, t_ld, B, C, invT, gscale, lscale, loss_out, gp,
-                                                             g_ld, accumulate, part, counter);
-    } else if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);  // 1024 x 8 measured 2x slower
+    // unaligned / strided 4K..8K-column rows (the aligned ones take the streamed kernel above)
+    if (vec) KD_LAUNCH(256, 32, true); else KD_LAUNCH(256, 32, false);  // 1024 x 8 measured 2x slower
   } else {
     return fail(WACIL_E_SHAPE, "C = %d > 8192 columns is not supported", C);
   }
@@ -1154,7 +1072,7 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
 }
 
 size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout) {
-  return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8 * stat_reps();
+  return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8 * num_sms();  // grid barrier + [CTAs][2*cout] partial sums
 }
 
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
@@ -1169,8 +1087,6 @@ int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, cons
                 res_mode);
   unsigned* gbar = static_cast<unsigned*>(workspace);
   float* stats = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 64);
-  cudaError_t ce = cudaMemsetAsync(stats, 0, static_cast<size_t>(cout) * 8 * stat_reps(), S(stream));
-  if (ce != cudaSuccess) return cuda_fail(ce, "stats clear");
   ConvLaunch c;
   int e = setup_conv(c, x, N, H, W, cin, cout, stride, 9, w, EPI_STATS);
   if (e) return e;
@@ -1178,7 +1094,6 @@ int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, cons
   c.p.out = static_cast<__nv_bfloat16*>(y);
   c.p.act_out = static_cast<__nv_bfloat16*>(a);
   c.p.stats = stats;
-  c.p.stat_reps = stat_reps();
   c.p.saved = mean_rstd;
   c.p.gamma = gamma;
   c.p.beta = beta;

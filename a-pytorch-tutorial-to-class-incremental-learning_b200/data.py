@@ -70,8 +70,11 @@ class DeviceTaskSet:
         tt = torch.zeros(len(x), dtype=torch.long) if t is None else torch.as_tensor(t).long()
         self.t = torch.cat([self.t, tt.to(dev)])
 
-    def get_raw_samples(self):
-        """TaskSet.get_raw_samples (template.py:301): numpy (x uint8 [N,H,W,3], y, t)."""
+    def get_raw_samples(self, device=False):
+        """TaskSet.get_raw_samples (template.py:301): numpy (x uint8 [N,H,W,3], y, t) like upstream, or — device=True —
+        the device tensors themselves (RehearsalMemory.add herds on the GPU and keeps the exemplars in HBM)."""
+        if device:
+            return self.x, self.y, self.t
         return self.x.cpu().numpy(), self.y.cpu().numpy(), self.t.cpu().numpy()
 
     def draw_aug(self, n, seed=0, epoch=0, rank=0):

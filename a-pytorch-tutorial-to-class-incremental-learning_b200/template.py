@@ -18,8 +18,8 @@ from . import checkpoint as ckpt
 from .data import CIFAR100_CLASS_ORDER, build_dataset
 from .model import CilModel
 from .rehearsal import RehearsalMemory
-from .train import (add_runner_args, evaluate, extract_features, get_args_parser, init_distributed_mode, init_seed,
-                    train_task)
+from .train import (add_runner_args, broadcast_buffers, evaluate, extract_features, get_args_parser,
+                    init_distributed_mode, init_seed, train_task)
 
 
 def main(args, log=print):
@@ -56,16 +56,20 @@ def main(args, log=print):
 
         def on_epoch_end(epoch, stats, _val=dataset_val):
             if (epoch + 1) % args.eval_every_epoch == 0:                      # template.py:282-283
+                broadcast_buffers(model, args.world_size)                     # DDP: rank 0's BN statistics
                 evaluate(model, _val, args, log=say)
 
         train_task(model, teacher_model, dataset_train, args, on_epoch_end=on_epoch_end, log=say)  # :246-283
+        # DDP(broadcast_buffers=True), template.py:243-244: from here on (eval, teacher snapshot, herding features,
+        # checkpoint) every rank works with rank 0's BatchNorm running statistics -> identical teacher and memory
+        broadcast_buffers(model, args.world_size)
         model.after_model_adaption(inc, args)                                 # template.py:285-286 (weight align)
         acc1 = evaluate(model, dataset_val, args, log=say)[0]                 # template.py:287
         acc1s.append(acc1)
         say(f"task id = {task_id}  @Acc1 = {acc1:.5f}, acc1s = {acc1s}")
         teacher_model = model.copy().freeze()                                 # template.py:290
         features = extract_features(model, dataset_train, args.batch_size)    # template.py:292-299
-        memory.add(*dataset_train.get_raw_samples(), features.cpu().numpy())  # template.py:300-302
+        memory.add(*dataset_train.get_raw_samples(device=True), features)    # template.py:300-302, all in HBM
         args.known_classes += inc                                             # template.py:303
         if getattr(args, "checkpoint_dir", "") and rank == 0:
             path = os.path.join(args.checkpoint_dir, f"task_{task_id:02d}.pt")

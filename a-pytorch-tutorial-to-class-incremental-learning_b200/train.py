@@ -136,6 +136,20 @@ def allreduce_grads_(flat_grads, world_size, group=None):
     return 1.0 / world_size
 
 
+def broadcast_buffers(model, world_size=None, group=None, src=0):
+    """What DistributedDataParallel(broadcast_buffers=True) gives the reference (template.py:243-244): every rank
+    evaluates, snapshots the teacher and extracts herding features with RANK 0's BatchNorm running statistics.  The
+    reference broadcasts them before every forward; the training forward itself only overwrites them (train-mode BN
+    normalises with batch statistics), so one broadcast of the 2,303-element arena at the points where they are READ
+    (before eval / teacher snapshot / feature extraction / checkpoint) leaves the same observable state."""
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world_size > 1:
+        dist.broadcast(model.bn_running, src=src, group=group)
+        model._touch()
+    return model
+
+
 def reduce_epoch_stats(acc, steps, n_samples, world_size, group=None):
     """acc = per-rank running sums [ce, kd, loss, top1-count] over `steps` steps -> global means and top-1 % over
     `n_samples` samples (the reference's MetricLogger.synchronize_between_processes, utils.py:36-43,117, once per epoch)."""
@@ -297,9 +311,7 @@ class TaskTrainer:
                 st.graph_opt = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(st.graph_opt):
                     self._opt()
-                allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
-                st.graph_opt.replay()
-            return  # capture executed nothing for forward/backward: the caller's step counts from the next replay
+            return  # capture executes nothing (no forward/backward, no update): the caller replays the step right after
         st.graph_fb.replay()
         if not single:
             allreduce_grads_(self.model._arena.grads, self.world_size, self.pg)
@@ -414,6 +426,7 @@ def update_model(model, args, nb_new_classes, stage):
         model.prev_model_adaption(nb_new_classes)
         return model
     if stage == "after":
+        broadcast_buffers(model, getattr(args, "world_size", 1))  # the teacher is a copy of rank 0's statistics
         model.after_model_adaption(nb_new_classes, args)
         return model.copy().freeze()
     raise ValueError(stage)
@@ -423,7 +436,8 @@ def update_model(model, args, nb_new_classes, stage):
 def extract_features(model, x_all, batch_size=128):
     """Features of every sample for herding (template.py:292-299), eval-mode BN, kept on the device.  `x_all`: fp32
     [N,3,32,32] tensor or a data.DeviceTaskSet (centre crop, no flip: the reference extracts through the *train*
-    transform, whose random draws differ per rank — SURVEY 8e; here every rank computes identical features)."""
+    transform, whose random draws differ per rank — SURVEY 8e).  Every rank computes identical features provided the
+    caller synchronised the BatchNorm running statistics first (broadcast_buffers; template.main does)."""
     from .data import DeviceTaskSet
     was_training = model.training
     model.eval()

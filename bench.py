@@ -310,6 +310,16 @@ def run_ours(args, rank, local_rank, world):
         ms_e2e = timed(step_e2e, args.steps, world)
     _dbg('e2e done')
     launches_per_step = tr.launches_per_step
+    # data-parallel replicas must stay in lock step (DDP semantics, template.py:243-244): compare the whole parameter
+    # arena, the momentum buffer and (after rank 0's broadcast, what the reference's DDP does) nothing else — the
+    # BatchNorm running statistics are per-rank by design until a task boundary
+    replicas_identical = None
+    if world > 1:
+        torch.cuda.synchronize()
+        mine = torch.cat([model.arena.detach().reshape(-1), tr.mom.reshape(-1)])
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        replicas_identical = bool(all(torch.equal(parts[0], p_) for p_ in parts[1:]))
     imgs = args.steps * BATCH * world
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
@@ -341,6 +351,8 @@ def run_ours(args, rank, local_rank, world):
         "step_tensor_frac": value / world * F_STEP / (pk["tflops"] * 1e12),
         "final_losses": final_loss,
     }
+    if replicas_identical is not None:
+        line["replicas_identical"] = replicas_identical
     if roof is not None:
         c = roof["conv"]
         line["roofline"] = {"bound": "hbm", "achieved": c["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -161,8 +161,8 @@ def test_runner_end_to_end_and_resume(w, tmp_path):
     """template.main on a 3-task synthetic protocol (>= 80 optimisation steps per task, the last ones at a small cosine
     learning rate, so that the BatchNorm running statistics the evaluation uses have caught up with the weights):
     learns (accuracy far above chance), writes a checkpoint per task, and a run resumed from the task-0 checkpoint
-    completes the protocol from there (the weight-gradient reductions use atomics, so two runs are not bit-identical;
-    exact state restoration is covered by test_checkpoint_round_trip_is_exact)."""
+    completes the protocol from there with bit-identical results: every reduction of the step has a fixed order, the
+    augmentation draws are seeded per (seed, epoch, rank), and the checkpoint restores the RNG streams."""
     logs = []
     acc_full = w.template.main(_runner_args(w, tmp_path / "a"), log=logs.append)
     assert len(acc_full) == 3 and acc_full[0] > 80.0 and acc_full[-1] > 40.0, acc_full  # chance: 50 % / 16.7 %
@@ -171,9 +171,45 @@ def test_runner_end_to_end_and_resume(w, tmp_path):
     acc_res = w.template.main(_runner_args(w, tmp_path / "b", ("--resume", str(ck0))), log=lambda *a: None)
     assert len(acc_res) == 3 and acc_res[0] == acc_full[0]
     assert acc_res[1] > 50.0 and acc_res[2] > 40.0, acc_res  # chance: 25 % / 16.7 %
-    s_full = torch.load(tmp_path / "a" / "task_02.pt", weights_only=False)
+    s_full = torch.load(tmp_path / "a" / "task_02.pt", weights_only=True)  # tensors + plain python only
+    s_res = torch.load(tmp_path / "b" / "task_02.pt", weights_only=True)
     assert s_full["known_classes"] == 6 and sorted(s_full["seen_classes"]) == list(range(6))
     assert len(s_full["memory"]["y"]) <= 60 + 40  # dedup_old=False keeps the upstream duplicates
+    # the resumed run IS the uninterrupted run: same accuracies, same parameters, same exemplars
+    assert acc_res == acc_full, (acc_res, acc_full)
+    assert all(torch.equal(s_full["model"][k], s_res["model"][k]) for k in s_full["model"])
+    assert torch.equal(s_full["memory"]["x"], s_res["memory"]["x"]) and torch.equal(s_full["memory"]["y"], s_res["memory"]["y"])
+    with pytest.raises(ValueError):  # resuming into a different protocol is refused up front
+        w.template.main(_runner_args(w, tmp_path / "c", ("--resume", str(ck0), "--backbone", "resnet32")), log=lambda *a: None)
+
+
+def test_device_resident_memory_matches_numpy_memory(w):
+    """RehearsalMemory fed with device tensors (template.main's path: exemplars, labels and features never leave HBM)
+    keeps exactly what the upstream-style numpy memory keeps — barycenter and cluster, growing, dedup on/off, and
+    --fixed_memory (quota = memory_size // nb_total_classes, no reduction of old classes)."""
+    rs = np.random.RandomState(3)
+    for method in ("barycenter", "cluster"):
+        for dedup, fixed in ((False, False), (True, False), (False, True)):
+            mn = w.RehearsalMemory(24, method, fixed_memory=fixed, nb_total_classes=6, dedup_old=dedup)
+            md = w.RehearsalMemory(24, method, fixed_memory=fixed, nb_total_classes=6, dedup_old=dedup)
+            for task, classes in enumerate(([0, 1], [2, 3], [4, 5])):
+                y = np.repeat(np.asarray(classes), 20)
+                x = rs.randint(0, 256, (len(y), 4, 4, 3)).astype(np.uint8)
+                t = np.full(len(y), task)
+                if task > 0:  # template.py:231: the task set contains the old exemplars again
+                    ox, oy, ot = mn.get()
+                    x, y, t = np.concatenate([x, ox]), np.concatenate([y, oy]), np.concatenate([t, ot])
+                feats = np.maximum(rs.normal(0.5, 0.3, (len(y), 64)), 0).astype(np.float32)
+                mn.add(x, y, t, feats)
+                md.add(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(t).cuda(),
+                       torch.from_numpy(feats).cuda())
+                dx, dy, dt = md.get()
+                assert dx.is_cuda and dy.is_cuda
+                nx, ny, nt = mn.get()
+                assert np.array_equal(dx.cpu().numpy(), nx) and np.array_equal(dy.cpu().numpy(), ny) \
+                    and np.array_equal(dt.cpu().numpy(), nt), (method, dedup, fixed, task)
+            if fixed:
+                assert mn.memory_per_class == 4 and all((mn.get()[1] == c).sum() >= 4 for c in range(6))
 
 
 def test_checkpoint_round_trip_is_exact(w, tmp_path):
@@ -191,7 +227,7 @@ def test_checkpoint_round_trip_is_exact(w, tmp_path):
     mem2, args2 = w.RehearsalMemory(20, "barycenter"), argparse.Namespace(known_classes=0)
     m2, teacher, task_id, acc1s = w.checkpoint.load_checkpoint(path, mem2, args2, device="cuda")
     assert task_id == 1 and acc1s == [91.0, 80.5] and args2.known_classes == 4 and mem2.seen_classes == {0, 1, 2, 3}
-    assert np.array_equal(mem2.get()[1], mem.get()[1])
+    assert np.array_equal(mem2.get_numpy()[1], mem.get()[1]) and mem2.get()[1].is_cuda  # resumed straight into HBM
     sd1, sd2 = model.state_dict(), m2.state_dict()
     assert sd1.keys() == sd2.keys() and all(torch.equal(sd1[k].cpu(), sd2[k].cpu()) for k in sd1)
     x = torch.randn(5, 3, 32, 32, device="cuda")

@@ -72,7 +72,10 @@ def _gpu_state(m, plan, depth):
     return st, a0
 
 
-@pytest.mark.parametrize("depth,batch,heads", [(20, 16, [10, 10]), (32, 32, [10, 10, 10]), (32, 9, [10])])
+@pytest.mark.parametrize("depth,batch,heads", [(20, 16, [10, 10]), (32, 32, [10, 10, 10]), (32, 9, [10]),
+                                               (32, 128, [10, 10]),      # the benchmarked configuration (task 1)
+                                               (32, 128, [10] * 10),     # task 9: 100 seen classes
+                                               (56, 32, [10, 10]), (110, 32, [10])])
 def test_train_forward_backward_matches_oracle(w, depth, batch, heads):
     """Three layers of evidence (a deep bf16 ReLU network is chaotic in its roundings, so end-to-end agreement between
     two bf16 evaluations is ~3e-3 at best and gradients disagree by several % through ReLU-mask flips):
@@ -180,9 +183,10 @@ def test_two_training_steps_match_reference_golden(w, name, golden_dir):
     sd = m.state_dict()
     for k in gi.FULL_PARAM_KEYS(case["depth"]):
         ref = g["param/" + k]
-        # bf16 activations + atomically reduced weight gradients: the worst tensor (the first conv) lands 1.0-2.6 % from
-        # the fp32 reference and varies run to run (tools/two_steps_probe.py: 16 runs, 0.010-0.026) -> 5 % bound
-        assert np.abs(sd[k].cpu().numpy() - ref).max() <= 5e-2 * max(np.abs(ref).max(), 1e-3), k
+        # bf16 activations vs the fp32 reference: the worst tensor (the first conv) lands 1-2.6 % off; the BatchNorm sums
+        # and weight gradients are reduced in a fixed order (no atomics), so the figure does not vary run to run
+        # (test_training_is_bit_reproducible) -> 3 % bound
+        assert np.abs(sd[k].cpu().numpy() - ref).max() <= 3e-2 * max(np.abs(ref).max(), 1e-3), k
     m.eval()
     lg, ft = m(gi.batch(case, 0)[0].cuda())
     assert np.abs(ft.cpu().numpy() - g["eval_feats"]).max() <= 5e-2 * np.abs(g["eval_feats"]).max()
@@ -190,7 +194,7 @@ def test_two_training_steps_match_reference_golden(w, name, golden_dir):
 
 def test_fused_trainer_equals_autograd_path_and_graph_replay(w):
     """Same step three ways: reference-style autograd (model(x); loss.backward(); torch SGD), fused eager, fused
-    CUDA graph.  They run the same kernels, so parameters agree to fp32 round-off (atomics reorder sums)."""
+    CUDA graph.  They run the same kernels, so parameters agree to fp32 round-off."""
     depth, heads = 20, [10, 10]
     sd, tsd = _mild_state(depth, heads, 11), _mild_state(depth, heads[:1], 12)
     gen = torch.Generator().manual_seed(4)
@@ -322,13 +326,55 @@ def test_mini_class_incremental_run(w):
     assert acc > 0.7, acc
 
 
-def test_pixel_pair_form_stays_under_parity():
-    """The pixel-pair form of the 32x32 layers (WACIL_PAIR=7; the default is the plain form) runs the layer-by-layer
-    parity tests in a subprocess (the switch is read once per process)."""
-    import subprocess
-    import sys
-    env = dict(os.environ, WACIL_PAIR="7")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
-                        "train_forward_backward or two_training_steps or infer_forward or fused_trainer"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("heads,known", [([10, 10], 10), ([10] * 10, 90)])
+def test_full_batch_step_matches_oracle(w, heads, known):
+    """ONE full TaskTrainer.step at the benchmarked size (ResNet-32, batch 128, teacher + CE + 0.5*KD(T=2) + SGD) against
+    wo.train_step (template.py:255-271 restated; pinned to the unmodified reference by tests/test_oracle_golden.py), for
+    task 1 (20 seen / 10 known classes) and task 9 (100 / 90).  Tolerances: CE 2e-2 relative, KD 5e-2 relative + 1e-3,
+    student logits 3e-2 of max|ref|, teacher-driven KD through the folded-BN inference path included."""
+    depth, batch = 32, 128
+    sd, tsd = _mild_state(depth, heads, 21), _mild_state(depth, heads[:-1], 22)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, 3, 32, 32, generator=gen)
+    y = torch.randint(0, sum(heads), (batch,), generator=gen)
+    ref = wo.train_step(dict(sd), tsd, x, y, depth, known, 0.05, {}, lambda_kd=0.5, T=2.0, apply_update=False)
+    m = _model_from(w, depth, sd).train()
+    t = _model_from(w, depth, tsd).copy().freeze()
+    tr = w.TaskTrainer(m, t, known, lr=0.05, lambda_kd=0.5, T=2.0, use_graph=False)
+    losses = tr.step(x.cuda(), y.cuda()).cpu()
+    ce, kd = losses[0].item(), losses[1].item()
+    assert abs(ce - ref["loss_ce"].item()) <= 2e-2 * abs(ref["loss_ce"].item()), (ce, ref["loss_ce"])
+    assert abs(kd - ref["loss_kd"].item()) <= 5e-2 * abs(ref["loss_kd"].item()) + 1e-3, (kd, ref["loss_kd"])
+    st = tr._state(batch)
+    logits = st.plan_s._logits[: batch * sum(heads)].view(batch, sum(heads)).cpu()
+    assert (logits - ref["logits"]).abs().max().item() <= 3e-2 * max(ref["logits"].abs().max().item(), 1.0)
+    top1_ref = (ref["logits"].argmax(1) == y).sum().item()
+    assert abs(losses[3].item() - top1_ref) <= 2  # logits within 3e-2 can flip a near-tie
+    # the update moved the parameters along the oracle's gradient: cosine of the conv-weight step vs -grad
+    a = m._arena
+    step = torch.cat([(a.conv_weight(l).cpu() - sd[conv + ".weight"]).reshape(-1) for l, (conv, _) in enumerate(a.names)])
+    gref = torch.cat([(ref["grads"][conv + ".weight"] + 5e-4 * sd[conv + ".weight"]).reshape(-1) for conv, _ in a.names])
+    cos = torch.nn.functional.cosine_similarity(step.double(), -gref.double(), dim=0).item()
+    assert cos >= 0.85, cos
+
+
+def test_training_is_bit_reproducible(w):
+    """The reference runs with cudnn.deterministic = True (template.py:57).  Here every reduction has a fixed order
+    (per-CTA BatchNorm partial sums, per-CTA weight-gradient slots, last-CTA loss finish): two runs of the same four
+    steps — eager and CUDA-graph replay, teacher included — must give bit-identical parameters, statistics and losses."""
+    depth, heads = 32, [10, 10]
+    sd, tsd = _mild_state(depth, heads, 31), _mild_state(depth, heads[:1], 32)
+    gen = torch.Generator().manual_seed(6)
+    xs = [torch.randn(128, 3, 32, 32, generator=gen).cuda() for _ in range(4)]
+    ys = [torch.randint(0, 20, (128,), generator=gen).cuda() for _ in range(4)]
+    outs = []
+    for run in range(3):
+        m = _model_from(w, depth, sd).train()
+        t = _model_from(w, depth, tsd).copy().freeze()
+        tr = w.TaskTrainer(m, t, 10, lr=0.05, lambda_kd=0.5, use_graph=(run == 2))
+        ls = [tr.step(x, y).clone() for x, y in zip(xs, ys)]
+        torch.cuda.synchronize()
+        outs.append((m.arena.data.clone(), m.bn_running.clone(), torch.stack(ls)))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    # the captured graph launches the same kernels with the same grids
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])

@@ -1,5 +1,7 @@
-"""Two-GPU test of the fused NVLink all-reduce + SGD step (wacil_allreduce_sgd) against NCCL all-reduce + SGD.
-Needs >= 2 CUDA devices (skipped on the 1-GPU box the driver uses for `-m gpu`; run with `gpurun --gpus 2`)."""
+"""Two-GPU tests: the fused NVLink all-reduce + SGD step (wacil_allreduce_sgd) against NCCL all-reduce + SGD, and
+template.main under torch.distributed — every rank must finish each task with the same BatchNorm statistics, the same
+teacher and the same rehearsal memory (what DDP's buffer broadcast gives the reference, template.py:243-244).
+Needs >= 2 CUDA devices (skipped on a 1-GPU box; run with `gpurun --gpus 2`)."""
 import os
 import sys
 
@@ -88,7 +90,71 @@ def test_fused_p2p_allreduce_sgd_matches_nccl():
     for rank, fused_identical, nccl_identical, rel1, rel4, kerr in results:
         assert fused_identical, "fused path: replicas must be bit-identical (fixed rank-order sums)"
         assert kerr < 2e-6, kerr  # the kernel on identical inputs: fp32 summation order only
-        # whole training runs: the atomics-ordered reductions upstream differ run to run in the last bits and the bf16
-        # forward amplifies that, for either collective
-        assert rel1 < 5e-3, rel1
-        assert rel4 < 6e-2, rel4
+        # whole training runs: NCCL's ring order vs the kernel's rank order differ in the last bits of the gradient mean
+        # and the bf16 forward amplifies that step by step; everything else is bit-reproducible
+        assert rel1 < 1e-4, rel1
+        assert rel4 < 1e-3, rel4
+
+
+def _main_worker(rank, world, port, q, tmp):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import argparse
+    import torch.distributed as dist
+    import wacil_b200 as w
+    p = argparse.ArgumentParser(parents=[w.get_args_parser()])
+    w.train.add_runner_args(p)
+    args = p.parse_args(["--data_set", "synthetic", "--nb_classes", "6", "--num_bases", "2", "--increment", "2",
+                         "--backbone", "resnet20", "--batch_size", "32", "--num_epochs", "4", "--lr", "0.05",
+                         "--memory_size", "40", "--synthetic_per_class", "96", "--synthetic_val_per_class", "32",
+                         "--eval_every_epoch", "2", "--max_tasks", "2", "--checkpoint_dir", os.path.join(tmp, "ck")])
+    captured = {}
+    orig_add = w.RehearsalMemory.add
+
+    def add(self, x, y, t, z):  # what each rank herds from, and what it keeps
+        captured.setdefault("feats", []).append(z.detach().clone())
+        orig_add(self, x, y, t, z)
+        captured["mem"] = tuple(a.clone() for a in self.get())
+
+    orig_copy = w.CilModel.copy
+
+    def copy(self):  # the teacher snapshot of template.py:290
+        new = orig_copy(self)
+        captured["teacher"] = (new.arena.detach().clone(), new.bn_running.clone())
+        return new
+
+    w.RehearsalMemory.add, w.CilModel.copy = add, copy
+    acc = w.template.main(args, log=lambda *a, **k: None)
+
+    def same(tensor):
+        parts = [torch.zeros_like(tensor) for _ in range(world)]
+        dist.all_gather(parts, tensor.contiguous())
+        return all(torch.equal(parts[0], o) for o in parts)
+
+    ok = {"teacher_params": same(captured["teacher"][0]), "teacher_bn": same(captured["teacher"][1]),
+          "features": all(same(f) for f in captured["feats"]),
+          "memory_x": same(captured["mem"][0]), "memory_y": same(captured["mem"][1])}
+    q.put((rank, ok, acc, int(captured["mem"][1].numel())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_template_main_keeps_ranks_identical(tmp_path):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_main_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    accs = [r[2] for r in results]
+    for rank, ok, acc, nmem in results:
+        assert all(ok.values()), (rank, ok)   # teacher, herding features and exemplar memory identical on every rank
+        assert len(acc) == 2 and nmem > 0
+    assert accs[0] == accs[1]  # the meter is all-reduced: same numbers everywhere
+    assert accs[0][0] > 70.0, accs
