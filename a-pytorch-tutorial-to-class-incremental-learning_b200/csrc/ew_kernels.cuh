@@ -250,7 +250,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) 
     const int V = 2 * p.C, half = threadIdx.x / 128, v = threadIdx.x % 128;
     float t = 0.f;
     if (v < V)
-      for (int r = half; r < p.nparts; r += 2) t += __ldcg(p.part + static_cast<long long>(r) * V + v);
+      for (int r0 = half; r0 < p.nparts; r0 += 2 * 16) {  // sixteen independent loads in flight, added in row order
+        float q[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = r0 + 2 * j;
+          q[j] = r < p.nparts ? __ldcg(p.part + static_cast<long long>(r) * V + v) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t += q[j];
+      }
     s_sum[half][v] = t;
   }
   __syncthreads();

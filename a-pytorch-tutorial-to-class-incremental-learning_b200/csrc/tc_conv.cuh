@@ -235,6 +235,25 @@ __device__ __forceinline__ void issue_tap_group(bool leader, uint32_t d_tmem, ui
 
 constexpr int kConvThreads = 192;
 
+// Fixed-order sum of rows first, first + step, ... (< rows) of a [rows][V] fp32 table, column v.  The loads of a batch
+// of 32 rows are independent and issued together (one L2 round trip per batch instead of one per row); the additions
+// keep the row order, so the result is the same on every CTA and every run.
+__device__ __forceinline__ float ordered_row_sum(const float* __restrict__ table, int V, int v, int first, int step,
+                                                 int rows) {
+  float acc = 0.f;
+  for (int r0 = first; r0 < rows; r0 += step * 32) {
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int r = r0 + j * step;
+      t[j] = r < rows ? __ldcg(table + static_cast<size_t>(r) * V + v) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += t[j];
+  }
+  return acc;
+}
+
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CUtensorMap& mapW, const ConvGemmParams& p) {
   constexpr int EW = 4;        // epilogue warps (one per TMEM lane quarter)
   constexpr int ET = EW * 32;  // epilogue threads
@@ -582,9 +601,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       // slice + S, ... (coalesced 4*V-byte rows, all loads independent), the S slice sums are combined in order
       const int V = 2 * p.nc, S = ET / V;  // 32/64/128 values -> 4/2/1 row slices
       const int v = tid128 % V, sl = tid128 / V;
-      float acc = 0.f;
-      for (int r = sl; r < static_cast<int>(gridDim.x); r += S) acc += __ldcg(p.stats + static_cast<size_t>(r) * V + v);
-      s_part[sl * 128 + v] = acc;  // the per-warp partials are dead after the stores above
+      // (the per-warp partials are dead after the stores above: their rows serve as scratch)
+      s_part[sl * 128 + v] = ordered_row_sum(p.stats, V, v, sl, S, static_cast<int>(gridDim.x));
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 < p.nc) {
@@ -963,18 +981,22 @@ struct WgradReduceDesc {
   int nparts;
   int elems;  // taps*cin*cout, a multiple of 4
 };
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ descs) {
-  const WgradReduceDesc d = descs[blockIdx.y];
+__device__ __forceinline__ void wgrad_reduce_body(const WgradReduceDesc& d) {
   const int n4 = d.elems >> 2;
   const int sub = threadIdx.x & 7;
   for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; e < ((n4 + 31) & ~31); e += (gridDim.x * blockDim.x) >> 3) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e < n4) {
       const float4* src = reinterpret_cast<const float4*>(d.part) + e;
-#pragma unroll 4
-      for (int r = sub; r < d.nparts; r += 8) {
-        const float4 t = __ldcg(src + static_cast<size_t>(r) * n4);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      for (int r0 = sub; r0 < d.nparts; r0 += 8 * 8) {  // eight independent 16-byte loads in flight per lane
+        float4 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r0 + 8 * j;
+          t[j] = r < d.nparts ? __ldcg(src + static_cast<size_t>(r) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
       }
     }
 #pragma unroll
@@ -987,6 +1009,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc
     if (sub == 0 && e < n4) reinterpret_cast<float4*>(d.dst)[e] = acc;
   }
 }
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ descs) {
+  wgrad_reduce_body(descs[blockIdx.y]);
+}
+__global__ void __launch_bounds__(256) wgrad_reduce_one_kernel(const WgradReduceDesc d) { wgrad_reduce_body(d); }
 
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor-map construction and launch helpers (no torch, no allocation).

@@ -11,6 +11,7 @@
 #include "ew_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "tc_conv.cuh"
+#include "tc_chain.cuh"
 
 using namespace wacil;
 
@@ -143,10 +144,14 @@ struct Carve {
 };
 
 struct Offsets {
-  size_t table, wbuf, bias, stats, bstats, saved, a0, dfeats, gbar, gy[3], gz[2], tmp[3], wred;
-  std::vector<size_t> y, a, gyup, wpart;
+  size_t table, wbuf, bias, stats, bstats, saved, a0, dfeats, gbar, sync_f, sync_b, gz[2], tmp[4], wred, ctab, cmaps;
+  std::vector<size_t> y, a, gy, gyup, wpart;
+  std::vector<size_t> flag_f, flag_b;  // per chain element: offset of its ready flags inside sync_f / sync_b
+  size_t sync_f_bytes = 0, sync_b_bytes = 0;
   size_t stat_elems = 0, wbuf_elems = 0, total = 0;
 };
+
+constexpr int kSyncCounters = 64;  // grid-barrier counters (one per chain launch) at the head of a sync region
 
 // Grid of the weight-gradient kernel of a layer (pixel tiles are split into contiguous chunks, one per CTA) — also the
 // number of partial-sum slots its workspace holds.
@@ -155,6 +160,8 @@ int wgrad_grid(int num_tiles) {
   if (g > 2 * num_sms()) g = 2 * num_sms();
   return g < 1 ? 1 : g;
 }
+
+inline int tiles_of(int batch, int H) { return (batch * H * H + 127) / 128; }
 
 void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offsets& o) {
   Carve c;
@@ -176,6 +183,25 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
   o.gbar = c.take(64);
+  // chain tables: one ChainLayer + two tensor maps per chain element (forward: nl; backward: nl - 1)
+  o.ctab = c.take(2 * nl * sizeof(ChainLayer));
+  o.cmaps = c.take(2 * nl * 2 * sizeof(CUtensorMap));
+  // sync regions (zeroed at the start of every forward / backward): barrier counters, then per-tile ready flags
+  o.flag_f.assign(nl, 0);
+  o.flag_b.assign(nl, 0);
+  size_t ff = kSyncCounters * 4, fb = kSyncCounters * 4;
+  for (size_t l = 0; l < nl; ++l) {
+    o.flag_f[l] = ff;
+    ff += static_cast<size_t>(tiles_of(batch, L[l].H_out)) * 4;
+    if (l >= 1) {  // backward element of layer l produces the gradient wrt y_{l-1}: tiles of layer l-1's output
+      o.flag_b[l] = fb;
+      fb += static_cast<size_t>(tiles_of(batch, L[l - 1].H_out)) * 4;
+    }
+  }
+  o.sync_f_bytes = ff;
+  o.sync_f = c.take(ff);
+  o.sync_b_bytes = mode == WACIL_NET_TRAIN ? fb : 0;
+  o.sync_b = mode == WACIL_NET_TRAIN ? c.take(fb) : 0;
   size_t max_act = 0;
   for (auto& d : L) {
     const size_t in_b = static_cast<size_t>(batch) * d.H_in * d.H_in * d.cin_pad * 2;
@@ -185,28 +211,33 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   }
   o.y.assign(nl, 0);
   o.a.assign(nl, 0);
+  o.gy.assign(nl, 0);
   o.gyup.assign(nl, 0);
   o.wpart.assign(nl, 0);
   o.wred = 0;
+  o.gz[0] = o.gz[1] = 0;
+  for (int i = 0; i < 4; ++i) o.tmp[i] = 0;
   if (mode == WACIL_NET_TRAIN) {
     o.wred = c.take(nl * sizeof(WgradReduceDesc));
     for (size_t l = 0; l < nl; ++l) {  // weight-gradient partial slots [CTAs][9*cin][cout] fp32
-      const int tiles = (batch * L[l].H_out * L[l].H_out + 127) / 128;
+      const int tiles = tiles_of(batch, L[l].H_out);
       o.wpart[l] = c.take(static_cast<size_t>(wgrad_grid(tiles)) * 9 * L[l].cin_pad * L[l].cout * 4);
     }
     for (size_t l = 0; l < nl; ++l) {
       const size_t out_b = static_cast<size_t>(batch) * L[l].H_out * L[l].H_out * L[l].cout * 2;
       o.y[l] = c.take(out_b);
       o.a[l] = c.take(out_b);
+      // every layer keeps its own gradient buffer: the data-gradient chain never waits for a weight-gradient kernel
+      // (which reads GY_l) to release one
+      o.gy[l] = c.take(out_b);
       if (L[l].stride == 2) o.gyup[l] = c.take(out_b * 4);
     }
-    for (int i = 0; i < 3; ++i) o.gy[i] = c.take(max_act);
     o.gz[0] = c.take(max_act);
     o.gz[1] = c.take(max_act);
-    o.tmp[0] = o.tmp[1] = o.tmp[2] = 0;
   } else {
-    for (int i = 0; i < 3; ++i) o.tmp[i] = c.take(max_act);
-    o.gy[0] = o.gy[1] = o.gy[2] = o.gz[0] = o.gz[1] = 0;
+    // four rotating activation buffers: a CTA may run a layer ahead of a distant one (only neighbouring tiles are
+    // ordered by the ready flags), the fourth buffer keeps a block input alive one block longer than its last reader
+    for (int i = 0; i < 4; ++i) o.tmp[i] = c.take(max_act);
   }
   o.total = c.off;
 }
@@ -216,6 +247,7 @@ struct ConvLaunch {
   ConvGemmParams p;
   int grid;
   size_t smem;
+  int dep_up = 0;  // chain element: the input tensor is a zero-upsampled copy of the previous element's output
 };
 
 struct WgradLaunch {
@@ -227,8 +259,10 @@ struct WgradLaunch {
 
 int conv_max_resident(size_t smem);
 
+// ring_budget > 0: the operand ring of a chain launch has this many bytes (the weight tile lives beside it);
+// 0: the single-layer kernel's own half-SM budget.
 int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int nc, int stride, int taps,
-               const void* wts, int epi) {
+               const void* wts, int epi, size_t ring_budget = 0) {
   ConvGemmParams& p = c.p;
   memset(&p, 0, sizeof(p));
   const int Ho = H / stride, Wo = W / stride;
@@ -241,13 +275,11 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   p.num_tiles = (p.num_pixels + 127) / 128;
   p.Ho = Ho;
   p.Wo = Wo;
-  {
-    static int rm_env = -2;  // WACIL_RMERGE=0 restores one box per tap
-    if (rm_env == -2) { const char* ev = getenv("WACIL_RMERGE"); rm_env = ev ? (ev[0] == '0' ? 0 : 1) : 1; }
-    p.rmerge = (rm_env && conv_can_rmerge(kc, nc, taps, stride, Ho, Wo)) ? 1 : 0;
-  }
-  if (p.rmerge) conv_pick_rmerge_pipeline(kc, nc, p.Ht, Wo, p.tps, p.stages);
-  else conv_pick_pipeline(kc, nc, taps, p.tps, p.stages);
+  size_t total = kConvSmemMax;
+  if (ring_budget > 0) total = ring_budget + 6144 + (((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023));
+  p.rmerge = conv_can_rmerge(kc, nc, taps, stride, Ho, Wo, total) ? 1 : 0;
+  if (p.rmerge) conv_pick_rmerge_pipeline(kc, nc, p.Ht, Wo, p.tps, p.stages, total);
+  else conv_pick_pipeline(kc, nc, taps, p.tps, p.stages, total);
   p.epi = epi;
   p.acc_stages = 2;
   p.res_stride = 1;
@@ -258,10 +290,12 @@ int setup_conv(ConvLaunch& c, const void* in, int N, int H, int W, int kc, int n
   if (e) return fail(WACIL_E_DRIVER, "weight tensor map (%dx%d): %d", nc, kc, e);
   c.smem = conv_smem_bytes(p);
   // one CTA per SM: oversubscribing the non-cooperative launches 2x was measured slower (1.43 vs 1.36 ms/step)
-  const int cap = conv_max_resident(c.smem);
+  const int cap = ring_budget > 0 ? num_sms() : conv_max_resident(c.smem);
   c.grid = p.num_tiles < cap ? p.num_tiles : cap;
   return 0;
 }
+
+constexpr size_t kChainSmemMax = 227 * 1024;
 
 int conv_attrs() {
   static bool set = false;
@@ -277,7 +311,19 @@ int conv_attrs() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv/wgrad)");
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kChainSmemMax));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_chain_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kChainSmemMax));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_chain_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv/wgrad/chain)");
   set = true;
   return 0;
 }
@@ -319,7 +365,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   return 0;
 }
 
-// Switch a prepared launch to a fused mode: one TMEM accumulator stage per tile of a CTA.
+// Switch a prepared single-layer launch to a fused mode: one TMEM accumulator stage per tile of a CTA.
 int make_fused(ConvLaunch& c, int epi, unsigned* grid_bar) {
   c.p.epi = epi;
   c.p.acc_stages = (c.p.num_tiles + c.grid - 1) / c.grid;
@@ -382,6 +428,63 @@ int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------- chain launches
+// Tuning knobs of the chain launches (host side only; the defaults are the measured best, profiles/r02_chain_ab.md):
+//   WACIL_CHAIN_EW     epilogue warps of the fused (BatchNorm) chains: 4 | 8
+//   WACIL_CHAIN_FWD    layers per forward launch (a launch never crosses a resolution change)
+//   WACIL_CHAIN_BWD    layers per backward launch (the weight gradients of a launch's layers start when it ends)
+//   WACIL_CHAIN_SMEM   shared-memory budget of a chain CTA in KB (<= 227)
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 8, 4, 8); return v == 8 ? 8 : 4; }
+int chain_fwd_len() { static int v = env_int("WACIL_CHAIN_FWD", 64, 1, 1000); return v; }
+int chain_bwd_len() { static int v = env_int("WACIL_CHAIN_BWD", 4, 1, 1000); return v; }
+size_t chain_smem_budget() { static int v = env_int("WACIL_CHAIN_SMEM", 113, 48, 227); return static_cast<size_t>(v) * 1024; }
+
+struct ChainPlan {
+  ChainParams cp;
+  int grid = 0, ew = 4, first = 0, count = 0;
+  size_t smem = 0;
+};
+
+inline uint32_t w_tile_bytes(int kc, int nc) { return static_cast<uint32_t>((9u * nc * kc * 2 + 1023) & ~1023u); }
+
+// Operand-ring bytes a chain whose widest weight tile is w_max gets inside the shared-memory budget.
+size_t chain_ring_bytes(uint32_t w_max, int ew) {
+  const size_t fixed = chain_smem_bytes(w_max, 0, ew);
+  const size_t budget = chain_smem_budget();
+  if (budget <= fixed + 8192) return 8192;
+  return (budget - fixed) & ~size_t(1023);
+}
+
+int launch_chain(const ChainPlan& c, cudaStream_t st) {
+  { int e0 = conv_attrs(); if (e0) return e0; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(c.grid);
+  cfg.blockDim = dim3(96 + 32 * c.ew);
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;  // grid barriers and cross-CTA ready flags: all CTAs co-resident
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (c.cp.pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t e = c.ew == 8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<8>, c.cp) : cudaLaunchKernelEx(&cfg, conv_chain_kernel<4>, c.cp);
+  if (e != cudaSuccess) return cuda_fail(e, "conv_chain_kernel");
+  return 0;
+}
+
 }  // namespace
 
 // ============================================================================================ the engine
@@ -392,11 +495,13 @@ struct wacil_net {
   Offsets off;
   float *params, *grads, *bn;
   uint8_t* ws;
-  std::vector<ConvLaunch> fprop, dgrad;
+  std::vector<ConvLaunch> fprop, dgrad;   // chain elements: forward layer l; backward element of layer l (l >= 1)
   std::vector<WgradLaunch> wgrad;
+  std::vector<ChainPlan> fchains, bchains;
   bool fwd_done = false;
-  cudaStream_t side = nullptr;          // optional second stream: weight gradients overlap the data-gradient chain
-  std::vector<cudaEvent_t> ev_gy, ev_wg;  // GY_l ready (main) / wgrad_l done (side)
+  cudaStream_t side = nullptr;            // optional second stream: weight gradients run beside the data-gradient chain
+  std::vector<cudaEvent_t> ev_chain;      // backward chain i finished (main stream)
+  cudaEvent_t ev_join = nullptr;          // all weight gradients reduced (side stream)
   const float* last_feats = nullptr;
   bool folded = false;
   int launches = 0;
@@ -404,6 +509,54 @@ struct wacil_net {
   template <typename T> T* at(size_t o) const { return reinterpret_cast<T*>(ws + o); }
   __nv_bfloat16* act_in(int l) const { return l == 0 ? at<__nv_bfloat16>(off.a0) : at<__nv_bfloat16>(off.a[l - 1]); }
 };
+
+namespace {
+
+// Fill one ChainLayer from a prepared ConvLaunch (geometry + epilogue operands) and its place in the launch.
+void fill_chain_layer(ChainLayer& cl, const ConvLaunch& c, const ConvLaunch* prev, int grid, unsigned* flags,
+                      const unsigned* dep_flags) {
+  memset(&cl, 0, sizeof(cl));
+  const ConvGemmParams& p = c.p;
+  cl.kc = p.kc; cl.nc = p.nc; cl.stride = p.stride; cl.Ht = p.Ht; cl.Nt = p.Nt; cl.tiles_h = p.tiles_h;
+  cl.num_tiles = p.num_tiles; cl.num_pixels = p.num_pixels; cl.Ho = p.Ho; cl.Wo = p.Wo;
+  cl.rmerge = p.rmerge; cl.tps = p.tps; cl.stages = p.stages; cl.epi = p.epi;
+  cl.flags = flags;
+  if (prev != nullptr) {
+    const ConvGemmParams& q = prev->p;
+    const int nacc = (p.num_tiles + grid - 1) / grid, pacc = (q.num_tiles + grid - 1) / grid;
+    cl.tmem_sync = (p.nc != q.nc || nacc != pacc) ? 1 : 0;
+    const size_t st = p.rmerge ? (size_t)3 * (p.Ht + 2) * p.Wo * p.kc * 2 : (size_t)p.tps * 128 * p.kc * 2;
+    const size_t sq = q.rmerge ? (size_t)3 * (q.Ht + 2) * q.Wo * q.kc * 2 : (size_t)q.tps * 128 * q.kc * 2;
+    cl.ring_sync = (st != sq || p.stages != q.stages) ? 1 : 0;
+    cl.dep = 1;
+    cl.dep_H = q.Ho; cl.dep_W = q.Wo; cl.dep_tiles = q.num_tiles; cl.dep_up = c.dep_up;
+    cl.dep_flags = dep_flags;
+  }
+  cl.res_stride = p.res_stride; cl.res_c = p.res_c; cl.gres_mode = p.gres_mode;
+  cl.eps = kBnEps; cl.momentum = kBnMomentum;
+  cl.out = p.out; cl.act_out = p.act_out; cl.res = p.res; cl.bias = p.bias;
+  cl.gamma = p.gamma; cl.beta = p.beta; cl.running_mean = p.running_mean; cl.running_var = p.running_var;
+  cl.saved = p.saved; cl.stats = p.stats;
+  cl.g_res = p.g_res; cl.act_in = p.act_in; cl.y_in = p.y_in; cl.dgamma = p.dgamma; cl.dbeta = p.dbeta;
+  cl.gy = p.gy; cl.gy_up = p.gy_up; cl.gz = p.gz;
+}
+
+// Group consecutive elements [0, n) into launches: a new launch starts where `starts_group(i)` says the resolution
+// changes, or after `max_len` elements.
+template <typename F>
+std::vector<std::pair<int, int>> split_chains(int n, int max_len, F starts_group) {
+  std::vector<std::pair<int, int>> out;
+  int first = 0;
+  for (int i = 1; i <= n; ++i) {
+    if (i == n || starts_group(i) || i - first >= max_len) {
+      out.emplace_back(first, i - first);
+      first = i;
+    }
+  }
+  return out;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -459,161 +612,293 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     return fail(WACIL_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, n->off.total);
   }
   n->params = params; n->grads = grads; n->bn = bn_running; n->ws = static_cast<uint8_t*>(workspace);
-  const size_t nl = n->L.size();
+  const int nl = static_cast<int>(n->L.size());
   cudaError_t ce = cudaMemcpy(n->ws + n->off.table, n->L.data(), nl * sizeof(LayerDesc), cudaMemcpyHostToDevice);
   if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "layer table upload"); }
   __nv_bfloat16* wbuf = n->at<__nv_bfloat16>(n->off.wbuf);
+  const int ew_fused = chain_ew();
+  const bool pdl = pdl_enabled();
+  std::vector<size_t> so(nl);
+  {
+    size_t o = 0;
+    for (int l = 0; l < nl; ++l) { so[l] = o; o += 2 * n->L[l].cout; }
+  }
+  // a launch never spans a resolution change: the stride-2 layer opens the next group (its weight tile and operand
+  // ring are sized with that group's)
+  auto fwd_group_start = [&](int l) { return n->L[l].stride == 2; };
   n->fprop.resize(nl);
+  std::vector<ChainLayer> tab(2 * nl);
+  std::vector<CUtensorMap> maps(4 * nl);
+  ChainLayer* dtab = n->at<ChainLayer>(n->off.ctab);
+  CUtensorMap* dmaps = n->at<CUtensorMap>(n->off.cmaps);
+  unsigned* sync_f = n->at<unsigned>(n->off.sync_f);
+
+  // ------------------------------------------------------------------------------------------ forward chains
+  const int fwd_ew = mode == WACIL_NET_TRAIN ? ew_fused : 4;
+  const auto fsplit = split_chains(nl, chain_fwd_len(), fwd_group_start);
+  float* bias = n->at<float>(n->off.bias);
+  int cur = 0;  // INFER: rotating buffer holding the current block input
+  for (size_t ci = 0; ci < fsplit.size(); ++ci) {
+    const int first = fsplit[ci].first, count = fsplit[ci].second;
+    uint32_t w_max = 0;
+    for (int l = first; l < first + count; ++l) w_max = std::max(w_max, w_tile_bytes(n->L[l].cin_pad, n->L[l].cout));
+    const size_t ring = chain_ring_bytes(w_max, fwd_ew);
+    int max_tiles = 0;
+    for (int l = first; l < first + count; ++l) {
+      const LayerDesc& d = n->L[l];
+      ConvLaunch& c = n->fprop[l];
+      if (mode == WACIL_NET_TRAIN) {
+        e = setup_conv(c, n->act_in(l), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off,
+                       EPI_BN_TRAIN, ring);
+        if (e) { delete n; return e; }
+        c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
+        c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
+        c.p.stats = n->at<float>(n->off.stats) + so[l] * num_sms();  // [grid <= SMs][2*cout] partial sums
+        c.p.saved = n->at<float>(n->off.saved) + so[l];
+        c.p.gamma = n->params + d.gamma_off;
+        c.p.beta = n->params + d.beta_off;
+        c.p.running_mean = n->bn + d.rmean_off;
+        c.p.running_var = n->bn + d.rvar_off;
+        c.p.res = nullptr;
+        if (l >= 2 && l % 2 == 0) {  // conv_b: add the block input through the shortcut
+          const LayerDesc& da = n->L[l - 1];
+          c.p.res = n->act_in(l - 1);
+          const bool ds = (da.stride == 2 || da.cin != da.cout);
+          c.p.res_stride = ds ? 2 : 1;
+          c.p.res_c = ds ? da.cin : c.p.nc;
+        }
+      } else {
+        // INFER: block input in tmp[cur], conv_a -> tmp[cur+1], conv_b (+ shortcut from tmp[cur]) -> tmp[cur+2]
+        const void* in;
+        __nv_bfloat16* outp;
+        const __nv_bfloat16* res = nullptr;
+        int res_stride = 1, res_c = d.cout;
+        if (l == 0) {
+          in = n->at<void>(n->off.a0);
+          outp = n->at<__nv_bfloat16>(n->off.tmp[cur]);
+        } else if (l % 2 == 1) {  // conv_a
+          in = n->at<void>(n->off.tmp[cur]);
+          outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 1) % 4]);
+        } else {  // conv_b
+          in = n->at<void>(n->off.tmp[(cur + 1) % 4]);
+          outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 2) % 4]);
+          res = n->at<__nv_bfloat16>(n->off.tmp[cur]);
+          const LayerDesc& da = n->L[l - 1];
+          if (da.stride == 2 || da.cin != da.cout) { res_stride = 2; res_c = da.cin; }
+          cur = (cur + 2) % 4;
+        }
+        e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER, ring);
+        if (e) { delete n; return e; }
+        c.p.out = outp;
+        c.p.bias = bias + d.bias_off;
+        c.p.res = res;
+        c.p.res_stride = res_stride;
+        c.p.res_c = res_c;
+      }
+      max_tiles = std::max(max_tiles, c.p.num_tiles);
+    }
+    ChainPlan cpn;
+    cpn.first = first; cpn.count = count; cpn.ew = fwd_ew;
+    cpn.grid = std::min(max_tiles, num_sms());
+    uint32_t cols = 0;
+    for (int l = first; l < first + count; ++l) {
+      const ConvLaunch& c = n->fprop[l];
+      const int nacc = (c.p.num_tiles + cpn.grid - 1) / cpn.grid;
+      uint32_t need = mode == WACIL_NET_TRAIN ? static_cast<uint32_t>(nacc * c.p.nc) * (c.p.res != nullptr ? 2u : 1u) : 128u;
+      if (mode == WACIL_NET_TRAIN && nacc > kChainMaxSlots) need = 1024;
+      cols = std::max(cols, need);
+      const bool last = l == first + count - 1;
+      unsigned* flags = last ? nullptr : sync_f + n->off.flag_f[l] / 4;
+      const unsigned* dflags = l > first ? sync_f + n->off.flag_f[l - 1] / 4 : nullptr;
+      fill_chain_layer(tab[l], c, l > first ? &n->fprop[l - 1] : nullptr, cpn.grid, flags, dflags);
+      maps[2 * l] = c.mapA;
+      maps[2 * l + 1] = c.mapW;
+    }
+    if (cols > 256) {
+      delete n;
+      return fail(WACIL_E_SHAPE, "batch %d too large for the fused BatchNorm path (%u TMEM columns per CTA > 256)", batch, cols);
+    }
+    cpn.cp.layers = dtab + first;
+    cpn.cp.maps = dmaps + 2 * first;
+    cpn.cp.n_layers = count;
+    cpn.cp.grid_bar = sync_f + ci;
+    cpn.cp.pdl = pdl ? 1 : 0;
+    cpn.cp.w_bytes_max = w_max;
+    cpn.cp.ring_bytes = static_cast<uint32_t>(ring);
+    cpn.cp.tmem_cols = 32;
+    while (cpn.cp.tmem_cols < cols) cpn.cp.tmem_cols <<= 1;
+    cpn.cp.dbg = nullptr;
+    cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), fwd_ew);
+    if (static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+    n->fchains.push_back(cpn);
+  }
+
   if (mode == WACIL_NET_TRAIN) {
+    // ---------------------------------------------------------------------------------------- backward
     n->dgrad.resize(nl);
     n->wgrad.resize(nl);
-    float* stats = n->at<float>(n->off.stats);
-    float* saved = n->at<float>(n->off.saved);
-    unsigned* gbar = n->at<unsigned>(n->off.gbar);
-    ce = cudaMemset(gbar, 0, 64);
-    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "grid barrier clear"); }
-    std::vector<size_t> so(nl);
-    {
-      size_t o = 0;
-      for (size_t l = 0; l < nl; ++l) { so[l] = o; o += 2 * n->L[l].cout; }
-    }
     std::vector<WgradReduceDesc> wred(nl);
-    for (size_t l = 0; l < nl; ++l) {
+    unsigned* sync_b = n->at<unsigned>(n->off.sync_b);
+    for (int l = 0; l < nl; ++l) {
       const LayerDesc& d = n->L[l];
-      // ---- forward: conv + batch statistics + BatchNorm + shortcut + ReLU in one cooperative launch
-      ConvLaunch& c = n->fprop[l];
-      e = setup_conv(c, n->act_in(static_cast<int>(l)), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9,
-                     wbuf + d.wf_off, EPI_STATS);
+      // wgrad: X = layer input, dY = GY_l (its own buffer)
+      e = setup_wgrad(n->wgrad[l], n->act_in(l), n->at<void>(n->off.gy[l]), n->at<float>(n->off.wpart[l]), batch, d.H_in,
+                      d.H_in, d.cin_pad, d.cout, d.stride, 9);
       if (e) { delete n; return e; }
-      if ((e = make_fused(c, EPI_BN_TRAIN, gbar))) { delete n; return e; }
-      c.p.pdl = pdl_enabled() ? 1 : 0;
-      c.p.w_early = l > 0 ? 1 : 0;  // layer 0 is launched right after cast_weights
-      c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
-      c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
-      c.p.stats = stats + so[l] * num_sms();  // [grid <= SMs][2*cout] partial sums
-      c.p.saved = saved + so[l];
-      c.p.gamma = n->params + d.gamma_off;
-      c.p.beta = n->params + d.beta_off;
-      c.p.running_mean = n->bn + d.rmean_off;
-      c.p.running_var = n->bn + d.rvar_off;
-      c.p.res = nullptr;
-      if (l >= 2 && l % 2 == 0) {  // conv_b: add the block input through the shortcut
-        const LayerDesc& da = n->L[l - 1];
-        c.p.res = n->act_in(static_cast<int>(l) - 1);
-        const bool ds = (da.stride == 2 || da.cin != da.cout);
-        c.p.res_stride = ds ? 2 : 1;
-        c.p.res_c = ds ? da.cin : c.p.nc;
-      }
-      // ---- wgrad: X = layer input, dY = GY[l % 3]
-      e = setup_wgrad(n->wgrad[l], n->act_in(static_cast<int>(l)), n->at<void>(n->off.gy[l % 3]),
-                      n->at<float>(n->off.wpart[l]), batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9);
-      if (e) { delete n; return e; }
+      n->wgrad[l].p.pdl = pdl ? 1 : 0;
       wred[l].part = n->at<float>(n->off.wpart[l]);
       wred[l].dst = n->grads + d.w_off;
       wred[l].nparts = wgrad_active_ctas(n->wgrad[l].p.num_tiles, n->wgrad[l].grid);
       wred[l].elems = 9 * d.cin_pad * d.cout;
-      n->wgrad[l].p.pdl = pdl_enabled() ? 1 : 0;
-      if (l > 0) {
-        // ---- dgrad of layer l (stride-1 conv over GY or its zero-upsampled copy, flipped [cin][cout] weights)
-        //      fused with the ReLU mask + BatchNorm backward of layer l-1
-        const LayerDesc& pd = n->L[l - 1];
-        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l % 3]);
+      if (d.stride == 2) {
+        ce = cudaMemset(n->ws + n->off.gyup[l], 0, static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
+        if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "gy_up clear"); }
+      }
+    }
+    ce = cudaMemcpy(n->ws + n->off.wred, wred.data(), nl * sizeof(WgradReduceDesc), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "weight-gradient reduction table upload"); }
+    // elements e = 0 .. nl-2 <-> layer l = nl-1-e: dgrad of layer l (stride-1 conv over GY_l or its zero-upsampled copy,
+    // flipped [cin][cout] weights) fused with the ReLU mask + BatchNorm backward of layer l-1
+    const int ne = nl - 1;
+    auto layer_of = [&](int el) { return nl - 1 - el; };
+    const auto bsplit = split_chains(ne, chain_bwd_len(), [&](int el) { return n->L[layer_of(el)].stride == 2; });
+    for (size_t ci = 0; ci < bsplit.size(); ++ci) {
+      const int first = bsplit[ci].first, count = bsplit[ci].second;
+      uint32_t w_max = 0;
+      for (int el = first; el < first + count; ++el) {
+        const LayerDesc& d = n->L[layer_of(el)];
+        w_max = std::max(w_max, w_tile_bytes(d.cout, d.cin_pad));
+      }
+      const size_t ring = chain_ring_bytes(w_max, ew_fused);
+      int max_tiles = 0;
+      for (int el = first; el < first + count; ++el) {
+        const int l = layer_of(el), pl = l - 1;
+        const LayerDesc& d = n->L[l];
+        const LayerDesc& pd = n->L[pl];
+        const void* src = d.stride == 2 ? n->at<void>(n->off.gyup[l]) : n->at<void>(n->off.gy[l]);
         ConvLaunch& g = n->dgrad[l];
-        e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_RAW);
+        e = setup_conv(g, src, batch, d.H_in, d.H_in, d.cout, d.cin_pad, 1, 9, wbuf + d.wd_off, EPI_BNBWD, ring);
         if (e) { delete n; return e; }
-        if ((e = make_fused(g, EPI_BNBWD, gbar))) { delete n; return e; }
-        g.p.pdl = pdl_enabled() ? 1 : 0;
-        g.p.w_early = 1;  // operand copies were written by cast_weights in the forward
-        const int pl = static_cast<int>(l) - 1;
+        g.dep_up = d.stride == 2 ? 1 : 0;
         g.p.g_res = nullptr;
         const bool block_output = (pl == 0) || (pl % 2 == 0);
-        if (block_output && pl + 2 < static_cast<int>(nl)) {
+        if (block_output && pl + 2 < nl) {
           const LayerDesc& na = n->L[pl + 1];
           g.p.g_res = n->at<__nv_bfloat16>(n->off.gz[(pl / 2) % 2]);
           g.p.gres_mode = (na.stride == 2 || na.cin != na.cout) ? 2 : 1;
         }
         g.p.act_in = n->at<__nv_bfloat16>(n->off.a[pl]);
         g.p.y_in = n->at<__nv_bfloat16>(n->off.y[pl]);
-        g.p.saved = saved + so[pl];
+        g.p.saved = n->at<float>(n->off.saved) + so[pl];
         g.p.gamma = n->params + pd.gamma_off;
         g.p.dgamma = n->grads + pd.gamma_off;
         g.p.dbeta = n->grads + pd.beta_off;
         g.p.stats = n->at<float>(n->off.bstats) + so[pl] * num_sms();
-        g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl % 3]);
+        g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl]);
         g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
         g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
-        if (d.stride == 2) {
-          ce = cudaMemset(n->ws + n->off.gyup[l], 0, static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
-          if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "gy_up clear"); }
-        }
+        max_tiles = std::max(max_tiles, g.p.num_tiles);
       }
-    }
-    ce = cudaMemcpy(n->ws + n->off.wred, wred.data(), nl * sizeof(WgradReduceDesc), cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "weight-gradient reduction table upload"); }
-  } else {
-    // INFER: block input in tmp[cur], conv_a -> tmp[mid], conv_b (+shortcut from tmp[cur]) -> tmp[nxt]
-    float* bias = n->at<float>(n->off.bias);
-    int cur = 0;
-    for (size_t l = 0; l < nl; ++l) {
-      const LayerDesc& d = n->L[l];
-      ConvLaunch& c = n->fprop[l];
-      const void* in;
-      __nv_bfloat16* outp;
-      const __nv_bfloat16* res = nullptr;
-      int res_stride = 1, res_c = d.cout;
-      if (l == 0) {
-        in = n->at<void>(n->off.a0);
-        outp = n->at<__nv_bfloat16>(n->off.tmp[cur]);
-      } else if (l % 2 == 1) {  // conv_a
-        in = n->at<void>(n->off.tmp[cur]);
-        outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 1) % 3]);
-      } else {  // conv_b
-        in = n->at<void>(n->off.tmp[(cur + 1) % 3]);
-        outp = n->at<__nv_bfloat16>(n->off.tmp[(cur + 2) % 3]);
-        res = n->at<__nv_bfloat16>(n->off.tmp[cur]);
-        const LayerDesc& da = n->L[l - 1];
-        if (da.stride == 2 || da.cin != da.cout) { res_stride = 2; res_c = da.cin; }
-        cur = (cur + 2) % 3;
+      ChainPlan cpn;
+      cpn.first = first; cpn.count = count; cpn.ew = ew_fused;
+      cpn.grid = std::min(max_tiles, num_sms());
+      uint32_t cols = 0;
+      for (int el = first; el < first + count; ++el) {
+        const int l = layer_of(el);
+        const ConvLaunch& c = n->dgrad[l];
+        const int nacc = (c.p.num_tiles + cpn.grid - 1) / cpn.grid;
+        uint32_t need = static_cast<uint32_t>(nacc * c.p.nc) * 2u;
+        if (nacc > kChainMaxSlots) need = 1024;
+        cols = std::max(cols, need);
+        const bool last = el == first + count - 1;
+        unsigned* flags = last ? nullptr : sync_b + n->off.flag_b[l] / 4;
+        const unsigned* dflags = el > first ? sync_b + n->off.flag_b[l + 1] / 4 : nullptr;
+        fill_chain_layer(tab[nl + el], c, el > first ? &n->dgrad[l + 1] : nullptr, cpn.grid, flags, dflags);
+        maps[2 * (nl + el)] = c.mapA;
+        maps[2 * (nl + el) + 1] = c.mapW;
       }
-      e = setup_conv(c, in, batch, d.H_in, d.H_in, d.cin_pad, d.cout, d.stride, 9, wbuf + d.wf_off, EPI_INFER);
-      if (e) { delete n; return e; }
-      c.p.pdl = pdl_enabled() ? 1 : 0;
-      c.p.w_early = 1;  // folded once per task by wacil_net_fold
-      c.p.out = outp;
-      c.p.bias = bias + d.bias_off;
-      c.p.res = res;
-      c.p.res_stride = res_stride;
-      c.p.res_c = res_c;
+      if (cols > 256) {
+        delete n;
+        return fail(WACIL_E_SHAPE, "batch %d too large for the fused BatchNorm path (%u TMEM columns per CTA > 256)", batch, cols);
+      }
+      cpn.cp.layers = dtab + nl + first;
+      cpn.cp.maps = dmaps + 2 * (nl + first);
+      cpn.cp.n_layers = count;
+      cpn.cp.grid_bar = sync_b + ci;
+      cpn.cp.pdl = pdl ? 1 : 0;
+      cpn.cp.w_bytes_max = w_max;
+      cpn.cp.ring_bytes = static_cast<uint32_t>(ring);
+      cpn.cp.tmem_cols = 32;
+      while (cpn.cp.tmem_cols < cols) cpn.cp.tmem_cols <<= 1;
+      cpn.cp.dbg = nullptr;
+      cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), ew_fused);
+      if (static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+      n->bchains.push_back(cpn);
     }
   }
+  ce = cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(dmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "chain table upload"); }
   *out = n;
   return 0;
 }
 
 void wacil_net_destroy(wacil_net_t* net) {
   if (!net) return;
-  for (cudaEvent_t e : net->ev_gy) cudaEventDestroy(e);
-  for (cudaEvent_t e : net->ev_wg) cudaEventDestroy(e);
+  for (cudaEvent_t e : net->ev_chain) cudaEventDestroy(e);
+  if (net->ev_join) cudaEventDestroy(net->ev_join);
   delete net;
 }
 
 int wacil_net_set_side_stream(wacil_net_t* n, void* side_stream) {
   if (!n) return fail(WACIL_E_NULL, "net is NULL");
   n->side = static_cast<cudaStream_t>(side_stream);
-  if (n->side != nullptr && n->ev_gy.empty()) {
-    const size_t nl = n->L.size();
-    n->ev_gy.resize(nl);
-    n->ev_wg.resize(nl);
-    for (size_t l = 0; l < nl; ++l) {
-      cudaError_t e = cudaEventCreateWithFlags(&n->ev_gy[l], cudaEventDisableTiming);
-      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&n->ev_wg[l], cudaEventDisableTiming);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
-    }
+  if (n->side != nullptr && n->ev_join == nullptr) {
+    n->ev_chain.resize(n->bchains.size() + 1);
+    cudaError_t e = cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming);
+    for (size_t i = 0; i < n->ev_chain.size() && e == cudaSuccess; ++i)
+      e = cudaEventCreateWithFlags(&n->ev_chain[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
   }
   return 0;
 }
 
 int wacil_net_last_launches(const wacil_net_t* net) { return net ? net->launches : 0; }
+
+int wacil_net_chain_count(const wacil_net_t* n, int backward) {
+  if (!n) return 0;
+  return static_cast<int>(backward ? n->bchains.size() : n->fchains.size());
+}
+
+int wacil_net_chain_info(const wacil_net_t* n, int backward, int index, int* first_layer, int* n_layers, int* grid,
+                         int* epilogue_warps, size_t* smem_bytes) {
+  if (!n) return fail(WACIL_E_NULL, "net is NULL");
+  const std::vector<ChainPlan>& v = backward ? n->bchains : n->fchains;
+  if (index < 0 || index >= static_cast<int>(v.size())) return fail(WACIL_E_SHAPE, "chain %d of %zu", index, v.size());
+  const ChainPlan& c = v[index];
+  const int nl = static_cast<int>(n->L.size());
+  if (first_layer) *first_layer = backward ? nl - 1 - c.first : c.first;  // backward: the layer whose dgrad runs first
+  if (n_layers) *n_layers = c.count;
+  if (grid) *grid = c.grid;
+  if (epilogue_warps) *epilogue_warps = c.ew;
+  if (smem_bytes) *smem_bytes = c.smem;
+  return 0;
+}
+
+int wacil_net_run_chain(wacil_net_t* n, int backward, int index, long long* dbg, void* stream) {
+  if (!n) return fail(WACIL_E_NULL, "net is NULL");
+  std::vector<ChainPlan>& v = backward ? n->bchains : n->fchains;
+  if (index < 0 || index >= static_cast<int>(v.size())) return fail(WACIL_E_SHAPE, "chain %d of %zu", index, v.size());
+  if (n->mode == WACIL_NET_INFER && !n->folded) return fail(WACIL_E_STATE, "INFER plan used before wacil_net_fold");
+  cudaStream_t st = S(stream);
+  cudaError_t ce = backward ? cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st)
+                            : cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
+  ChainPlan c = v[index];
+  c.cp.dbg = dbg;
+  c.cp.pdl = 0;
+  return launch_chain(c, st);
+}
 
 int wacil_net_tensor(const wacil_net_t* n, int what, int layer, void** ptr, size_t* bytes) {
   if (!n || !ptr || !bytes) return fail(WACIL_E_NULL, "NULL argument");
@@ -654,35 +939,30 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
   if (!n || !x || !feats) return fail(WACIL_E_NULL, "NULL argument");
   if (C_seen < 0 || C_seen > n->max_classes) return fail(WACIL_E_SHAPE, "C_seen %d > max_classes %d", C_seen, n->max_classes);
   if (logits == nullptr && C_seen != 0) return fail(WACIL_E_NULL, "logits is NULL but C_seen = %d", C_seen);
+  if (n->mode == WACIL_NET_INFER && !n->folded) return fail(WACIL_E_STATE, "INFER plan used before wacil_net_fold");
   cudaStream_t st = S(stream);
   const size_t nl = n->L.size();
   int launches = 0;
   int e;
+  cudaError_t ce = cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);  // barrier counters + ready flags
+  if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
   const long long npix0 = static_cast<long long>(n->batch) * 32 * 32;
   pack_input_kernel<<<static_cast<int>((npix0 + 255) / 256), 256, 0, st>>>(x, n->at<__nv_bfloat16>(n->off.a0),
                                                                          n->batch, 32 * 32);
   WACIL_LAUNCH_CHECK("pack_input_kernel");
   ++launches;
-  const __nv_bfloat16* last = nullptr;
   if (n->mode == WACIL_NET_TRAIN) {
     dim3 grid(36, static_cast<unsigned>(nl));  // <= 4 elements per thread for the largest (64x64x9) layers
     cast_weights_kernel<<<grid, 256, 0, st>>>(n->params, n->at<__nv_bfloat16>(n->off.wbuf),
                                               n->at<LayerDesc>(n->off.table));
     WACIL_LAUNCH_CHECK("cast_weights_kernel");
     ++launches;
-    for (size_t l = 0; l < nl; ++l) {
-      if ((e = launch_conv(n->fprop[l], st))) return e;
-      ++launches;
-    }
-    last = n->at<__nv_bfloat16>(n->off.a[nl - 1]);
-  } else {
-    if (!n->folded) return fail(WACIL_E_STATE, "INFER plan used before wacil_net_fold");
-    for (size_t l = 0; l < nl; ++l) {
-      if ((e = launch_conv(n->fprop[l], st))) return e;
-      ++launches;
-    }
-    last = n->fprop[nl - 1].p.out;
   }
+  for (const ChainPlan& c : n->fchains) {
+    if ((e = launch_chain(c, st))) return e;
+    ++launches;
+  }
+  const __nv_bfloat16* last = n->mode == WACIL_NET_TRAIN ? n->at<__nv_bfloat16>(n->off.a[nl - 1]) : n->fprop[nl - 1].p.out;
   pool_fc_fwd_kernel<<<n->batch, 64, 0, st>>>(last, 64, kFeatDim, n->params + n->lay.fc_weight_off,
                                               n->params + n->lay.fc_bias_off, C_seen, feats, logits);
   WACIL_LAUNCH_CHECK("pool_fc_fwd_kernel");
@@ -703,6 +983,8 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   int launches = 0, e;
   cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
+  ce = cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
   float* dfeats = n->at<float>(n->off.dfeats);
   fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
                                                   C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
@@ -728,7 +1010,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     bp.gamma = n->params + d.gamma_off;
     bp.dgamma = n->grads + d.gamma_off;
     bp.dbeta = n->grads + d.beta_off;
-    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l % 3]);
+    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l]);
     bp.gy_up = d.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[l]) : nullptr;
     bp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
     bp.C = d.cout;
@@ -738,7 +1020,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     const int lanes = 256 / (d.cout / 8);
     int rgrid = static_cast<int>((bp.num_pixels + lanes - 1) / lanes);
     if (rgrid > num_sms()) rgrid = num_sms();
-    bp.part = n->at<float>(n->off.bstats) + soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no fused launch uses them)
+    bp.part = n->at<float>(n->off.bstats) + soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no chain element uses them)
     bp.nparts = rgrid;
     bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
@@ -746,8 +1028,9 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
     launches += 2;
   }
-  // dW_l needs (a_{l-1}, GY_l); the fused dgrad_l + BN-backward_{l-1} needs GY_l and writes GY_{l-1} into buffer
-  // (l-1) % 3, which is the buffer wgrad_{l+2} reads.  With a side stream the weight gradients run beside that chain.
+  // GY_{nl-1} is ready.  Every chain launch produces the gradients GY_{l-1} of its layers l; the weight gradient of
+  // layer l needs (a_{l-1}, GY_l), so the weight gradients of a launch's OUTPUTS start when the launch ends and run
+  // (on the side stream) beside the next launch.  Every layer has its own GY buffer: the chain never waits for them.
   cudaStream_t ws = n->side ? n->side : st;
   const bool par = n->side != nullptr;
 #define WACIL_EV(call, what)                                   \
@@ -755,28 +1038,39 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     cudaError_t ce_ = (call);                                  \
     if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
   } while (0)
-  if (par) WACIL_EV(cudaEventRecord(n->ev_gy[nl - 1], st), "event record");
-  int pending = 0;  // weight gradients whose partial slots have not been reduced yet (layers l .. l + pending - 1)
-  for (int l = nl - 1; l >= 0; --l) {
-    if (par) WACIL_EV(cudaStreamWaitEvent(ws, n->ev_gy[l], 0), "event wait");
-    if ((e = launch_wgrad(n->wgrad[l], ws))) return e;
-    if (par && l > 0) WACIL_EV(cudaEventRecord(n->ev_wg[l], ws), "event record");
+  auto wgrads = [&](int l_hi, int l_lo) -> int {  // weight gradients of layers l_hi .. l_lo (descending) + their reduction
+    for (int l = l_hi; l >= l_lo; --l) {
+      int e2 = launch_wgrad(n->wgrad[l], ws);
+      if (e2) return e2;
+      ++launches;
+    }
+    wgrad_reduce_kernel<<<dim3(48, static_cast<unsigned>(l_hi - l_lo + 1)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l_lo);
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return cuda_fail(e_, "wgrad_reduce_kernel");
     ++launches;
-    if (++pending == 6 || l == 0) {  // ordered sum of the per-CTA slots -> the gradient arena, a few layers per launch
-      wgrad_reduce_kernel<<<dim3(48, static_cast<unsigned>(pending)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l);
-      WACIL_LAUNCH_CHECK("wgrad_reduce_kernel");
-      ++launches;
-      pending = 0;
-    }
-    if (par && l == 0) WACIL_EV(cudaEventRecord(n->ev_wg[0], ws), "event record");
-    if (l > 0) {
-      if (par && l + 2 <= nl - 1) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[l + 2], 0), "event wait");
-      if ((e = launch_conv(n->dgrad[l], st))) return e;
-      if (par) WACIL_EV(cudaEventRecord(n->ev_gy[l - 1], st), "event record");
-      ++launches;
-    }
+    return 0;
+  };
+  if (par) {
+    WACIL_EV(cudaEventRecord(n->ev_chain[0], st), "event record");
+    WACIL_EV(cudaStreamWaitEvent(ws, n->ev_chain[0], 0), "event wait");
   }
-  if (par) WACIL_EV(cudaStreamWaitEvent(st, n->ev_wg[0], 0), "event wait");  // join (the side stream is in order)
+  if ((e = wgrads(nl - 1, nl - 1))) return e;
+  for (size_t ci = 0; ci < n->bchains.size(); ++ci) {
+    const ChainPlan& c = n->bchains[ci];
+    if ((e = launch_chain(c, st))) return e;
+    ++launches;
+    if (par) {
+      WACIL_EV(cudaEventRecord(n->ev_chain[ci + 1], st), "event record");
+      WACIL_EV(cudaStreamWaitEvent(ws, n->ev_chain[ci + 1], 0), "event wait");
+    }
+    // elements first .. first+count-1 are layers l = nl-1-first .. ; they produced GY_{l-1}
+    const int l_hi = nl - 1 - c.first - 1, l_lo = nl - 1 - (c.first + c.count - 1) - 1;
+    if ((e = wgrads(l_hi, l_lo))) return e;
+  }
+  if (par) {
+    WACIL_EV(cudaEventRecord(n->ev_join, ws), "event record");
+    WACIL_EV(cudaStreamWaitEvent(st, n->ev_join, 0), "event wait");  // join (the side stream is in order)
+  }
 #undef WACIL_EV
   n->launches = launches;
   return 0;
@@ -1105,16 +1399,28 @@ int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, cons
   return launch_conv(c, S(stream));
 }
 
+size_t wacil_conv3x3_wgrad_workspace_bytes(int N, int H, int cin, int cout, int stride) {
+  if (N < 1 || H < 1 || stride < 1 || cin < 1 || cout < 1) return 0;
+  const int Ho = H / stride;
+  return static_cast<size_t>(wgrad_grid((N * Ho * Ho + 127) / 128)) * 9 * cin * cout * 4;
+}
+
 int wacil_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout, int stride,
-                        void* stream) {
-  if (!x || !dy || !dw) return fail(WACIL_E_NULL, "NULL argument");
+                        void* workspace, void* stream) {
+  if (!x || !dy || !dw || !workspace) return fail(WACIL_E_NULL, "NULL argument");
   if ((cin != 16 && cin != 32 && cin != 64) || (cout != 16 && cout != 32 && cout != 64) ||
       (stride != 1 && stride != 2) || H != W || (H != 32 && H != 16 && H != 8) || (H / stride) < 8 || N < 1)
     return fail(WACIL_E_SHAPE, "wgrad N=%d H=%d cin=%d cout=%d stride=%d", N, H, cin, cout, stride);
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(WACIL_E_ALIGN, "workspace must be 16-byte aligned");
   WgradLaunch wl;
-  int e = setup_wgrad(wl, x, dy, dw, N, H, W, cin, cout, stride, 9);
+  int e = setup_wgrad(wl, x, dy, static_cast<float*>(workspace), N, H, W, cin, cout, stride, 9);
   if (e) return e;
-  return launch_wgrad(wl, S(stream));
+  if ((e = launch_wgrad(wl, S(stream)))) return e;
+  // per-CTA partial sums -> dw, added in CTA order (bit-reproducible)
+  WgradReduceDesc rd{static_cast<const float*>(workspace), dw, wgrad_active_ctas(wl.p.num_tiles, wl.grid), 9 * cin * cout};
+  wgrad_reduce_one_kernel<<<dim3(48, 1), 256, 0, S(stream)>>>(rd);
+  WACIL_LAUNCH_CHECK("wgrad_reduce_one_kernel");
+  return 0;
 }
 
 }  // extern "C"

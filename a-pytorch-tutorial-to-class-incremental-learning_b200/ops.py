@@ -221,7 +221,8 @@ def conv3x3_wgrad(x, dy, stride=1):
     _need_cuda(x, dy)
     N, H, W_, cin = x.shape
     cout = dy.shape[3]
-    dw = torch.zeros((9, cin, cout), dtype=torch.float32, device=x.device)
-    check(lib().wacil_conv3x3_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W_, cin, cout, stride, _stream()),
-          "wacil_conv3x3_wgrad")
+    dw = torch.empty((9, cin, cout), dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib().wacil_conv3x3_wgrad_workspace_bytes(N, H, cin, cout, stride), dtype=torch.uint8, device=x.device)
+    check(lib().wacil_conv3x3_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W_, cin, cout, stride, ws.data_ptr(),
+                                    _stream()), "wacil_conv3x3_wgrad")
     return dw

@@ -221,6 +221,17 @@ int wacil_net_tensor(const wacil_net_t* net, int what, int layer, void** ptr, si
 /* Number of kernels the last forward / backward call launched (for bench.py's gpu_launches). */
 int wacil_net_last_launches(const wacil_net_t* net);
 
+/* The convolution layers of a plan run as a few persistent "chain" launches (several layers per cooperative launch,
+ * csrc/tc_chain.cuh).  Introspection + profiling: number of chain launches of the forward (backward = 0) or of the
+ * data-gradient pass (backward = 1); layout of one of them; and a stand-alone run of ONE chain launch on the plan's
+ * own buffers (after a forward, and for backward chains after a backward, so that its inputs hold real data) —
+ * bench.py times the dominant kernel this way.  dbg: NULL, or [grid][n_layers][4] int64 clock64 stamps of the
+ * epilogue phases (phase 1 done, grid barrier passed, phase 2 done). */
+int wacil_net_chain_count(const wacil_net_t* net, int backward);
+int wacil_net_chain_info(const wacil_net_t* net, int backward, int index, int* first_layer, int* n_layers, int* grid,
+                         int* epilogue_warps, size_t* smem_bytes);
+int wacil_net_run_chain(wacil_net_t* net, int backward, int index, long long* dbg, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Single-operator entry points kept for the parity tests (same kernels the engine launches).
  * --------------------------------------------------------------------------------------------------- */
@@ -238,9 +249,13 @@ size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout);
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
                           int res_mode, void* y, void* a, float* mean_rstd, float* running_mean, float* running_var,
                           int N, int H, int W, int cin, int cout, int stride, void* workspace, void* stream);
-/* dW[9][cin][cout] fp32 += sum over pixels of x (shifted) * dy;  x: [N][H][W][cin], dy: [N][H/s][W/s][cout] */
+/* dW[9][cin][cout] fp32 = sum over pixels of x (shifted) * dy  (the weight gradient autograd forms at template.py:270);
+ * x: [N][H][W][cin], dy: [N][H/s][W/s][cout], bf16 NHWC.  Overwrites dw.  workspace:
+ * wacil_conv3x3_wgrad_workspace_bytes() bytes, 16-byte aligned (per-CTA partial sums, added in CTA order: the result is
+ * bit-reproducible — the reference runs with cudnn.deterministic = True, template.py:57). */
+size_t wacil_conv3x3_wgrad_workspace_bytes(int N, int H, int cin, int cout, int stride);
 int wacil_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int cin, int cout,
-                        int stride, void* stream);
+                        int stride, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }
