@@ -15,10 +15,13 @@
 //                 -> BatchNorm backward                                                     (data-gradient chain)
 //   EPI_INFER     conv + folded-BN bias + shortcut + ReLU, no grid barrier                  (teacher / eval / features)
 //
-// Warp roles (96 + 32*EW threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..2+EW-1 epilogue
-// (EW = 4 or 8; with 8, two groups of four warps take alternate tiles), last warp = flag signaller (one lane:
-// waits for a tile's stores through a shared-memory counter, then publishes the tile with a gpu-scope release, so
-// that no epilogue warp ever stalls on a memory fence).
+// Warp roles (64 + 32*EW threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..2+EW-1 epilogue
+// (EW = 4 or 8; with 8, two groups of four warps take alternate tiles).
+// Hand-off between layers: all layers of a launch share one tile geometry (a launch never crosses a resolution
+// change), tile t belongs to CTA t mod G, and a 3x3 box of tile t touches tiles t-1, t, t+1 only — so a CTA needs the
+// rows of CTAs b-1, b, b+1.  Every epilogue warp publishes "my rows of this layer are stored" ONCE per layer (one
+// gpu-scope release per warp and layer; per-tile releases stalled the epilogue warps ~1 k cycles per tile on the
+// store acknowledgements) and the producer polls three per-CTA counters before the first load of the next layer.
 //
 // Determinism: BatchNorm sums go through per-CTA partial rows added in CTA order by every CTA; nothing is atomic
 // except the barrier counter itself.
@@ -29,7 +32,6 @@ namespace wacil {
 
 constexpr int kChainMaxStages = 6;   // operand ring depth (mbarrier pairs)
 constexpr int kChainMaxSlots = 8;    // TMEM accumulator slots = tiles of a CTA in a fused layer
-constexpr int kChainCntRing = 16;    // tile-done counters in flight (signaller handshake)
 
 struct ChainLayer {
   // ---- geometry of this layer's implicit GEMM (3x3, pad 1)
@@ -41,13 +43,10 @@ struct ChainLayer {
   int epi;
   int tmem_sync;         // accumulator slot layout differs from the previous layer's: wait until all its slots are free
   int ring_sync;         // operand ring shape differs from the previous layer's: drain it first
-  // ---- dependency on the previous layer of the chain (its per-tile ready flags)
-  int dep;               // 0: the input was complete before the launch
-  int dep_H, dep_W;      // rows / columns per image of the producer's output map
-  int dep_up;            // the input tensor is the zero-upsampled copy of the producer's output (row r <- row r/2)
-  int dep_tiles;         // producer's tile count
-  const unsigned* dep_flags;
-  unsigned* flags;       // [num_tiles] ready flags of THIS layer's output (nullptr: nobody in this launch reads it)
+  // ---- dependency on the previous layer of the chain
+  int dep;               // 0: the input was complete before the launch; 1: wait for CTAs b-1, b, b+1 of that layer
+  const unsigned* dep_flags;  // [gridDim.x] epilogue warps of CTA c that have stored all their rows of the previous layer
+  unsigned* flags;       // [gridDim.x] the same for THIS layer's output (nullptr: nobody in this launch reads it)
   // ---- epilogue operands (a subset per mode, see ConvGemmParams)
   int res_stride, res_c, gres_mode;
   float eps, momentum;
@@ -92,25 +91,19 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// Producer tiles whose output rows the box loads of consumer tile (n0, h0) touch -> [lo, hi] (tile indices).
-__device__ __forceinline__ void chain_dep_range(const ChainLayer* L, int stride, int Ht, int Nt, int n0, int h0, int& lo,
-                                                int& hi) {
-  int r_lo, r_hi;  // input-tensor rows of the tile's boxes (before clamping)
-  if (stride == 1) { r_lo = h0 - 1; r_hi = h0 + Ht; }
-  else { r_lo = 2 * h0 - 1; r_hi = 2 * (h0 + Ht - 1) + 1; }
-  const int H = L->dep_H, W = L->dep_W;
-  if (L->dep_up) {  // only the even rows of the upsampled copy are written (row 2j <- producer row j)
-    r_lo = (r_lo + 1) >> 1;  // ceil(r / 2) for r >= -1
-    r_hi = r_hi >> 1;
+// TMEM slot hand-back: the ordering that matters (tcgen05.ld before the next tcgen05.mma) comes from the tcgen05 fences
+// around the synchronisation; a releasing arrive would additionally wait for the tile's global stores to be acknowledged.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One epilogue warp has stored all its rows of a layer: count it in this CTA's flag (gpu-scope release, cumulative over
+// the warp's stores after __syncwarp).
+__device__ __forceinline__ void chain_publish(unsigned* flags, int lane) {
+  __syncwarp();
+  if (lane == 0 && flags != nullptr) {
+    fence_proxy_async();  // consumers read these rows through TMA (async proxy)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flags + blockIdx.x) : "memory");
   }
-  r_lo = r_lo < 0 ? 0 : r_lo;
-  r_hi = r_hi > H - 1 ? H - 1 : r_hi;
-  const long long p_lo = (static_cast<long long>(n0) * H + r_lo) * W;
-  const long long p_hi = (static_cast<long long>(n0 + Nt - 1) * H + r_hi) * W + (W - 1);
-  lo = static_cast<int>(p_lo >> 7);
-  hi = static_cast<int>(p_hi >> 7);
-  if (hi > L->dep_tiles - 1) hi = L->dep_tiles - 1;  // batch tail (Nt images per tile, odd batch)
 }
 
 template <int ET>
@@ -130,7 +123,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned targe
 }
 
 template <int EW>
-__global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const ChainParams cp) {
+__global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const ChainParams cp) {
   constexpr int ET = EW * 32;  // epilogue threads
   constexpr int NG = EW / 4;   // epilogue groups (tiles alternate between them)
   extern __shared__ uint8_t smem_raw[];
@@ -148,8 +141,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
   uint64_t* accfull = wempty + 1;                   // [kChainMaxSlots]
   uint64_t* accempty = accfull + kChainMaxSlots;    // [kChainMaxSlots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + kChainMaxSlots);
-  unsigned* s_cnt = tmem_slot + 4;                  // [kChainCntRing] epilogue warps that finished tile seq (monotonic)
-  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_cnt + kChainCntRing) + 15) & ~uintptr_t(15));
+  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kChainMaxStages; ++i) {
@@ -166,7 +158,6 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
   }
   if (warp == 1) tmem_alloc(tmem_slot, cp.tmem_cols);
   for (int i = threadIdx.x; i < (2 * EW + 5) * 64; i += blockDim.x) s_stats[i] = 0.f;
-  if (threadIdx.x < kChainCntRing) s_cnt[threadIdx.x] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -212,29 +203,25 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
         for (int s = 0; s < kChainMaxStages; ++s) mbar_wait(&empty[s], ((ring_phase >> s) & 1) ^ 1);
         stage = 0;
       }
-      const bool dep = L->dep != 0;
-      const unsigned* dflags = L->dep_flags;
+      if (L->dep != 0) {
+        // rows of tiles t-1, t, t+1 of the previous layer = CTAs b-1, b, b+1 (mod G): three counters, once per layer
+        const unsigned* dflags = L->dep_flags;
+        if (lane < 3) {
+          const int c = (static_cast<int>(blockIdx.x) + lane - 1 + G) % G;
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(dflags + c) < static_cast<unsigned>(EW)) {
+            if (clock64() - t0 > 4000000000LL) {
+              printf("wacil: chain flag timeout (block %d layer %d waits for block %d)\n", blockIdx.x, l, c);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+        fence_proxy_async();  // those rows were written through the generic proxy, TMA reads through the async one
+      }
       for (int tile = blockIdx.x; tile < ntiles; tile += G) {
         const int n0 = (tile / tiles_h) * Nt;
         const int h0 = (tile % tiles_h) * Ht;
-        if (dep) {
-          int lo, hi;
-          chain_dep_range(L, stride, Ht, Nt, n0, h0, lo, hi);
-          for (int base = lo; base <= hi; base += 32) {
-            const int t = base + lane;
-            if (t <= hi) {
-              const long long t0 = clock64();
-              while (ld_acquire_gpu(dflags + t) == 0u) {
-                if (clock64() - t0 > 4000000000LL) {
-                  printf("wacil: chain flag timeout (block %d layer %d tile %d waits for tile %d)\n", blockIdx.x, l, tile, t);
-                  __trap();
-                }
-              }
-            }
-          }
-          __syncwarp();
-          fence_proxy_async();  // the producer tiles were written through the generic proxy, TMA reads through the async one
-        }
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&empty[stage], ((ring_phase >> stage) & 1) ^ 1);
           uint8_t* dst = smem_a + stage * stage_bytes;
@@ -348,7 +335,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
     float* s_mean = s_stats + EW * 128 + 192;   // [nc]
     float* s_rstd = s_stats + EW * 128 + 256;   // [nc]
     uint32_t acc_phase = 0;
-    int seq = 0;          // tiles of this CTA so far (all layers): signaller handshake index, INFER slot parity
+    int seq = 0;          // tiles of this CTA so far (all layers): INFER slot parity
     unsigned nbar = 0;    // grid barriers passed
     for (int l = 0; l < nl; ++l) {
       const ChainLayer* L = cp.layers + l;
@@ -396,13 +383,11 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&accempty[slot]);
-              asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(&s_cnt[seq % kChainCntRing])) : "memory");
-            }
+            if (lane == 0) mbar_arrive_relaxed(&accempty[slot]);
           }
           acc_phase ^= 1u << slot;
         }
+        chain_publish(L->flags, lane);
         continue;
       }
       // -------------------------------------------------------------------- fused BatchNorm modes
@@ -641,44 +626,16 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
               }
             }
           }
-          // the tile's accumulator slot is free and its rows are stored: tell the MMA warp and the signaller
+          // the tile's accumulator slot is free: the MMA warp may start the next layer's tile on it
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&accempty[k]);
-            asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(&s_cnt[(seq + k) % kChainCntRing])) : "memory");
-          }
+          if (lane == 0) mbar_arrive_relaxed(&accempty[k]);
         }
+        chain_publish(L->flags, lane);
       }
       if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 4 + 2] = clock64();
       acc_phase ^= (1u << my_tiles) - 1u;
       seq += my_tiles;
-    }
-  } else {
-    // ================================================================================== flag signaller (one lane)
-    if (lane == 0) {
-      int seq = 0;
-      for (int l = 0; l < nl; ++l) {
-        const ChainLayer* L = cp.layers + l;
-        const int ntiles = L->num_tiles;
-        unsigned* flags = L->flags;
-        for (int tile = blockIdx.x; tile < ntiles; tile += G, ++seq) {
-          if (flags == nullptr) continue;
-          const unsigned want = 4u * static_cast<unsigned>(seq / kChainCntRing + 1);
-          const uint32_t addr = smem_u32(&s_cnt[seq % kChainCntRing]);
-          const long long t0 = clock64();
-          unsigned have;
-          do {
-            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(addr) : "memory");
-            if (have < want && clock64() - t0 > 8000000000LL) {
-              printf("wacil: chain signaller timeout (block %d layer %d tile %d)\n", blockIdx.x, l, tile);
-              __trap();
-            }
-          } while (have < want);
-          fence_proxy_async();           // consumers read these rows through TMA (async proxy)
-          st_release_gpu(flags + tile, 1u);  // cumulative: the epilogue warps' stores happen-before this release
-        }
-      }
     }
   }
 
@@ -693,7 +650,7 @@ __global__ void __launch_bounds__(96 + 32 * EW, 1) conv_chain_kernel(const Chain
 // ------------------------------------------------------------------------------------------------ host helpers
 inline size_t chain_smem_bytes(uint32_t w_bytes_max, uint32_t ring_bytes, int ew) {
   return 1024 + static_cast<size_t>(w_bytes_max) + ring_bytes + (2 * kChainMaxStages + 2 + 2 * kChainMaxSlots) * 8 + 16 +
-         kChainCntRing * 4 + 16 + static_cast<size_t>(2 * ew + 5) * 64 * 4 + 64;
+         16 + static_cast<size_t>(2 * ew + 5) * 64 * 4 + 64;
 }
 
 }  // namespace wacil

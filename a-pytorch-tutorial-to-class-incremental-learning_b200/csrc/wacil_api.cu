@@ -186,16 +186,16 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   // chain tables: one ChainLayer + two tensor maps per chain element (forward: nl; backward: nl - 1)
   o.ctab = c.take(2 * nl * sizeof(ChainLayer));
   o.cmaps = c.take(2 * nl * 2 * sizeof(CUtensorMap));
-  // sync regions (zeroed at the start of every forward / backward): barrier counters, then per-tile ready flags
+  // sync regions (zeroed at the start of every forward / backward): barrier counters, then per-CTA ready counters
   o.flag_f.assign(nl, 0);
   o.flag_b.assign(nl, 0);
   size_t ff = kSyncCounters * 4, fb = kSyncCounters * 4;
-  for (size_t l = 0; l < nl; ++l) {
+  for (size_t l = 0; l < nl; ++l) {  // one counter per CTA and chain element
     o.flag_f[l] = ff;
-    ff += static_cast<size_t>(tiles_of(batch, L[l].H_out)) * 4;
-    if (l >= 1) {  // backward element of layer l produces the gradient wrt y_{l-1}: tiles of layer l-1's output
+    ff += static_cast<size_t>(num_sms()) * 4;
+    if (l >= 1) {
       o.flag_b[l] = fb;
-      fb += static_cast<size_t>(tiles_of(batch, L[l - 1].H_out)) * 4;
+      fb += static_cast<size_t>(num_sms()) * 4;
     }
   }
   o.sync_f_bytes = ff;
@@ -465,7 +465,7 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(96 + 32 * c.ew);
+  cfg.blockDim = dim3(64 + 32 * c.ew);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -528,8 +528,7 @@ void fill_chain_layer(ChainLayer& cl, const ConvLaunch& c, const ConvLaunch* pre
     const size_t st = p.rmerge ? (size_t)3 * (p.Ht + 2) * p.Wo * p.kc * 2 : (size_t)p.tps * 128 * p.kc * 2;
     const size_t sq = q.rmerge ? (size_t)3 * (q.Ht + 2) * q.Wo * q.kc * 2 : (size_t)q.tps * 128 * q.kc * 2;
     cl.ring_sync = (st != sq || p.stages != q.stages) ? 1 : 0;
-    cl.dep = 1;
-    cl.dep_H = q.Ho; cl.dep_W = q.Wo; cl.dep_tiles = q.num_tiles; cl.dep_up = c.dep_up;
+    cl.dep = 1;  // same tile geometry as the previous element (split_chains): CTAs b-1, b, b+1 hold the rows a tile reads
     cl.dep_flags = dep_flags;
   }
   cl.res_stride = p.res_stride; cl.res_c = p.res_c; cl.gres_mode = p.gres_mode;

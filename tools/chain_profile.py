@@ -1,0 +1,73 @@
+"""Per-chain timing of a TRAIN / INFER plan at the benchmarked size: CUDA events around stand-alone chain launches
+(wacil_net_run_chain) and the clock64 stamps of the epilogue phases (phase 1 done / grid barrier passed / phase 2 done)
+per layer.  Usage: python tools/chain_profile.py [depth] [batch]"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import torch  # noqa: E402
+
+import wacil_b200 as w  # noqa: E402
+
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+lib = w._lib.lib()
+m = w.CilModel(f"resnet{depth}").cuda()
+m.prev_model_adaption(10)
+m.prev_model_adaption(10)
+m.train()
+x = torch.randn(batch, 3, 32, 32, device="cuda")
+y = torch.randint(0, 20, (batch,), device="cuda")
+plan = m._plan(w._lib.NET_TRAIN, batch)
+side = torch.cuda.Stream()
+st = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / reps
+
+
+logits, feats = plan.forward(x, 20)
+losses, dl = w.ops.ce_kd_fwd_bwd(logits, y, None, 0)
+plan.backward(dl)
+torch.cuda.synchronize()
+print(f"resnet{depth} batch {batch}: forward {timed(lambda: plan.forward(x, 20)):.1f} us, "
+      f"backward (one stream) {timed(lambda: plan.backward(dl)):.1f} us")
+plan.set_side_stream(side)
+print(f"backward (weight gradients on a side stream) {timed(lambda: plan.backward(dl)):.1f} us")
+tplan = m.copy().freeze()._plan(w._lib.NET_INFER, batch)
+tplan.fold()
+print(f"inference forward {timed(lambda: tplan.forward(x, 20)):.1f} us")
+for pl, name in ((plan, "train"), (tplan, "infer")):
+    for bwd in ((0, 1) if pl is plan else (0,)):
+        nch = lib.wacil_net_chain_count(pl.handle, bwd)
+        for i in range(nch):
+            first, nlay, grid, ew, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+            lib.wacil_net_chain_info(pl.handle, bwd, i, C.byref(first), C.byref(nlay), C.byref(grid), C.byref(ew), C.byref(smem))
+            dbg = torch.zeros((grid.value, nlay.value, 4), dtype=torch.int64, device="cuda")
+            us = timed(lambda: w._lib.check(lib.wacil_net_run_chain(pl.handle, bwd, i, None, st), "run_chain"))
+            w._lib.check(lib.wacil_net_run_chain(pl.handle, bwd, i, dbg.data_ptr(), st), "run_chain")
+            torch.cuda.synchronize()
+            d = dbg.cpu()
+            line = f"{name} {'bwd' if bwd else 'fwd'} chain {i}: first layer {first.value}, {nlay.value} layers, grid {grid.value}, " \
+                   f"ew {ew.value}, smem {smem.value}: {us:.1f} us ({us / nlay.value:.2f} us/layer)"
+            print(line)
+            if d.abs().sum() > 0:
+                c0 = d[0]
+                base = c0[0, 0].item()
+                rows = []
+                for l in range(nlay.value):
+                    p1, gb, p2 = (c0[l, k].item() - base for k in range(3))
+                    rows.append(f"L{l}: p1 {p1} bar {gb} p2 {p2}")
+                print("   cta0 cycles since its first phase-1 end:  " + " | ".join(rows[:12]))
