@@ -79,7 +79,9 @@ struct ChainParams {
   uint32_t w_bytes_max;       // weight tile region (multiple of 1024)
   uint32_t ring_bytes;        // operand ring region (multiple of 1024)
   uint32_t tmem_cols;         // power of two >= the widest layer's accumulator + stash columns
-  long long* dbg;             // optional [gridDim.x][n_layers][4] clock64 stamps of the epilogue phases
+  long long* dbg;             // optional [gridDim.x][n_layers][48] clock64 stamps: 0 phase 1 done, 1 grid barrier passed,
+                              // 2 phase 2 stored, 3 published | 4 producer: dependencies met, 5 last load issued |
+                              // 6 MMA warp: first operands landed, 7 last MMA issued
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -169,9 +171,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
 
   if (warp == 0) {
     // ================================================================================== TMA producer
-    const bool leader = elect_one_sync();
+    // TMA box loads issued by ONE thread execute one after the other (~750 cycles each on B200: tma_probe.cu), loads
+    // issued by different lanes overlap.  Every box of a stage goes out from its own lane; the lane window rotates
+    // (`bx`), so the boxes of the next tiles never queue behind those of the previous ones.
+    const bool leader = lane == 0;
     uint32_t ring_phase = 0;  // bit s: uses of stage s so far, mod 2
     int stage = 0, wuse = 0;
+    int bx = 0;               // rotating first lane of the next group of boxes
     for (int l = 0; l < nl; ++l) {
       const ChainLayer* L = cp.layers + l;
       const int ntiles = L->num_tiles;
@@ -194,9 +200,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       }
       // weights of this layer: the tile is free once the previous layer's last MMA has completed
       mbar_wait(wempty, (wuse & 1) ^ 1);
-      if (leader) {
-        mbar_expect_tx(wfull, 9 * w_tap_bytes);
-        for (int t = 0; t < 9; ++t) tma_load_2d(smem_w + t * w_tap_bytes, mapW, wfull, 0, t * nc);
+      if (leader) mbar_expect_tx(wfull, 9 * w_tap_bytes);
+      __syncwarp();
+      {
+        const int t = (lane - bx) & 31;  // tap t of the weight tile from lane (bx + t) % 32
+        if (t < 9) tma_load_2d(smem_w + t * w_tap_bytes, mapW, wfull, 0, t * nc);
+        bx = (bx + 9) & 31;
       }
       ++wuse;
       if (L->ring_sync) {  // stages change size: every stage of the old shape must have been consumed
@@ -219,32 +228,36 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         __syncwarp();
         fence_proxy_async();  // those rows were written through the generic proxy, TMA reads through the async one
       }
+      if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 4] = clock64();
       for (int tile = blockIdx.x; tile < ntiles; tile += G) {
         const int n0 = (tile / tiles_h) * Nt;
         const int h0 = (tile % tiles_h) * Ht;
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&empty[stage], ((ring_phase >> stage) & 1) ^ 1);
+          if (cp.dbg != nullptr && leader && g == 0 && (tile - blockIdx.x) / G < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 16 + (tile - blockIdx.x) / G] = clock64();
           uint8_t* dst = smem_a + stage * stage_bytes;
+          const int j = (lane - bx) & 31;  // box j of this stage from lane (bx + j) % 32
           if (rm) {
-            if (leader) {
-              mbar_expect_tx(&full[stage], 3 * box_bytes);
-              tma_load_5d(dst, mapA, &full[stage], 0, -1, h0 - 1, n0, 0);
-              tma_load_5d(dst + box_bytes, mapA, &full[stage], 0, 0, h0 - 1, n0, 0);
-              tma_load_5d(dst + 2 * box_bytes, mapA, &full[stage], 0, 1, h0 - 1, n0, 0);
-            }
+            if (leader) mbar_expect_tx(&full[stage], 3 * box_bytes);
+            __syncwarp();
+            if (j < 3) tma_load_5d(dst + j * box_bytes, mapA, &full[stage], 0, j - 1, h0 - 1, n0, 0);
+            bx = (bx + 3) & 31;
           } else {
             const int tap_lo = g * tps;
             if (leader) mbar_expect_tx(&full[stage], tps * a_bytes);
-            for (int j = 0; j < tps; ++j) {
+            __syncwarp();
+            if (j < tps) {
               int c0, c1, c2, c3, c4;
               tap_coords(9, stride, tap_lo + j, kc, h0, n0, c0, c1, c2, c3, c4);
-              if (leader) tma_load_5d(dst + j * a_bytes, mapA, &full[stage], c0, c1, c2, c3, c4);
+              tma_load_5d(dst + j * a_bytes, mapA, &full[stage], c0, c1, c2, c3, c4);
             }
+            bx = (bx + tps) & 31;
           }
           ring_phase ^= 1u << stage;
           if (++stage == nstages) stage = 0;
         }
       }
+      if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 5] = clock64();
     }
   } else if (warp == 1) {
     // ================================================================================== MMA issuer
@@ -289,6 +302,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         for (int g = 0; g < groups; ++g) {
           mbar_wait(&full[stage], (ring_phase >> stage) & 1);
           tc_fence_after();
+          if (cp.dbg != nullptr && leader && k == 0 && g == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 6] = clock64();
+          if (cp.dbg != nullptr && leader && g == 0 && k < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 24 + k] = clock64();
           const uint64_t adesc = a_ring_desc + stage * stage16;
           if (rm) {
             if (ksteps == 1) issue_rmerge_tile<1>(leader, d_tmem, adesc, w_desc, idesc, box16, win16, wtap16);
@@ -316,9 +331,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
           if (++stage == nstages) stage = 0;
         }
         if (leader) umma_commit(&accfull[slot]);
+        if (cp.dbg != nullptr && leader && k < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 32 + k] = clock64();
         acc_phase ^= 1u << slot;
       }
       if (leader) umma_commit(wempty);  // the weight tile may be overwritten once these MMAs have completed
+      if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 7] = clock64();
     }
   } else if (warp < 2 + EW) {
     // ================================================================================== epilogue warps
@@ -448,6 +465,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
           }
           mbar_wait(&accfull[k], (acc_phase >> k) & 1);
           tc_fence_after();
+          if (cp.dbg != nullptr && tid == 0 && k == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 11] = clock64();
           for (int c0 = 0; c0 < nc; c0 += 16) {
             float v[16], s2[16];
             tmem_ld16(tmem_base + lane_base + k * nc + c0, v);
@@ -492,8 +510,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
           }
         }
       }
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 12] = clock64();
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 4 + 0] = clock64();
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 0] = clock64();
       {
         float* g0 = L->stats + static_cast<size_t>(blockIdx.x) * (2 * nc);
         for (int c = tid; c < nc; c += ET) {
@@ -517,7 +536,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       }
       ++nbar;
       chain_grid_barrier<ET>(cp.grid_bar, nbar * static_cast<unsigned>(G), tid);
-      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 4 + 1] = clock64();
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 1] = clock64();
       // ---------------- per-channel constants from the per-CTA partial rows, added in CTA order by every CTA
       const float cnt = static_cast<float>(npix);
       {
@@ -526,6 +545,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         // scratch over the (already consumed) per-warp partials
         if (sl < S) s_part[sl * 128 + v] = ordered_row_sum(L->stats, V, v, sl, S, G);
       }
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 8] = clock64();
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       if (tid < nc) {
         const int c = tid;
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       // this warp's private partial rows back to zero for the next layer (the scratch above overlapped them)
       for (int i = lane; i < 128; i += 32) s_part[ew * 128 + i] = 0.f;
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 9] = clock64();
       // ---------------- phase 2: normalise (forward) / BatchNorm backward, from TMEM only
       {
         __nv_bfloat16* outp = L->out;
@@ -630,10 +651,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_relaxed(&accempty[k]);
+          if (cp.dbg != nullptr && tid == 0 && k == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 10] = clock64();
         }
+        if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 2] = clock64();
         chain_publish(L->flags, lane);
       }
-      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 4 + 2] = clock64();
+      if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 3] = clock64();
       acc_phase ^= (1u << my_tiles) - 1u;
       seq += my_tiles;
     }

@@ -318,9 +318,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
 
   // Programmatic dependent launch: everything above (and the weight TMA when the weights are older than the upstream
   // grid) overlaps the tail of the previous kernel; its outputs are only touched after griddepcontrol.wait.
-  if (p.pdl && p.w_early && warp == 0 && lane == 0) {
-    mbar_expect_tx(wfull, w_bytes);
-    for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+  if (p.pdl && p.w_early && warp == 0) {  // one lane per tap: loads of one thread would run one after the other
+    if (lane == 0) mbar_expect_tx(wfull, w_bytes);
+    __syncwarp();
+    if (lane < p.taps) tma_load_2d(smem_w + lane * w_tap_bytes, &mapW, wfull, 0, lane * p.nc);
   }
   if (p.pdl) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -333,11 +334,12 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     {
       const bool leader = elect_one_sync();
       const bool timing = p.dbg != nullptr;
-      if (leader && !(p.pdl && p.w_early)) {
-        mbar_expect_tx(wfull, w_bytes);
-        for (int t = 0; t < p.taps; ++t) tma_load_2d(smem_w + t * w_tap_bytes, &mapW, wfull, 0, t * p.nc);
+      if (!(p.pdl && p.w_early)) {
+        if (leader) mbar_expect_tx(wfull, w_bytes);
+        __syncwarp();
+        if (lane < p.taps) tma_load_2d(smem_w + lane * w_tap_bytes, &mapW, wfull, 0, lane * p.nc);
       }
-      int stage = 0;
+      int stage = 0, bx = 0;
       uint32_t phase = 0;
       long long dbg_wait = 0, dbg_t = 0;  // profiling only (p.dbg): cycles blocked on a free slot
       const int nstages = p.stages, ntiles = p.num_tiles, tstride = gridDim.x, tps = p.tps, taps = p.taps;
@@ -349,22 +351,24 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           mbar_wait(&empty[stage], phase ^ 1);
           if (timing) dbg_wait += clock64() - dbg_t;
           uint8_t* dst = smem_a + stage * stage_bytes;
+          // every box from its own lane: loads of one thread run one after the other (tma_probe.cu), lanes overlap
+          const int j = (lane - bx) & 31;
           if (rm) {  // per horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
-            if (leader) {
-              mbar_expect_tx(&full[stage], 3 * box_bytes);
-              tma_load_5d(dst, &mapA, &full[stage], 0, -1, h0 - 1, n0, 0);
-              tma_load_5d(dst + box_bytes, &mapA, &full[stage], 0, 0, h0 - 1, n0, 0);
-              tma_load_5d(dst + 2 * box_bytes, &mapA, &full[stage], 0, 1, h0 - 1, n0, 0);
-            }
+            if (leader) mbar_expect_tx(&full[stage], 3 * box_bytes);
+            __syncwarp();
+            if (j < 3) tma_load_5d(dst + j * box_bytes, &mapA, &full[stage], 0, j - 1, h0 - 1, n0, 0);
+            bx = (bx + 3) & 31;
           } else {
             const int tap_lo = g * tps;
             const int ntap = min(tps, taps - tap_lo);
             if (leader) mbar_expect_tx(&full[stage], ntap * a_bytes);
-            for (int j = 0; j < ntap; ++j) {
+            __syncwarp();
+            if (j < ntap) {
               int c0, c1, c2, c3, c4;
               tap_coords(taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
-              if (leader) tma_load_5d(dst + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+              tma_load_5d(dst + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
             }
+            bx = (bx + ntap) & 31;
           }
           if (++stage == nstages) {
             stage = 0;
@@ -868,18 +872,20 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   // Producer and MMA warps run their loops with all 32 lanes (uniform control flow: the descriptor arithmetic stays in
   // uniform registers); the TMA / tcgen05 instructions are issued by the elect.sync leader (see conv_gemm_body).
   if (warp == 0) {
-    const bool leader = elect_one_sync();
-    int gs = 0, ys = 0;
+    // TMA loads issued by one thread run one after the other (~750 cycles each, tma_probe.cu); every box goes out from
+    // its own lane and the lane window rotates (bx), so the up to ten boxes of a pixel tile overlap
+    const bool leader = lane == 0;
+    int gs = 0, ys = 0, bx = 0;
     uint32_t gphase = 0, yphase = 0;
     const int ring = p.ring, taps = p.taps;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int n0 = (tile / p.tiles_h) * p.Nt;
       const int h0 = (tile % p.tiles_h) * p.Ht;
       mbar_wait(&yempty[ys], yphase ^ 1);
-      if (leader) {
-        mbar_expect_tx(&yfull[ys], y_bytes);
-        tma_load_2d(smem_y + ys * y_stride, &mapDY, &yfull[ys], 0, tile * 128);
-      }
+      if (leader) mbar_expect_tx(&yfull[ys], y_bytes);
+      __syncwarp();
+      if (((lane - bx) & 31) == 0) tma_load_2d(smem_y + ys * y_stride, &mapDY, &yfull[ys], 0, tile * 128);
+      bx = (bx + 1) & 31;
       if (++ys == 2) {
         ys = 0;
         yphase ^= 1;
@@ -889,10 +895,15 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         const int ntap = min(tpg, taps - tap_lo);
         mbar_wait(&gempty[gs], gphase ^ 1);
         if (leader) mbar_expect_tx(&gfull[gs], ntap * slot_bytes);
-        for (int j = 0; j < ntap; ++j) {
-          int c0, c1, c2, c3, c4;
-          tap_coords(taps, p.stride, tap_lo + j, p.cin, h0, n0, c0, c1, c2, c3, c4);
-          if (leader) tma_load_5d(smem_g + gs * group_bytes + j * slot_bytes, &mapX, &gfull[gs], c0, c1, c2, c3, c4);
+        __syncwarp();
+        {
+          const int j = (lane - bx) & 31;
+          if (j < ntap) {
+            int c0, c1, c2, c3, c4;
+            tap_coords(taps, p.stride, tap_lo + j, p.cin, h0, n0, c0, c1, c2, c3, c4);
+            tma_load_5d(smem_g + gs * group_bytes + j * slot_bytes, &mapX, &gfull[gs], c0, c1, c2, c3, c4);
+          }
+          bx = (bx + ntap) & 31;
         }
         if (++gs == ring) {
           gs = 0;

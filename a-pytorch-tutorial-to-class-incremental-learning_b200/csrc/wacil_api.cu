@@ -443,6 +443,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 8, 4, 8); return v == 8 ? 8 : 4; }
 int chain_fwd_len() { static int v = env_int("WACIL_CHAIN_FWD", 64, 1, 1000); return v; }
 int chain_bwd_len() { static int v = env_int("WACIL_CHAIN_BWD", 4, 1, 1000); return v; }
+int chain_grid_cap() { static int v = env_int("WACIL_CHAIN_GRID", 1 << 20, 1, 1 << 20); return v; }  // experiments only
 size_t chain_smem_budget() { static int v = env_int("WACIL_CHAIN_SMEM", 113, 48, 227); return static_cast<size_t>(v) * 1024; }
 
 struct ChainPlan {
@@ -698,7 +699,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     }
     ChainPlan cpn;
     cpn.first = first; cpn.count = count; cpn.ew = fwd_ew;
-    cpn.grid = std::min(max_tiles, num_sms());
+    cpn.grid = std::min(std::min(max_tiles, num_sms()), chain_grid_cap());
     uint32_t cols = 0;
     for (int l = first; l < first + count; ++l) {
       const ConvLaunch& c = n->fprop[l];
@@ -800,7 +801,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       ChainPlan cpn;
       cpn.first = first; cpn.count = count; cpn.ew = ew_fused;
-      cpn.grid = std::min(max_tiles, num_sms());
+      cpn.grid = std::min(std::min(max_tiles, num_sms()), chain_grid_cap());
       uint32_t cols = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el);

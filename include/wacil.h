@@ -225,8 +225,9 @@ int wacil_net_last_launches(const wacil_net_t* net);
  * csrc/tc_chain.cuh).  Introspection + profiling: number of chain launches of the forward (backward = 0) or of the
  * data-gradient pass (backward = 1); layout of one of them; and a stand-alone run of ONE chain launch on the plan's
  * own buffers (after a forward, and for backward chains after a backward, so that its inputs hold real data) —
- * bench.py times the dominant kernel this way.  dbg: NULL, or [grid][n_layers][4] int64 clock64 stamps of the
- * epilogue phases (phase 1 done, grid barrier passed, phase 2 done). */
+ * bench.py times the dominant kernel this way.  dbg: NULL, or [grid][n_layers][48] int64 clock64 stamps
+ * (epilogue: phase 1 done, grid barrier passed, phase 2 stored, published; producer: dependencies met, last load issued;
+ * MMA warp: first operands landed, last MMA issued). */
 int wacil_net_chain_count(const wacil_net_t* net, int backward);
 int wacil_net_chain_info(const wacil_net_t* net, int backward, int index, int* first_layer, int* n_layers, int* grid,
                          int* epilogue_warps, size_t* smem_bytes);

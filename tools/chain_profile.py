@@ -55,7 +55,7 @@ for pl, name in ((plan, "train"), (tplan, "infer")):
         for i in range(nch):
             first, nlay, grid, ew, smem = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
             lib.wacil_net_chain_info(pl.handle, bwd, i, C.byref(first), C.byref(nlay), C.byref(grid), C.byref(ew), C.byref(smem))
-            dbg = torch.zeros((grid.value, nlay.value, 4), dtype=torch.int64, device="cuda")
+            dbg = torch.zeros((grid.value, nlay.value, 48), dtype=torch.int64, device="cuda")
             us = timed(lambda: w._lib.check(lib.wacil_net_run_chain(pl.handle, bwd, i, None, st), "run_chain"))
             w._lib.check(lib.wacil_net_run_chain(pl.handle, bwd, i, dbg.data_ptr(), st), "run_chain")
             torch.cuda.synchronize()
@@ -64,10 +64,16 @@ for pl, name in ((plan, "train"), (tplan, "infer")):
                    f"ew {ew.value}, smem {smem.value}: {us:.1f} us ({us / nlay.value:.2f} us/layer)"
             print(line)
             if d.abs().sum() > 0:
-                c0 = d[0]
-                base = c0[0, 0].item()
-                rows = []
-                for l in range(nlay.value):
-                    p1, gb, p2 = (c0[l, k].item() - base for k in range(3))
-                    rows.append(f"L{l}: p1 {p1} bar {gb} p2 {p2}")
-                print("   cta0 cycles since its first phase-1 end:  " + " | ".join(rows[:12]))
+                for cta in (0, grid.value // 2):
+                    c0 = d[cta]
+                    base = c0[0, 4].item() or c0[0, 0].item()
+                    names = ["p1", "bar", "p2", "pub", "dep", "ld", "op", "mma", "sum", "cst", "p2t0", "acc0", "p1e"]
+                    order = [4, 6, 5, 11, 7, 12, 0, 1, 8, 9, 10, 2, 3]
+                    rows = []
+                    for l in range(min(nlay.value, 4)):
+                        rows.append(f"L{l}: " + " ".join(f"{names[k]} {c0[l, k].item() - base}" for k in order if c0[l, k].item()))
+                    print(f"   cta{cta} cycles since its first dependency check:  " + " | ".join(rows))
+                    if nlay.value > 1:
+                        b1 = c0[1, 4].item()
+                        for nm, off in (("producer slot free", 16), ("mma operands landed", 24), ("mma issued+commit", 32)):
+                            print(f"      layer 1 per tile, {nm}: " + " ".join(str(c0[1, off + k].item() - b1) for k in range(8) if c0[1, off + k].item()))
