@@ -15,8 +15,13 @@
 //                 -> BatchNorm backward                                                     (data-gradient chain)
 //   EPI_INFER     conv + folded-BN bias + shortcut + ReLU, no grid barrier                  (teacher / eval / features)
 //
-// Warp roles (64 + 32*EW threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..2+EW-1 epilogue
-// (EW = 4 or 8; with 8, two groups of four warps take alternate tiles).
+// Warp roles (96 + 32*EW threads): warps 0 and 1 TMA producers (alternate operand stages: one warp sustains one
+// stage per ~750-950 cycles whatever it holds, two reach the SM's limit for 32-byte rows — tma_probe2.cu), warp 2 TMEM
+// alloc + MMA issue, warps 3..3+EW-1 epilogue (EW = 4 or 8; with 8, two groups of four warps take alternate
+// tiles).  Two instantiations: FUSED (BatchNorm modes, <= 184 registers) and inference only (<= 104 registers), so that
+// a FUSED CTA leaves room on its SM (registers, <= 113 KB shared memory, <= 256 TMEM columns) for a CTA of the kernel
+// that runs beside it: the teacher's inference chain beside the student's forward, the weight-gradient kernels
+// beside the data-gradient chain.
 // Hand-off between layers: all layers of a launch share one tile geometry (a launch never crosses a resolution
 // change), tile t belongs to CTA t mod G, and a 3x3 box of tile t touches tiles t-1, t, t+1 only — so a CTA needs the
 // rows of CTAs b-1, b, b+1.  Every epilogue warp publishes "my rows of this layer are stored" ONCE per layer (one
@@ -124,8 +129,8 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned targe
   asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
 }
 
-template <int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const ChainParams cp) {
+template <int EW, bool FUSED>
+__global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kernel(const ChainParams cp) {
   constexpr int ET = EW * 32;  // epilogue threads
   constexpr int NG = EW / 4;   // epilogue groups (tiles alternate between them)
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, cp.tmem_cols);
+  if (warp == 2) tmem_alloc(tmem_slot, cp.tmem_cols);
   for (int i = threadIdx.x; i < (2 * EW + 5) * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -168,16 +173,18 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
 
   const int nl = cp.n_layers;
   const int G = gridDim.x;
-
-  if (warp == 0) {
-    // ================================================================================== TMA producer
-    // TMA box loads issued by ONE thread execute one after the other (~750 cycles each on B200: tma_probe.cu), loads
-    // issued by different lanes overlap.  Every box of a stage goes out from its own lane; the lane window rotates
-    // (`bx`), so the boxes of the next tiles never queue behind those of the previous ones.
+  // register budget: 128 per thread at launch (two CTAs per SM); TMA / MMA warps need few, the epilogue many
+  if (warp < 2) {
+    // ================================================================================== TMA producers (two warps)
+    // Both warps walk the same sequence of operand stages (all layers, tiles, tap groups) and keep the same ring
+    // bookkeeping; warp p fills the stages whose running index is p modulo 2.  Within a stage every box goes out from
+    // its own lane (rotating window `bx`).
     const bool leader = lane == 0;
+    const int me = warp;      // 0 also loads the weight tiles
     uint32_t ring_phase = 0;  // bit s: uses of stage s so far, mod 2
     int stage = 0, wuse = 0;
     int bx = 0;               // rotating first lane of the next group of boxes
+    unsigned q = 0;           // running stage index
     for (int l = 0; l < nl; ++l) {
       const ChainLayer* L = cp.layers + l;
       const int ntiles = L->num_tiles;
@@ -199,10 +206,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         tma_prefetch_desc(mapW);
       }
       // weights of this layer: the tile is free once the previous layer's last MMA has completed
-      mbar_wait(wempty, (wuse & 1) ^ 1);
-      if (leader) mbar_expect_tx(wfull, 9 * w_tap_bytes);
-      __syncwarp();
-      {
+      if (me == 0) {
+        mbar_wait(wempty, (wuse & 1) ^ 1);
+        if (leader) mbar_expect_tx(wfull, 9 * w_tap_bytes);
+        __syncwarp();
         const int t = (lane - bx) & 31;  // tap t of the weight tile from lane (bx + t) % 32
         if (t < 9) tma_load_2d(smem_w + t * w_tap_bytes, mapW, wfull, 0, t * nc);
         bx = (bx + 9) & 31;
@@ -228,11 +235,16 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         __syncwarp();
         fence_proxy_async();  // those rows were written through the generic proxy, TMA reads through the async one
       }
-      if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 4] = clock64();
+      if (cp.dbg != nullptr && leader && me == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 4] = clock64();
       for (int tile = blockIdx.x; tile < ntiles; tile += G) {
         const int n0 = (tile / tiles_h) * Nt;
         const int h0 = (tile % tiles_h) * Ht;
-        for (int g = 0; g < groups; ++g) {
+        for (int g = 0; g < groups; ++g, ++q) {
+          if ((q & 1u) != static_cast<unsigned>(me)) {  // the other producer's stage
+            ring_phase ^= 1u << stage;
+            if (++stage == nstages) stage = 0;
+            continue;
+          }
           mbar_wait(&empty[stage], ((ring_phase >> stage) & 1) ^ 1);
           if (cp.dbg != nullptr && leader && g == 0 && (tile - blockIdx.x) / G < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 16 + (tile - blockIdx.x) / G] = clock64();
           uint8_t* dst = smem_a + stage * stage_bytes;
@@ -257,9 +269,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
           if (++stage == nstages) stage = 0;
         }
       }
-      if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 5] = clock64();
+      if (cp.dbg != nullptr && leader && me == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 5] = clock64();
     }
-  } else if (warp == 1) {
+  } else if (warp == 2) {
     // ================================================================================== MMA issuer
     const bool leader = elect_one_sync();
     uint32_t ring_phase = 0, acc_phase = 0;
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       if (static_cast<int>(blockIdx.x) >= ntiles) continue;
       const int kc = L->kc, nc = L->nc, tps = L->tps, nstages = L->stages;
       const bool rm = L->rmerge != 0;
-      const bool fused = L->epi >= EPI_BN_TRAIN;
+      const bool fused = FUSED && L->epi >= EPI_BN_TRAIN;
       const int rowbytes = kc * 2;
       const uint32_t a_bytes = 128u * rowbytes;
       const uint32_t win_bytes = static_cast<uint32_t>(L->Wo) * rowbytes;
@@ -337,13 +349,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       if (leader) umma_commit(wempty);  // the weight tile may be overwritten once these MMAs have completed
       if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 7] = clock64();
     }
-  } else if (warp < 2 + EW) {
+  } else if (warp >= 3) {
     // ================================================================================== epilogue warps
-    const int ew = warp - 2;
+    const int ew = warp - 3;
     const int quarter = warp & 3;
     const int group = ew >> 2;            // which of the NG groups of four warps
     const int m = quarter * 32 + lane;
-    const int tid = threadIdx.x - 64;     // index among the ET epilogue threads
+    const int tid = threadIdx.x - 96;     // index among the ET epilogue threads
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     float* s_part = s_stats;                    // [EW warps][2][64] private per-warp partial sums (zero at rest)
     float* s_c0 = s_stats + EW * 128;           // [nc] scale    | k = gamma * rstd
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       const int Ho = L->Ho, Wo = L->Wo;
       if (l == nl - 1 && cp.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       const int my_tiles = static_cast<int>(blockIdx.x) < ntiles ? (ntiles - static_cast<int>(blockIdx.x) + G - 1) / G : 0;
-      if (epi == EPI_INFER) {
+      if (!FUSED || epi == EPI_INFER) {
         // ------------------------------------------------------------------ bias + shortcut + ReLU, tile by tile
         const __nv_bfloat16* res = L->res;
         const int res_stride = L->res_stride, res_c = L->res_c;
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
         chain_publish(L->flags, lane);
         continue;
       }
+      if constexpr (FUSED) {
       // -------------------------------------------------------------------- fused BatchNorm modes
       // slots move (channel count / tiles per CTA change): the other epilogue group may still be reading the old ones
       if (L->tmem_sync) asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
@@ -659,12 +672,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) conv_chain_kernel(const Chain
       if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 3] = clock64();
       acc_phase ^= (1u << my_tiles) - 1u;
       seq += my_tiles;
+      }  // FUSED
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, cp.tmem_cols);
   }

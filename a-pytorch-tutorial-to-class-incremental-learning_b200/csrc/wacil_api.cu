@@ -311,18 +311,15 @@ int conv_attrs() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(kChainSmemMax));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_chain_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(kChainSmemMax));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_chain_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+  const void* chains[3] = {reinterpret_cast<const void*>(conv_chain_kernel<4, true>),
+                           reinterpret_cast<const void*>(conv_chain_kernel<8, true>),
+                           reinterpret_cast<const void*>(conv_chain_kernel<4, false>)};
+  for (const void* k : chains) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kChainSmemMax));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv/wgrad/chain)");
   set = true;
   return 0;
@@ -440,7 +437,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   int v = atoi(e);
   return v < lo ? lo : (v > hi ? hi : v);
 }
-int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 8, 4, 8); return v == 8 ? 8 : 4; }
+int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 4, 4, 8); return v == 8 ? 8 : 4; }
 int chain_fwd_len() { static int v = env_int("WACIL_CHAIN_FWD", 64, 1, 1000); return v; }
 int chain_bwd_len() { static int v = env_int("WACIL_CHAIN_BWD", 4, 1, 1000); return v; }
 int chain_grid_cap() { static int v = env_int("WACIL_CHAIN_GRID", 1 << 20, 1, 1 << 20); return v; }  // experiments only
@@ -449,6 +446,7 @@ size_t chain_smem_budget() { static int v = env_int("WACIL_CHAIN_SMEM", 113, 48,
 struct ChainPlan {
   ChainParams cp;
   int grid = 0, ew = 4, first = 0, count = 0;
+  bool fused = true;  // BatchNorm chain (train forward / data gradients) or inference-only instantiation
   size_t smem = 0;
 };
 
@@ -466,7 +464,7 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(64 + 32 * c.ew);
+  cfg.blockDim = dim3(96 + 32 * c.ew);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -481,7 +479,9 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = c.ew == 8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<8>, c.cp) : cudaLaunchKernelEx(&cfg, conv_chain_kernel<4>, c.cp);
+  cudaError_t e = !c.fused ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<4, false>, c.cp)
+                  : (c.ew == 8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<8, true>, c.cp)
+                               : cudaLaunchKernelEx(&cfg, conv_chain_kernel<4, true>, c.cp));
   if (e != cudaSuccess) return cuda_fail(e, "conv_chain_kernel");
   return 0;
 }
@@ -699,6 +699,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     }
     ChainPlan cpn;
     cpn.first = first; cpn.count = count; cpn.ew = fwd_ew;
+    cpn.fused = mode == WACIL_NET_TRAIN;
     cpn.grid = std::min(std::min(max_tiles, num_sms()), chain_grid_cap());
     uint32_t cols = 0;
     for (int l = first; l < first + count; ++l) {

@@ -140,7 +140,9 @@ def test_train_forward_backward_matches_oracle(w, depth, batch, heads):
                           (bn + ".bias", a.bn_bias(l, g))):
             e = relerr(view.cpu(), ref_grads[key])
             worst_model = max(worst_model, e)
-            assert e <= 2e-2, (key, e)
+            # bf16 gradient tensors between the layers: the error of the chain grows with its length (calibrated at
+            # ResNet-32: 2e-2; ResNet-110 has 3.4x the layers)
+            assert e <= 2e-2 * max(1.0, (depth - 1) / 31.0), (key, e)
             worst_fp32 = max(worst_fp32, relerr(view.cpu(), r["grads"][key]))
     # vs the pure-fp32 oracle the per-tensor figure is dominated by ReLU-mask flips (0.3 .. 0.8 for these tiny
     # batches at random init); what must hold is that the overall descent direction is the same
