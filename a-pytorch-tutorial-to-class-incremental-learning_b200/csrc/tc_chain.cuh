@@ -15,10 +15,13 @@
 //                 -> BatchNorm backward                                                     (data-gradient chain)
 //   EPI_INFER     conv + folded-BN bias + shortcut + ReLU, no grid barrier                  (teacher / eval / features)
 //
-// Warp roles (96 + 32*EW threads): warps 0 and 1 TMA producers (alternate operand stages: one warp sustains one
-// stage per ~750-950 cycles whatever it holds, two reach the SM's limit for 32-byte rows — tma_probe2.cu), warp 2 TMEM
-// alloc + MMA issue, warps 3..3+EW-1 epilogue (EW = 4 or 8; with 8, two groups of four warps take alternate
-// tiles).  Two instantiations: FUSED (BatchNorm modes, <= 184 registers) and inference only (<= 104 registers), so that
+// Warp roles (128 + 32*EW threads): warps 0 and 1 TMA producers (alternate operand stages), warps 2 and 3 MMA issuers
+// (alternate tiles; warp 2 owns the TMEM allocation), warps 4..4+EW-1 epilogue (EW = 4 or 8; with 8, two groups of four
+// warps take alternate tiles).  Why two of each: a pipeline step of ONE warp is a chain of mbarrier round trips
+// (arrive.expect_tx ~220 cycles, try_wait ~270 cycles even when the phase has already completed, tma_probe3.cu) around
+// ~50-cycle TMA / MMA issues: one producer sustains a stage per ~700-950 cycles and one issuer a tile per ~1500 whatever
+// they hold, while the TMA unit and the tensor core are idle most of that time.  Two warps interleave their chains.
+// Two instantiations: FUSED (BatchNorm modes, <= 168 registers) and inference only (<= 88 registers), so that
 // a FUSED CTA leaves room on its SM (registers, <= 113 KB shared memory, <= 256 TMEM columns) for a CTA of the kernel
 // that runs beside it: the teacher's inference chain beside the student's forward, the weight-gradient kernels
 // beside the data-gradient chain.
@@ -130,7 +133,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned targe
 }
 
 template <int EW, bool FUSED>
-__global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kernel(const ChainParams cp) {
+__global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kernel(const ChainParams cp) {
   constexpr int ET = EW * 32;  // epilogue threads
   constexpr int NG = EW / 4;   // epilogue groups (tiles alternate between them)
   extern __shared__ uint8_t smem_raw[];
@@ -156,7 +159,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
       mbar_init(&empty[i], 1);
     }
     mbar_init(wfull, 1);
-    mbar_init(wempty, 1);
+    mbar_init(wempty, 2);  // both MMA warps have finished reading the weight tile
     for (int i = 0; i < kChainMaxSlots; ++i) {
       mbar_init(&accfull[i], 1);
       mbar_init(&accempty[i], 4);  // the four warps (one per TMEM lane quarter) that own a tile
@@ -208,9 +211,10 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
       // weights of this layer: the tile is free once the previous layer's last MMA has completed
       if (me == 0) {
         mbar_wait(wempty, (wuse & 1) ^ 1);
+        // expect_tx and the loads go out together (different lanes): the transaction count may run negative for a moment,
+        // the phase cannot complete before the expect_tx arrival
         if (leader) mbar_expect_tx(wfull, 9 * w_tap_bytes);
-        __syncwarp();
-        const int t = (lane - bx) & 31;  // tap t of the weight tile from lane (bx + t) % 32
+        const int t = (lane - bx - 1) & 31;  // tap t of the weight tile from lane (bx + 1 + t) % 32
         if (t < 9) tma_load_2d(smem_w + t * w_tap_bytes, mapW, wfull, 0, t * nc);
         bx = (bx + 9) & 31;
       }
@@ -248,16 +252,14 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
           mbar_wait(&empty[stage], ((ring_phase >> stage) & 1) ^ 1);
           if (cp.dbg != nullptr && leader && g == 0 && (tile - blockIdx.x) / G < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 16 + (tile - blockIdx.x) / G] = clock64();
           uint8_t* dst = smem_a + stage * stage_bytes;
-          const int j = (lane - bx) & 31;  // box j of this stage from lane (bx + j) % 32
+          const int j = (lane - bx - 1) & 31;  // box j of this stage from lane (bx + 1 + j) % 32 (lane 0: expect_tx)
           if (rm) {
             if (leader) mbar_expect_tx(&full[stage], 3 * box_bytes);
-            __syncwarp();
             if (j < 3) tma_load_5d(dst + j * box_bytes, mapA, &full[stage], 0, j - 1, h0 - 1, n0, 0);
             bx = (bx + 3) & 31;
           } else {
             const int tap_lo = g * tps;
             if (leader) mbar_expect_tx(&full[stage], tps * a_bytes);
-            __syncwarp();
             if (j < tps) {
               int c0, c1, c2, c3, c4;
               tap_coords(9, stride, tap_lo + j, kc, h0, n0, c0, c1, c2, c3, c4);
@@ -271,9 +273,12 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
       }
       if (cp.dbg != nullptr && leader && me == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 5] = clock64();
     }
-  } else if (warp == 2) {
-    // ================================================================================== MMA issuer
+  } else if (warp < 4) {
+    // ================================================================================== MMA issuers (two warps)
+    // Both walk the same sequence of tiles and keep the same bookkeeping; warp m issues the tiles whose running index
+    // is m modulo 2 (a tile's tap groups accumulate into one TMEM slot: they stay with one issuer, in order).
     const bool leader = elect_one_sync();
+    const int me = warp - 2;
     uint32_t ring_phase = 0, acc_phase = 0;
     int stage = 0, wuse = 0, seq = 0;
     for (int l = 0; l < nl; ++l) {
@@ -308,11 +313,21 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
       int k = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += G, ++k, ++seq) {
         const int slot = fused ? k : (seq & 1);
+        if ((seq & 1) != me) {  // the other issuer's tile
+          for (int g = 0; g < groups; ++g) {
+            ring_phase ^= 1u << stage;
+            if (++stage == nstages) stage = 0;
+          }
+          acc_phase ^= 1u << slot;
+          continue;
+        }
         const uint32_t d_tmem = tmem_base + (fused ? slot * nc : slot * 64);
-        mbar_wait(&accempty[slot], ((acc_phase >> slot) & 1) ^ 1);
-        tc_fence_after();
+        // the two waits of a tile in parallel (half a warp each): their round trips overlap
+        if (lane < 16) mbar_wait(&accempty[slot], ((acc_phase >> slot) & 1) ^ 1);
+        else mbar_wait(&full[stage], (ring_phase >> stage) & 1);
+        __syncwarp();
         for (int g = 0; g < groups; ++g) {
-          mbar_wait(&full[stage], (ring_phase >> stage) & 1);
+          if (g > 0) mbar_wait(&full[stage], (ring_phase >> stage) & 1);
           tc_fence_after();
           if (cp.dbg != nullptr && leader && k == 0 && g == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 6] = clock64();
           if (cp.dbg != nullptr && leader && g == 0 && k < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 24 + k] = clock64();
@@ -349,13 +364,13 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 184 : 144) : 104) conv_chain_kern
       if (leader) umma_commit(wempty);  // the weight tile may be overwritten once these MMAs have completed
       if (cp.dbg != nullptr && leader) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 7] = clock64();
     }
-  } else if (warp >= 3) {
+  } else {
     // ================================================================================== epilogue warps
-    const int ew = warp - 3;
+    const int ew = warp - 4;
     const int quarter = warp & 3;
     const int group = ew >> 2;            // which of the NG groups of four warps
     const int m = quarter * 32 + lane;
-    const int tid = threadIdx.x - 96;     // index among the ET epilogue threads
+    const int tid = threadIdx.x - 128;    // index among the ET epilogue threads
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     float* s_part = s_stats;                    // [EW warps][2][64] private per-warp partial sums (zero at rest)
     float* s_c0 = s_stats + EW * 128;           // [nc] scale    | k = gamma * rstd

@@ -464,7 +464,7 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(96 + 32 * c.ew);
+  cfg.blockDim = dim3(128 + 32 * c.ew);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
