@@ -15,16 +15,14 @@
 //                 -> BatchNorm backward                                                     (data-gradient chain)
 //   EPI_INFER     conv + folded-BN bias + shortcut + ReLU, no grid barrier                  (teacher / eval / features)
 //
-// Warp roles (128 + 32*EW threads): warps 0 and 1 TMA producers (alternate operand stages), warps 2 and 3 MMA issuers
-// (alternate tiles; warp 2 owns the TMEM allocation), warps 4..4+EW-1 epilogue (EW = 4 or 8; with 8, two groups of four
-// warps take alternate tiles).  Why two of each: a pipeline step of ONE warp is a chain of mbarrier round trips
-// (arrive.expect_tx ~220 cycles, try_wait ~270 cycles even when the phase has already completed, tma_probe3.cu) around
-// ~50-cycle TMA / MMA issues: one producer sustains a stage per ~700-950 cycles and one issuer a tile per ~1500 whatever
-// they hold, while the TMA unit and the tensor core are idle most of that time.  Two warps interleave their chains.
-// Two instantiations: FUSED (BatchNorm modes, <= 168 registers) and inference only (<= 88 registers), so that
-// a FUSED CTA leaves room on its SM (registers, <= 113 KB shared memory, <= 256 TMEM columns) for a CTA of the kernel
-// that runs beside it: the teacher's inference chain beside the student's forward, the weight-gradient kernels
-// beside the data-gradient chain.
+// Warp roles (64 + 32*EW threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..2+EW-1 epilogue
+// (EW = 4 or 8; with 8, two groups of four warps take alternate tiles).  Every TMA box of a stage is issued by its own
+// lane (loads of one lane queue behind each other, lanes overlap) after a relaxed expect_tx.
+// Two instantiations: FUSED (BatchNorm modes, <= 168 registers) and inference only (<= 96 registers).  Every CTA stays
+// under HALF an SM in registers (192 x 168 = 32 256) and shared memory (<= 113 KB) and under 256 TMEM columns: only then
+// do CTAs of a second kernel share the SM (measured: a 43 K-register chain CTA and an 18 K-register weight-gradient CTA
+// ran strictly one after the other) — the teacher's inference chain beside the student's forward, the weight-gradient
+// kernels beside the data-gradient chain.
 // Hand-off between layers: all layers of a launch share one tile geometry (a launch never crosses a resolution
 // change), tile t belongs to CTA t mod G, and a 3x3 box of tile t touches tiles t-1, t, t+1 only — so a CTA needs the
 // rows of CTAs b-1, b, b+1.  Every epilogue warp publishes "my rows of this layer are stored" ONCE per layer (one
@@ -40,6 +38,11 @@ namespace wacil {
 
 constexpr int kChainMaxStages = 6;   // operand ring depth (mbarrier pairs)
 constexpr int kChainMaxSlots = 8;    // TMEM accumulator slots = tiles of a CTA in a fused layer
+// Operand pipelines per CTA (producer warp + MMA issuer warp each, tiles dealt round-robin).  Two were measured: same
+// time per layer as one (16.9 vs 16.8 us for a 32x32 layer) — the main loop is not bound by either warp's own chain
+// of barrier round trips — while the extra 64 threads push a FUSED CTA over half an SM's registers, which stops CTAs
+// of a second kernel from sharing the SM (profiles/r02_chain_experiments.md).  One pipeline, 192 threads.
+constexpr int kChainPipes = 1;
 
 struct ChainLayer {
   // ---- geometry of this layer's implicit GEMM (3x3, pad 1)
@@ -133,7 +136,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned targe
 }
 
 template <int EW, bool FUSED>
-__global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kernel(const ChainParams cp) {
+__global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 96) : 96) conv_chain_kernel(const ChainParams cp) {
   constexpr int ET = EW * 32;  // epilogue threads
   constexpr int NG = EW / 4;   // epilogue groups (tiles alternate between them)
   extern __shared__ uint8_t smem_raw[];
@@ -159,14 +162,14 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       mbar_init(&empty[i], 1);
     }
     mbar_init(wfull, 1);
-    mbar_init(wempty, 2);  // both MMA warps have finished reading the weight tile
+    mbar_init(wempty, kChainPipes);  // every MMA issuer has finished reading the weight tile
     for (int i = 0; i < kChainMaxSlots; ++i) {
       mbar_init(&accfull[i], 1);
       mbar_init(&accempty[i], 4);  // the four warps (one per TMEM lane quarter) that own a tile
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, cp.tmem_cols);
+  if (warp == kChainPipes) tmem_alloc(tmem_slot, cp.tmem_cols);
   for (int i = threadIdx.x; i < (2 * EW + 5) * 64; i += blockDim.x) s_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
@@ -177,17 +180,21 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
   const int nl = cp.n_layers;
   const int G = gridDim.x;
   // register budget: 128 per thread at launch (two CTAs per SM); TMA / MMA warps need few, the epilogue many
-  if (warp < 2) {
-    // ================================================================================== TMA producers (two warps)
-    // Both warps walk the same sequence of operand stages (all layers, tiles, tap groups) and keep the same ring
-    // bookkeeping; warp p fills the stages whose running index is p modulo 2.  Within a stage every box goes out from
-    // its own lane (rotating window `bx`).
+  if (warp < kChainPipes) {
+    // ================================================================================== TMA producers
+    // Two independent operand pipelines: producer p feeds MMA issuer p through its own half of the ring and its own
+    // full/empty barriers, and the pair handles the tiles whose running index is p modulo 2 (all tap groups of a tile
+    // stay in one pipeline).  Sharing stage barriers between two consumers does not work: a consumer that waits for a
+    // use two phases ahead of the barrier sees "parity complete" at once.  Within a stage every box goes out from its own
+    // lane (rotating window `bx`): loads of one lane queue behind each other, lanes overlap.
     const bool leader = lane == 0;
-    const int me = warp;      // 0 also loads the weight tiles
-    uint32_t ring_phase = 0;  // bit s: uses of stage s so far, mod 2
-    int stage = 0, wuse = 0;
+    const int me = warp;      // pipeline index; producer 0 also loads the weight tiles
+    uint64_t* myfull = full + me * (kChainMaxStages / kChainPipes);
+    uint64_t* myempty = empty + me * (kChainMaxStages / kChainPipes);
+    uint8_t* myring = smem_a + me * (cp.ring_bytes / kChainPipes);
+    uint32_t ring_phase = 0;  // bit s: uses of my stage s so far, mod 2
+    int stage = 0, wuse = 0, seq = 0;
     int bx = 0;               // rotating first lane of the next group of boxes
-    unsigned q = 0;           // running stage index
     for (int l = 0; l < nl; ++l) {
       const ChainLayer* L = cp.layers + l;
       const int ntiles = L->num_tiles;
@@ -196,7 +203,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       const CUtensorMap* mapA = cp.maps + 2 * l;
       const CUtensorMap* mapW = mapA + 1;
       const int kc = L->kc, nc = L->nc, stride = L->stride, Ht = L->Ht, Nt = L->Nt, tiles_h = L->tiles_h;
-      const int tps = L->tps, nstages = L->stages;
+      const int tps = L->tps, nstages = L->stages >= kChainPipes ? L->stages / kChainPipes : 1;  // my share of the layer's stages
       const bool rm = L->rmerge != 0;
       const int rowbytes = kc * 2;
       const uint32_t a_bytes = 128u * rowbytes;
@@ -208,19 +215,20 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
         tma_prefetch_desc(mapA);
         tma_prefetch_desc(mapW);
       }
-      // weights of this layer: the tile is free once the previous layer's last MMA has completed
+      // weights of this layer: the tile is free once the previous layer's last MMAs (both issuers) have completed
       if (me == 0) {
         mbar_wait(wempty, (wuse & 1) ^ 1);
-        // expect_tx and the loads go out together (different lanes): the transaction count may run negative for a moment,
-        // the phase cannot complete before the expect_tx arrival
-        if (leader) mbar_expect_tx(wfull, 9 * w_tap_bytes);
+        // expect_tx strictly before the loads (bytes completing ahead of their expectation wedged the barrier on
+        // hardware), relaxed: no release fence in front of it
+        if (leader) mbar_expect_tx_relaxed(wfull, 9 * w_tap_bytes);
+        __syncwarp();
         const int t = (lane - bx - 1) & 31;  // tap t of the weight tile from lane (bx + 1 + t) % 32
         if (t < 9) tma_load_2d(smem_w + t * w_tap_bytes, mapW, wfull, 0, t * nc);
         bx = (bx + 9) & 31;
       }
       ++wuse;
       if (L->ring_sync) {  // stages change size: every stage of the old shape must have been consumed
-        for (int s = 0; s < kChainMaxStages; ++s) mbar_wait(&empty[s], ((ring_phase >> s) & 1) ^ 1);
+        for (int s = 0; s < kChainMaxStages / kChainPipes; ++s) mbar_wait(&myempty[s], ((ring_phase >> s) & 1) ^ 1);
         stage = 0;
       }
       if (L->dep != 0) {
@@ -240,30 +248,28 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
         fence_proxy_async();  // those rows were written through the generic proxy, TMA reads through the async one
       }
       if (cp.dbg != nullptr && leader && me == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 4] = clock64();
-      for (int tile = blockIdx.x; tile < ntiles; tile += G) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += G, ++seq) {
+        if ((seq % kChainPipes) != me) continue;  // another pipeline's tile
         const int n0 = (tile / tiles_h) * Nt;
         const int h0 = (tile % tiles_h) * Ht;
-        for (int g = 0; g < groups; ++g, ++q) {
-          if ((q & 1u) != static_cast<unsigned>(me)) {  // the other producer's stage
-            ring_phase ^= 1u << stage;
-            if (++stage == nstages) stage = 0;
-            continue;
-          }
-          mbar_wait(&empty[stage], ((ring_phase >> stage) & 1) ^ 1);
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(&myempty[stage], ((ring_phase >> stage) & 1) ^ 1);
           if (cp.dbg != nullptr && leader && g == 0 && (tile - blockIdx.x) / G < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 16 + (tile - blockIdx.x) / G] = clock64();
-          uint8_t* dst = smem_a + stage * stage_bytes;
+          uint8_t* dst = myring + stage * stage_bytes;
           const int j = (lane - bx - 1) & 31;  // box j of this stage from lane (bx + 1 + j) % 32 (lane 0: expect_tx)
           if (rm) {
-            if (leader) mbar_expect_tx(&full[stage], 3 * box_bytes);
-            if (j < 3) tma_load_5d(dst + j * box_bytes, mapA, &full[stage], 0, j - 1, h0 - 1, n0, 0);
+            if (leader) mbar_expect_tx_relaxed(&myfull[stage], 3 * box_bytes);
+            __syncwarp();
+            if (j < 3) tma_load_5d(dst + j * box_bytes, mapA, &myfull[stage], 0, j - 1, h0 - 1, n0, 0);
             bx = (bx + 3) & 31;
           } else {
             const int tap_lo = g * tps;
-            if (leader) mbar_expect_tx(&full[stage], tps * a_bytes);
+            if (leader) mbar_expect_tx_relaxed(&myfull[stage], tps * a_bytes);
+            __syncwarp();
             if (j < tps) {
               int c0, c1, c2, c3, c4;
               tap_coords(9, stride, tap_lo + j, kc, h0, n0, c0, c1, c2, c3, c4);
-              tma_load_5d(dst + j * a_bytes, mapA, &full[stage], c0, c1, c2, c3, c4);
+              tma_load_5d(dst + j * a_bytes, mapA, &myfull[stage], c0, c1, c2, c3, c4);
             }
             bx = (bx + tps) & 31;
           }
@@ -273,12 +279,14 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       }
       if (cp.dbg != nullptr && leader && me == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 5] = clock64();
     }
-  } else if (warp < 4) {
-    // ================================================================================== MMA issuers (two warps)
-    // Both walk the same sequence of tiles and keep the same bookkeeping; warp m issues the tiles whose running index
-    // is m modulo 2 (a tile's tap groups accumulate into one TMEM slot: they stay with one issuer, in order).
+  } else if (warp < 2 * kChainPipes) {
+    // ================================================================================== MMA issuers
+    // Issuer m consumes pipeline m (see the producers): the tiles whose running index is m modulo 2.
     const bool leader = elect_one_sync();
-    const int me = warp - 2;
+    const int me = warp - kChainPipes;
+    uint64_t* myfull = full + me * (kChainMaxStages / kChainPipes);
+    uint64_t* myempty = empty + me * (kChainMaxStages / kChainPipes);
+    uint8_t* myring = smem_a + me * (cp.ring_bytes / kChainPipes);
     uint32_t ring_phase = 0, acc_phase = 0;
     int stage = 0, wuse = 0, seq = 0;
     for (int l = 0; l < nl; ++l) {
@@ -286,7 +294,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       const int ntiles = L->num_tiles;
       if (l == nl - 1 && cp.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       if (static_cast<int>(blockIdx.x) >= ntiles) continue;
-      const int kc = L->kc, nc = L->nc, tps = L->tps, nstages = L->stages;
+      const int kc = L->kc, nc = L->nc, tps = L->tps, nstages = L->stages >= kChainPipes ? L->stages / kChainPipes : 1;
       const bool rm = L->rmerge != 0;
       const bool fused = FUSED && L->epi >= EPI_BN_TRAIN;
       const int rowbytes = kc * 2;
@@ -300,7 +308,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       const uint32_t idesc = umma_idesc_bf16(128, nc, 0, 0);
       const int ksteps = kc / 16;
       const uint64_t desc_hi = umma_smem_desc(0, 16, 8u * rowbytes, layout);
-      const uint64_t a_ring_desc = desc_hi | (smem_u32(smem_a) >> 4);
+      const uint64_t a_ring_desc = desc_hi | (smem_u32(myring) >> 4);
       const uint64_t w_desc = desc_hi | (smem_u32(smem_w) >> 4);
       const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4, win16 = win_bytes >> 4, wtap16 = w_tap_bytes >> 4;
       const uint32_t box16 = box_bytes >> 4;
@@ -313,21 +321,17 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
       int k = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += G, ++k, ++seq) {
         const int slot = fused ? k : (seq & 1);
-        if ((seq & 1) != me) {  // the other issuer's tile
-          for (int g = 0; g < groups; ++g) {
-            ring_phase ^= 1u << stage;
-            if (++stage == nstages) stage = 0;
-          }
+        if ((seq % kChainPipes) != me) {  // another issuer's tile
           acc_phase ^= 1u << slot;
           continue;
         }
         const uint32_t d_tmem = tmem_base + (fused ? slot * nc : slot * 64);
         // the two waits of a tile in parallel (half a warp each): their round trips overlap
         if (lane < 16) mbar_wait(&accempty[slot], ((acc_phase >> slot) & 1) ^ 1);
-        else mbar_wait(&full[stage], (ring_phase >> stage) & 1);
+        else mbar_wait(&myfull[stage], (ring_phase >> stage) & 1);
         __syncwarp();
         for (int g = 0; g < groups; ++g) {
-          if (g > 0) mbar_wait(&full[stage], (ring_phase >> stage) & 1);
+          if (g > 0) mbar_wait(&myfull[stage], (ring_phase >> stage) & 1);
           tc_fence_after();
           if (cp.dbg != nullptr && leader && k == 0 && g == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 6] = clock64();
           if (cp.dbg != nullptr && leader && g == 0 && k < 8) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 24 + k] = clock64();
@@ -353,7 +357,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
               else issue_tap_group<4, 1>(leader, d_tmem, adesc, bdesc, idesc, a16, wtap16, first);
             }
           }
-          if (leader) umma_commit(&empty[stage]);
+          if (leader) umma_commit(&myempty[stage]);
           ring_phase ^= 1u << stage;
           if (++stage == nstages) stage = 0;
         }
@@ -366,11 +370,11 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
     }
   } else {
     // ================================================================================== epilogue warps
-    const int ew = warp - 4;
+    const int ew = warp - 2 * kChainPipes;
     const int quarter = warp & 3;
     const int group = ew >> 2;            // which of the NG groups of four warps
     const int m = quarter * 32 + lane;
-    const int tid = threadIdx.x - 128;    // index among the ET epilogue threads
+    const int tid = threadIdx.x - 64 * kChainPipes;  // index among the ET epilogue threads
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     float* s_part = s_stats;                    // [EW warps][2][64] private per-warp partial sums (zero at rest)
     float* s_c0 = s_stats + EW * 128;           // [nc] scale    | k = gamma * rstd
@@ -693,7 +697,7 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 144) : 88) conv_chain_kerne
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kChainPipes) {
     tc_fence_after();
     tmem_dealloc(tmem_base, cp.tmem_cols);
   }

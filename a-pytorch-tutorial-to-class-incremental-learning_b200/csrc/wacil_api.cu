@@ -453,18 +453,20 @@ struct ChainPlan {
 inline uint32_t w_tile_bytes(int kc, int nc) { return static_cast<uint32_t>((9u * nc * kc * 2 + 1023) & ~1023u); }
 
 // Operand-ring bytes a chain whose widest weight tile is w_max gets inside the shared-memory budget.
-size_t chain_ring_bytes(uint32_t w_max, int ew) {
+// `wide`: the launch uses at most half of the SMs (8x8 layers: 64 tiles), so its CTAs and those of the kernel running
+// beside it land on different SMs and the half-SM footprint rule does not apply.
+size_t chain_ring_bytes(uint32_t w_max, int ew, bool wide) {
   const size_t fixed = chain_smem_bytes(w_max, 0, ew);
-  const size_t budget = chain_smem_budget();
+  const size_t budget = wide ? std::max(chain_smem_budget(), static_cast<size_t>(200 * 1024)) : chain_smem_budget();
   if (budget <= fixed + 8192) return 8192;
-  return (budget - fixed) & ~size_t(1023);
+  return (budget - fixed) & ~size_t(2047);  // two pipelines: each half of the ring starts on a 1 KB boundary
 }
 
 int launch_chain(const ChainPlan& c, cudaStream_t st) {
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
-  cfg.blockDim = dim3(128 + 32 * c.ew);
+  cfg.blockDim = dim3(64 * kChainPipes + 32 * c.ew);
   cfg.dynamicSmemBytes = c.smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -642,7 +644,9 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     const int first = fsplit[ci].first, count = fsplit[ci].second;
     uint32_t w_max = 0;
     for (int l = first; l < first + count; ++l) w_max = std::max(w_max, w_tile_bytes(n->L[l].cin_pad, n->L[l].cout));
-    const size_t ring = chain_ring_bytes(w_max, fwd_ew);
+    int group_tiles = 0;
+    for (int l = first; l < first + count; ++l) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[l].H_out));
+    const size_t ring = chain_ring_bytes(w_max, fwd_ew, group_tiles * 2 <= num_sms());
     int max_tiles = 0;
     for (int l = first; l < first + count; ++l) {
       const LayerDesc& d = n->L[l];
@@ -770,7 +774,9 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         const LayerDesc& d = n->L[layer_of(el)];
         w_max = std::max(w_max, w_tile_bytes(d.cout, d.cin_pad));
       }
-      const size_t ring = chain_ring_bytes(w_max, ew_fused);
+      int group_tiles = 0;
+      for (int el = first; el < first + count; ++el) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[layer_of(el)].H_in));
+      const size_t ring = chain_ring_bytes(w_max, ew_fused, group_tiles * 2 <= num_sms());
       int max_tiles = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el), pl = l - 1;

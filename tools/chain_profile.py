@@ -77,3 +77,32 @@ for pl, name in ((plan, "train"), (tplan, "infer")):
                         b1 = c0[1, 4].item()
                         for nm, off in (("producer slot free", 16), ("mma operands landed", 24), ("mma issued+commit", 32)):
                             print(f"      layer 1 per tile, {nm}: " + " ".join(str(c0[1, off + k].item() - b1) for k in range(8) if c0[1, off + k].item()))
+
+# ---- do CTAs of two kernels share an SM?  a backward chain launch on the main stream, weight-gradient launches on a side stream
+import wacil_b200.ops as ops  # noqa: E402
+xa = torch.randn(128, 32, 32, 16, device="cuda").bfloat16()
+dya = torch.randn(128, 32, 32, 16, device="cuda").bfloat16()
+s2 = torch.cuda.Stream()
+nb = lib.wacil_net_chain_count(plan.handle, 1)
+
+
+def both():
+    s2.wait_stream(torch.cuda.current_stream())
+    w._lib.check(lib.wacil_net_run_chain(plan.handle, 1, nb - 2, None, st), "run_chain")
+    with torch.cuda.stream(s2):
+        for _ in range(4):
+            ops.conv3x3_wgrad(xa, dya, 1)
+    torch.cuda.current_stream().wait_stream(s2)
+
+
+def only_chain():
+    w._lib.check(lib.wacil_net_run_chain(plan.handle, 1, nb - 2, None, st), "run_chain")
+
+
+def only_wgrad():
+    for _ in range(4):
+        ops.conv3x3_wgrad(xa, dya, 1)
+
+
+print(f"co-residency probe: chain alone {timed(only_chain):.1f} us, 4 stage-1 wgrads alone {timed(only_wgrad):.1f} us, "
+      f"both on two streams {timed(both):.1f} us")
