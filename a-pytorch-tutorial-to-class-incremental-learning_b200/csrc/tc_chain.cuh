@@ -43,6 +43,9 @@ constexpr int kChainMaxSlots = 8;    // TMEM accumulator slots = tiles of a CTA 
 // of barrier round trips — while the extra 64 threads push a FUSED CTA over half an SM's registers, which stops CTAs
 // of a second kernel from sharing the SM (profiles/r02_chain_experiments.md).  One pipeline, 192 threads.
 constexpr int kChainPipes = 1;
+#ifndef WACIL_CHAIN_REGS
+#define WACIL_CHAIN_REGS 160
+#endif
 
 struct ChainLayer {
   // ---- geometry of this layer's implicit GEMM (3x3, pad 1)
@@ -136,7 +139,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned* bar, unsigned targe
 }
 
 template <int EW, bool FUSED>
-__global__ void __maxnreg__(FUSED ? (EW == 4 ? 168 : 96) : 96) conv_chain_kernel(const ChainParams cp) {
+__global__ void __maxnreg__(FUSED ? (EW == 4 ? WACIL_CHAIN_REGS : 96) : 128) conv_chain_kernel(const ChainParams cp) {
   constexpr int ET = EW * 32;  // epilogue threads
   constexpr int NG = EW / 4;   // epilogue groups (tiles alternate between them)
   extern __shared__ uint8_t smem_raw[];

@@ -319,7 +319,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   // Programmatic dependent launch: everything above (and the weight TMA when the weights are older than the upstream
   // grid) overlaps the tail of the previous kernel; its outputs are only touched after griddepcontrol.wait.
   if (p.pdl && p.w_early && warp == 0) {  // one lane per tap: loads of one thread would run one after the other
-    if (lane == 0) mbar_expect_tx(wfull, w_bytes);
+    if (lane == 0) mbar_expect_tx_relaxed(wfull, w_bytes);
     __syncwarp();
     if (lane < p.taps) tma_load_2d(smem_w + lane * w_tap_bytes, &mapW, wfull, 0, lane * p.nc);
   }
@@ -335,7 +335,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       const bool leader = elect_one_sync();
       const bool timing = p.dbg != nullptr;
       if (!(p.pdl && p.w_early)) {
-        if (leader) mbar_expect_tx(wfull, w_bytes);
+        if (leader) mbar_expect_tx_relaxed(wfull, w_bytes);
         __syncwarp();
         if (lane < p.taps) tma_load_2d(smem_w + lane * w_tap_bytes, &mapW, wfull, 0, lane * p.nc);
       }
@@ -354,14 +354,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           // every box from its own lane: loads of one thread run one after the other (tma_probe.cu), lanes overlap
           const int j = (lane - bx) & 31;
           if (rm) {  // per horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
-            if (leader) mbar_expect_tx(&full[stage], 3 * box_bytes);
+            if (leader) mbar_expect_tx_relaxed(&full[stage], 3 * box_bytes);
             __syncwarp();
             if (j < 3) tma_load_5d(dst + j * box_bytes, &mapA, &full[stage], 0, j - 1, h0 - 1, n0, 0);
             bx = (bx + 3) & 31;
           } else {
             const int tap_lo = g * tps;
             const int ntap = min(tps, taps - tap_lo);
-            if (leader) mbar_expect_tx(&full[stage], ntap * a_bytes);
+            if (leader) mbar_expect_tx_relaxed(&full[stage], ntap * a_bytes);
             __syncwarp();
             if (j < ntap) {
               int c0, c1, c2, c3, c4;
@@ -409,13 +409,16 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       long long dbg_wait = 0, dbg_t = 0;  // profiling only (p.dbg): cycles blocked on operands
       bool first_stage = true;
       for (int tile = blockIdx.x; tile < ntiles; tile += tstride) {
-        mbar_wait(&accempty[as], aphase ^ 1);
-        tc_fence_after();
+        // an mbarrier try_wait costs ~270 cycles even when the phase has completed (tma_probe3.cu): the two waits of a
+        // tile go out from the two halves of the warp at the same time
+        if (timing) dbg_t = clock64();
+        if (lane < 16) mbar_wait(&accempty[as], aphase ^ 1);
+        else mbar_wait(&full[stage], phase);
+        __syncwarp();
+        if (timing) dbg_wait += clock64() - dbg_t;
         const uint32_t d_tmem = tmem_base + as * nc;
         for (int g = 0; g < groups; ++g) {
-          if (timing) dbg_t = clock64();
-          mbar_wait(&full[stage], phase);
-          if (timing) dbg_wait += clock64() - dbg_t;
+          if (g > 0) mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (first_stage) { if (leader) WACIL_STAMP(4); first_stage = false; }  // first activation stage landed
           const uint64_t adesc = a_ring_desc + stage * stage16;
@@ -801,13 +804,17 @@ struct WgradParams {
   int tiles_h;
   int num_tiles;      // pixel tiles in total
   int ring;           // group ring depth (32 KB each)
-  float* part;        // [active CTAs][taps*cin][cout] fp32: every CTA that owns pixel tiles stores ITS partial sum with plain
-                      // stores (no atomics); wgrad_reduce_kernel adds the slots in CTA order -> bit-reproducible gradients
+  float* part;        // [pixel chunks][taps*cin][cout] fp32: every CTA stores ITS partial sum with plain stores (no atomics);
+                      // wgrad_reduce_kernel adds the slots in chunk order -> bit-reproducible gradients
+  int gsplit;         // CTAs per pixel chunk (1 .. groups): CTA (chunk, j) accumulates the 128-row tap groups j, j + gsplit, ...
+                      // of the chunk's tiles and writes those rows of the chunk's slot.  The 8x8 layers have 64 pixel tiles
+                      // and five 128-row groups of 64 channels each: splitting the groups puts 160 CTAs to work instead of
+                      // 32 and keeps a CTA at 64 TMEM columns instead of 512
   int pdl;            // launched with programmatic stream serialization
 };
-// CTAs of a wgrad launch that own pixel tiles (= partial slots written): contiguous chunks of `per` tiles
-__host__ __device__ inline int wgrad_active_ctas(int num_tiles, int grid) {
-  const int per = (num_tiles + grid - 1) / grid;
+// Pixel chunks of a wgrad launch that own tiles (= partial slots written): contiguous chunks of `per` tiles
+__host__ __device__ inline int wgrad_active_ctas(int num_tiles, int chunks) {
+  const int per = (num_tiles + chunks - 1) / chunks;
   return (num_tiles + per - 1) / per;
 }
 
@@ -838,11 +845,14 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
   const uint32_t y_stride = (y_bytes + 1023) & ~1023u;
 
-  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(groups * p.cout));
-
-  // contiguous chunk of pixel tiles for this CTA
-  const int per = (p.num_tiles + gridDim.x - 1) / gridDim.x;
-  const int t_begin = blockIdx.x * per;
+  // this CTA: pixel chunk `chunk` (contiguous tiles), tap groups gj, gj + gsplit, ...
+  const int gsplit = p.gsplit > 0 ? p.gsplit : 1;
+  const int chunk = blockIdx.x / gsplit, gj = blockIdx.x % gsplit;
+  const int chunks = gridDim.x / gsplit;
+  const int my_groups = (groups - gj + gsplit - 1) / gsplit;
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(my_groups * p.cout));
+  const int per = (p.num_tiles + chunks - 1) / chunks;
+  const int t_begin = chunk * per;
   const int t_end = min(p.num_tiles, t_begin + per);
 
   if (warp == 0 && lane == 0) {
@@ -882,7 +892,7 @@ __global__ void __launch_bounds__(kConvThreads, 2)
       const int n0 = (tile / p.tiles_h) * p.Nt;
       const int h0 = (tile % p.tiles_h) * p.Ht;
       mbar_wait(&yempty[ys], yphase ^ 1);
-      if (leader) mbar_expect_tx(&yfull[ys], y_bytes);
+      if (leader) mbar_expect_tx_relaxed(&yfull[ys], y_bytes);
       __syncwarp();
       if (((lane - bx) & 31) == 0) tma_load_2d(smem_y + ys * y_stride, &mapDY, &yfull[ys], 0, tile * 128);
       bx = (bx + 1) & 31;
@@ -890,11 +900,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         ys = 0;
         yphase ^= 1;
       }
-      for (int g = 0; g < groups; ++g) {
+      for (int g = gj; g < groups; g += gsplit) {
         const int tap_lo = g * tpg;
         const int ntap = min(tpg, taps - tap_lo);
         mbar_wait(&gempty[gs], gphase ^ 1);
-        if (leader) mbar_expect_tx(&gfull[gs], ntap * slot_bytes);
+        if (leader) mbar_expect_tx_relaxed(&gfull[gs], ntap * slot_bytes);
         __syncwarp();
         {
           const int j = (lane - bx) & 31;
@@ -930,11 +940,11 @@ __global__ void __launch_bounds__(kConvThreads, 2)
         tc_fence_after();
         const uint64_t b0 = b_hi | (smem_u32(smem_y + ys * y_stride) >> 4);
         const bool first_tile = tile == t_begin;
-        for (int g = 0; g < groups; ++g) {
+        for (int g = gj, gi = 0; g < groups; g += gsplit, ++gi) {
           mbar_wait(&gfull[gs], gphase);
           tc_fence_after();
           const uint64_t a0 = a_hi | (smem_u32(smem_g + gs * group_bytes) >> 4);
-          const uint32_t d_tmem = tmem_base + g * cout;
+          const uint32_t d_tmem = tmem_base + gi * cout;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {  // 8 K-steps of 16 pixels
             if (j == 0) { if (leader) umma_bf16(d_tmem, a0, b0, idesc, first_tile ? 0u : 1u); }
@@ -959,13 +969,13 @@ __global__ void __launch_bounds__(kConvThreads, 2)
     mbar_wait(accfull, 0);
     tc_fence_after();
     const int rows = p.taps * p.cin;
-    for (int g = 0; g < groups; ++g) {
+    for (int g = gj, gi = 0; g < groups; g += gsplit, ++gi) {
       const int row = g * 128 + quarter * 32 + lane;
       for (int c0 = 0; c0 < p.cout; c0 += 16) {
         float v[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * p.cout + c0, v);
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + gi * p.cout + c0, v);
         if (row < rows) {
-          float4* dst = reinterpret_cast<float4*>(p.part + (static_cast<size_t>(blockIdx.x) * rows + row) * p.cout + c0);
+          float4* dst = reinterpret_cast<float4*>(p.part + (static_cast<size_t>(chunk) * rows + row) * p.cout + c0);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]);
           dst[1] = make_float4(v[4], v[5], v[6], v[7]);
           dst[2] = make_float4(v[8], v[9], v[10], v[11]);
@@ -983,9 +993,9 @@ __global__ void __launch_bounds__(kConvThreads, 2)
   }
 }
 
-// Ordered reduction of the per-CTA weight-gradient slots: dst[e] = part[0][e] + part[1][e] + ... in a fixed tree.
-// Eight lanes share one float4 of the result: lane j adds slots j, j+8, ... in order, then a fixed xor-shuffle tree
-// combines the eight sums.  blockIdx.y selects the layer.
+// Ordered reduction of the per-chunk weight-gradient slots: dst[e] = part[0][e] + part[1][e] + ... in a fixed tree.
+// A warp shares one float4 of the result: lane j adds slots j, j+32, ... in order (independent loads, issued together),
+// then a fixed xor-shuffle tree combines the 32 sums.  blockIdx.y selects the layer.
 struct WgradReduceDesc {
   const float* part;
   float* dst;
@@ -994,30 +1004,29 @@ struct WgradReduceDesc {
 };
 __device__ __forceinline__ void wgrad_reduce_body(const WgradReduceDesc& d) {
   const int n4 = d.elems >> 2;
-  const int sub = threadIdx.x & 7;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; e < ((n4 + 31) & ~31); e += (gridDim.x * blockDim.x) >> 3) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n4; e += warps) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e < n4) {
-      const float4* src = reinterpret_cast<const float4*>(d.part) + e;
-      for (int r0 = sub; r0 < d.nparts; r0 += 8 * 8) {  // eight independent 16-byte loads in flight per lane
-        float4 t[8];
+    const float4* src = reinterpret_cast<const float4*>(d.part) + e;
+    for (int r0 = lane; r0 < d.nparts; r0 += 32 * 4) {  // four independent 16-byte loads in flight per lane
+      float4 t[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = r0 + 8 * j;
-          t[j] = r < d.nparts ? __ldcg(src + static_cast<size_t>(r) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + 32 * j;
+        t[j] = r < d.nparts ? __ldcg(src + static_cast<size_t>(r) * n4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
     }
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
       acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
       acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
     }
-    if (sub == 0 && e < n4) reinterpret_cast<float4*>(d.dst)[e] = acc;
+    if (lane == 0) reinterpret_cast<float4*>(d.dst)[e] = acc;
   }
 }
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ descs) {

@@ -288,10 +288,11 @@ static int run_wgrad(const Case& c) {
   if (g_timing) { grid = (p.num_tiles + 1) / 2; if (grid > 296) grid = 296; }
   {
     WgradReduceDesc rd{dpart, ddw, wgrad_active_ctas(p.num_tiles, grid), (int)nw};
+    p.gsplit = 1;
     CK(cudaMemcpy(ddesc, &rd, sizeof(rd), cudaMemcpyHostToDevice));
   }
   wgrad_gemm_kernel<<<grid, kConvThreads, smem>>>(mapX, mapDY, p);
-  wgrad_reduce_kernel<<<dim3(48, 1), 256>>>(ddesc);
+  wgrad_reduce_kernel<<<dim3(148, 1), 256>>>(ddesc);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   if (g_timing) {

@@ -399,11 +399,16 @@ int setup_wgrad(WgradLaunch& w, const void* x, const void* dy, float* part, int 
   p.num_tiles = static_cast<int>((npix + 127) / 128);
   p.ring = 2;
   p.part = part;
+  {
+    // the 8x8 layers (64 channels): few pixel tiles, five 128-row tap groups -> one CTA per (pixel chunk, group)
+    const int tpg = 128 / cin, groups = (taps + tpg - 1) / tpg;
+    p.gsplit = (cin >= 64 && groups > 1) ? groups : 1;
+  }
   int e = make_act_map(&w.mapX, x, N, H, W, cin, stride, p.Ht, p.Nt);
   if (e) return fail(WACIL_E_DRIVER, "wgrad activation tensor map: %d", e);
   e = make_mat_map(&w.mapDY, dy, npix, cout, 128);
   if (e) return fail(WACIL_E_DRIVER, "wgrad dY tensor map: %d", e);
-  w.grid = wgrad_grid(p.num_tiles);
+  w.grid = wgrad_grid(p.num_tiles) * p.gsplit;
   w.smem = wgrad_smem_bytes(p);
   return 0;
 }
@@ -438,6 +443,19 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return v < lo ? lo : (v > hi ? hi : v);
 }
 int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 4, 4, 8); return v == 8 ? 8 : 4; }
+// WACIL_ENGINE = layer | chain: one cooperative conv_gemm_kernel launch per layer (programmatic dependent launches hide
+// the prologues; kernels of the teacher / weight-gradient branches interleave between them), or several layers per
+// persistent conv_chain_kernel launch.  Measured on the step graph (profiles/r02_chain_experiments.md): see kDefaultEngine.
+enum { ENGINE_LAYER = 0, ENGINE_CHAIN = 1 };
+constexpr int kDefaultEngine = ENGINE_LAYER;
+int engine_kind() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WACIL_ENGINE");
+    v = e == nullptr ? kDefaultEngine : (e[0] == 'c' ? ENGINE_CHAIN : ENGINE_LAYER);
+  }
+  return v;
+}
 int chain_fwd_len() { static int v = env_int("WACIL_CHAIN_FWD", 64, 1, 1000); return v; }
 int chain_bwd_len() { static int v = env_int("WACIL_CHAIN_BWD", 4, 1, 1000); return v; }
 int chain_grid_cap() { static int v = env_int("WACIL_CHAIN_GRID", 1 << 20, 1, 1 << 20); return v; }  // experiments only
@@ -471,9 +489,12 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
-  attrs[na].id = cudaLaunchAttributeCooperative;  // grid barriers and cross-CTA ready flags: all CTAs co-resident
-  attrs[na].val.cooperative = 1;
-  ++na;
+  static int coop = env_int("WACIL_CHAIN_COOP", 1, 0, 1);  // experiment: 0 = plain launch
+  if (coop) {
+    attrs[na].id = cudaLaunchAttributeCooperative;  // grid barriers and cross-CTA ready flags: all CTAs co-resident
+    attrs[na].val.cooperative = 1;
+    ++na;
+  }
   if (c.cp.pdl) {
     attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
@@ -501,6 +522,7 @@ struct wacil_net {
   std::vector<ConvLaunch> fprop, dgrad;   // chain elements: forward layer l; backward element of layer l (l >= 1)
   std::vector<WgradLaunch> wgrad;
   std::vector<ChainPlan> fchains, bchains;
+  int engine = ENGINE_CHAIN;              // ENGINE_LAYER: every chain plan holds ONE element, launched as conv_gemm_kernel
   bool fwd_done = false;
   cudaStream_t side = nullptr;            // optional second stream: weight gradients run beside the data-gradient chain
   std::vector<cudaEvent_t> ev_chain;      // backward chain i finished (main stream)
@@ -620,6 +642,28 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   __nv_bfloat16* wbuf = n->at<__nv_bfloat16>(n->off.wbuf);
   const int ew_fused = chain_ew();
   const bool pdl = pdl_enabled();
+  n->engine = engine_kind();
+  const bool per_layer = n->engine == ENGINE_LAYER;
+  const int fwd_len = per_layer ? 1 : chain_fwd_len(), bwd_len = per_layer ? 1 : chain_bwd_len();
+  ce = cudaMemset(n->ws + n->off.gbar, 0, 64);
+  if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "grid barrier clear"); }
+  // ENGINE_LAYER: finish a chain element as a stand-alone conv_gemm_kernel launch
+  auto finish_layer_launch = [&](ConvLaunch& c, int grid, bool first_of_forward) -> int {
+    c.grid = grid;
+    c.p.acc_stages = c.p.epi >= EPI_BN_TRAIN ? (c.p.num_tiles + grid - 1) / grid : 2;
+    c.p.grid_bar = n->at<unsigned>(n->off.gbar);
+    c.p.eps = kBnEps;
+    c.p.momentum = kBnMomentum;
+    c.p.pdl = pdl ? 1 : 0;
+    c.p.w_early = first_of_forward ? 0 : 1;  // the operand copies are older than the upstream kernel, except right after cast_weights
+    c.smem = conv_smem_bytes(c.p);
+    while (c.smem > kConvSmemMax && c.p.stages > 2) {  // the ring was sized for the chain kernel's slightly larger budget
+      --c.p.stages;
+      c.smem = conv_smem_bytes(c.p);
+    }
+    if (c.smem > kConvSmemMax) return fail(WACIL_E_SHAPE, "layer launch needs %zu bytes of shared memory", c.smem);
+    return 0;
+  };
   std::vector<size_t> so(nl);
   {
     size_t o = 0;
@@ -637,7 +681,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
 
   // ------------------------------------------------------------------------------------------ forward chains
   const int fwd_ew = mode == WACIL_NET_TRAIN ? ew_fused : 4;
-  const auto fsplit = split_chains(nl, chain_fwd_len(), fwd_group_start);
+  const auto fsplit = split_chains(nl, fwd_len, fwd_group_start);
   float* bias = n->at<float>(n->off.bias);
   int cur = 0;  // INFER: rotating buffer holding the current block input
   for (size_t ci = 0; ci < fsplit.size(); ++ci) {
@@ -646,7 +690,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     for (int l = first; l < first + count; ++l) w_max = std::max(w_max, w_tile_bytes(n->L[l].cin_pad, n->L[l].cout));
     int group_tiles = 0;
     for (int l = first; l < first + count; ++l) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[l].H_out));
-    const size_t ring = chain_ring_bytes(w_max, fwd_ew, group_tiles * 2 <= num_sms());
+    const size_t ring = chain_ring_bytes(w_max, fwd_ew, !per_layer && group_tiles * 2 <= num_sms());
     int max_tiles = 0;
     for (int l = first; l < first + count; ++l) {
       const LayerDesc& d = n->L[l];
@@ -726,7 +770,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     cpn.cp.layers = dtab + first;
     cpn.cp.maps = dmaps + 2 * first;
     cpn.cp.n_layers = count;
-    cpn.cp.grid_bar = sync_f + ci;
+    cpn.cp.grid_bar = sync_f + (per_layer ? 0 : ci);
     cpn.cp.pdl = pdl ? 1 : 0;
     cpn.cp.w_bytes_max = w_max;
     cpn.cp.ring_bytes = static_cast<uint32_t>(ring);
@@ -734,7 +778,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     while (cpn.cp.tmem_cols < cols) cpn.cp.tmem_cols <<= 1;
     cpn.cp.dbg = nullptr;
     cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), fwd_ew);
-    if (static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+    if (!per_layer && static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+    if (per_layer && (e = finish_layer_launch(n->fprop[first], cpn.grid, mode == WACIL_NET_TRAIN && first == 0))) { delete n; return e; }
     n->fchains.push_back(cpn);
   }
 
@@ -753,7 +798,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       n->wgrad[l].p.pdl = pdl ? 1 : 0;
       wred[l].part = n->at<float>(n->off.wpart[l]);
       wred[l].dst = n->grads + d.w_off;
-      wred[l].nparts = wgrad_active_ctas(n->wgrad[l].p.num_tiles, n->wgrad[l].grid);
+      wred[l].nparts = wgrad_active_ctas(n->wgrad[l].p.num_tiles, n->wgrad[l].grid / n->wgrad[l].p.gsplit);
       wred[l].elems = 9 * d.cin_pad * d.cout;
       if (d.stride == 2) {
         ce = cudaMemset(n->ws + n->off.gyup[l], 0, static_cast<size_t>(batch) * d.H_in * d.H_in * d.cout * 2);
@@ -766,7 +811,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     // flipped [cin][cout] weights) fused with the ReLU mask + BatchNorm backward of layer l-1
     const int ne = nl - 1;
     auto layer_of = [&](int el) { return nl - 1 - el; };
-    const auto bsplit = split_chains(ne, chain_bwd_len(), [&](int el) { return n->L[layer_of(el)].stride == 2; });
+    const auto bsplit = split_chains(ne, bwd_len, [&](int el) { return n->L[layer_of(el)].stride == 2; });
     for (size_t ci = 0; ci < bsplit.size(); ++ci) {
       const int first = bsplit[ci].first, count = bsplit[ci].second;
       uint32_t w_max = 0;
@@ -776,7 +821,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       int group_tiles = 0;
       for (int el = first; el < first + count; ++el) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[layer_of(el)].H_in));
-      const size_t ring = chain_ring_bytes(w_max, ew_fused, group_tiles * 2 <= num_sms());
+      const size_t ring = chain_ring_bytes(w_max, ew_fused, !per_layer && group_tiles * 2 <= num_sms());
       int max_tiles = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el), pl = l - 1;
@@ -831,7 +876,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       cpn.cp.layers = dtab + nl + first;
       cpn.cp.maps = dmaps + 2 * (nl + first);
       cpn.cp.n_layers = count;
-      cpn.cp.grid_bar = sync_b + ci;
+      cpn.cp.grid_bar = sync_b + (per_layer ? 0 : ci);
       cpn.cp.pdl = pdl ? 1 : 0;
       cpn.cp.w_bytes_max = w_max;
       cpn.cp.ring_bytes = static_cast<uint32_t>(ring);
@@ -839,7 +884,8 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       while (cpn.cp.tmem_cols < cols) cpn.cp.tmem_cols <<= 1;
       cpn.cp.dbg = nullptr;
       cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), ew_fused);
-      if (static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+      if (!per_layer && static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
+      if (per_layer && (e = finish_layer_launch(n->dgrad[layer_of(first)], cpn.grid, false))) { delete n; return e; }
       n->bchains.push_back(cpn);
     }
   }
@@ -901,6 +947,12 @@ int wacil_net_run_chain(wacil_net_t* n, int backward, int index, long long* dbg,
   cudaError_t ce = backward ? cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st)
                             : cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
+  if (n->engine == ENGINE_LAYER) {  // one conv_gemm_kernel launch (no stamps)
+    ConvLaunch c = backward ? n->dgrad[static_cast<int>(n->L.size()) - 1 - v[index].first] : n->fprop[v[index].first];
+    c.p.pdl = 0;
+    c.p.w_early = 0;
+    return launch_conv(c, st);
+  }
   ChainPlan c = v[index];
   c.cp.dbg = dbg;
   c.cp.pdl = 0;
@@ -951,7 +1003,9 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
   const size_t nl = n->L.size();
   int launches = 0;
   int e;
-  cudaError_t ce = cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);  // barrier counters + ready flags
+  cudaError_t ce = cudaSuccess;
+  if (n->engine == ENGINE_CHAIN)  // barrier counters + ready flags of the chain launches
+    ce = cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
   const long long npix0 = static_cast<long long>(n->batch) * 32 * 32;
   pack_input_kernel<<<static_cast<int>((npix0 + 255) / 256), 256, 0, st>>>(x, n->at<__nv_bfloat16>(n->off.a0),
@@ -966,7 +1020,7 @@ int wacil_net_forward(wacil_net_t* n, const float* x, int C_seen, float* feats, 
     ++launches;
   }
   for (const ChainPlan& c : n->fchains) {
-    if ((e = launch_chain(c, st))) return e;
+    if ((e = n->engine == ENGINE_LAYER ? launch_conv(n->fprop[c.first], st) : launch_chain(c, st))) return e;
     ++launches;
   }
   const __nv_bfloat16* last = n->mode == WACIL_NET_TRAIN ? n->at<__nv_bfloat16>(n->off.a[nl - 1]) : n->fprop[nl - 1].p.out;
@@ -990,7 +1044,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   int launches = 0, e;
   cudaError_t ce = cudaMemsetAsync(n->grads, 0, static_cast<size_t>(n->lay.param_elems) * 4, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "grad clear");
-  ce = cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st);
+  if (n->engine == ENGINE_CHAIN) ce = cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
   float* dfeats = n->at<float>(n->off.dfeats);
   fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
@@ -1045,16 +1099,21 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     cudaError_t ce_ = (call);                                  \
     if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
   } while (0)
-  auto wgrads = [&](int l_hi, int l_lo) -> int {  // weight gradients of layers l_hi .. l_lo (descending) + their reduction
+  int pending = 0;  // weight gradients whose partial slots have not been reduced yet: layers l_lo .. l_lo + pending - 1
+  auto wgrads = [&](int l_hi, int l_lo) -> int {  // weight gradients of layers l_hi .. l_lo (descending) + ordered reduction
     for (int l = l_hi; l >= l_lo; --l) {
       int e2 = launch_wgrad(n->wgrad[l], ws);
       if (e2) return e2;
       ++launches;
     }
-    wgrad_reduce_kernel<<<dim3(48, static_cast<unsigned>(l_hi - l_lo + 1)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l_lo);
-    cudaError_t e_ = cudaGetLastError();
-    if (e_ != cudaSuccess) return cuda_fail(e_, "wgrad_reduce_kernel");
-    ++launches;
+    pending += l_hi - l_lo + 1;
+    if (pending >= 4 || l_lo == 0) {  // a few layers per reduction launch
+      wgrad_reduce_kernel<<<dim3(148, static_cast<unsigned>(pending)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l_lo);
+      cudaError_t e_ = cudaGetLastError();
+      if (e_ != cudaSuccess) return cuda_fail(e_, "wgrad_reduce_kernel");
+      ++launches;
+      pending = 0;
+    }
     return 0;
   };
   if (par) {
@@ -1064,7 +1123,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   if ((e = wgrads(nl - 1, nl - 1))) return e;
   for (size_t ci = 0; ci < n->bchains.size(); ++ci) {
     const ChainPlan& c = n->bchains[ci];
-    if ((e = launch_chain(c, st))) return e;
+    if ((e = n->engine == ENGINE_LAYER ? launch_conv(n->dgrad[nl - 1 - c.first], st) : launch_chain(c, st))) return e;
     ++launches;
     if (par) {
       WACIL_EV(cudaEventRecord(n->ev_chain[ci + 1], st), "event record");
@@ -1424,8 +1483,8 @@ int wacil_conv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int H, 
   if (e) return e;
   if ((e = launch_wgrad(wl, S(stream)))) return e;
   // per-CTA partial sums -> dw, added in CTA order (bit-reproducible)
-  WgradReduceDesc rd{static_cast<const float*>(workspace), dw, wgrad_active_ctas(wl.p.num_tiles, wl.grid), 9 * cin * cout};
-  wgrad_reduce_one_kernel<<<dim3(48, 1), 256, 0, S(stream)>>>(rd);
+  WgradReduceDesc rd{static_cast<const float*>(workspace), dw, wgrad_active_ctas(wl.p.num_tiles, wl.grid / wl.p.gsplit), 9 * cin * cout};
+  wgrad_reduce_one_kernel<<<dim3(148, 1), 256, 0, S(stream)>>>(rd);
   WACIL_LAUNCH_CHECK("wgrad_reduce_one_kernel");
   return 0;
 }

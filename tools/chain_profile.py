@@ -106,3 +106,42 @@ def only_wgrad():
 
 print(f"co-residency probe: chain alone {timed(only_chain):.1f} us, 4 stage-1 wgrads alone {timed(only_wgrad):.1f} us, "
       f"both on two streams {timed(both):.1f} us")
+
+# ---- the single-layer fused kernel (conv_gemm_kernel, cooperative) beside the weight-gradient kernel, and two chains side by side
+gam, bet = torch.ones(16, device="cuda"), torch.zeros(16, device="cuda")
+rm_, rv_ = torch.zeros(16, device="cuda"), torch.ones(16, device="cuda")
+wt = (torch.randn(9, 16, 16, device="cuda") * 0.1).bfloat16()
+yb, ab = torch.empty_like(xa), torch.empty_like(xa)
+savedb = torch.empty(32, device="cuda")
+wsb = torch.zeros(lib.wacil_conv3x3_bn_relu_workspace_bytes(16), dtype=torch.uint8, device="cuda")
+
+
+def fused4(stream):
+    for _ in range(4):
+        rc = lib.wacil_conv3x3_bn_relu(xa.data_ptr(), wt.data_ptr(), gam.data_ptr(), bet.data_ptr(), dya.data_ptr(), 1,
+                                       yb.data_ptr(), ab.data_ptr(), savedb.data_ptr(), rm_.data_ptr(), rv_.data_ptr(),
+                                       128, 32, 32, 16, 16, 1, wsb.data_ptr(), stream)
+        assert rc == 0
+
+
+def both_old():
+    s2.wait_stream(torch.cuda.current_stream())
+    fused4(st)
+    with torch.cuda.stream(s2):
+        only_wgrad()
+    torch.cuda.current_stream().wait_stream(s2)
+
+
+print(f"co-residency probe (single-layer fused kernel): 4 fused layers alone {timed(lambda: fused4(st)):.1f} us, "
+      f"with 4 wgrads on a second stream {timed(both_old):.1f} us")
+
+
+def two_chains():
+    s2.wait_stream(torch.cuda.current_stream())
+    w._lib.check(lib.wacil_net_run_chain(plan.handle, 0, 0, None, st), "run_chain")
+    with torch.cuda.stream(s2):
+        w._lib.check(lib.wacil_net_run_chain(tplan.handle, 0, 0, None, s2.cuda_stream), "run_chain")
+    torch.cuda.current_stream().wait_stream(s2)
+
+
+print(f"co-residency probe (train chain 0 + inference chain 0 on two streams): {timed(two_chains):.1f} us")
