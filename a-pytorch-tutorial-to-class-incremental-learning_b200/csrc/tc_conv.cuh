@@ -351,7 +351,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           mbar_wait(&empty[stage], phase ^ 1);
           if (timing) dbg_wait += clock64() - dbg_t;
           uint8_t* dst = smem_a + stage * stage_bytes;
-          // every box from its own lane: loads of one thread run one after the other (tma_probe.cu), lanes overlap
+#ifdef WACIL_MULTILANE_TMA
+          // every box from its own lane
           const int j = (lane - bx) & 31;
           if (rm) {  // per horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
             if (leader) mbar_expect_tx_relaxed(&full[stage], 3 * box_bytes);
@@ -370,6 +371,28 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
             }
             bx = (bx + ntap) & 31;
           }
+#else
+          // the elected lane issues the boxes back to back (~50 cycles each; the pipeline step is bound by the mbarrier
+          // round trips around them, not by the issue: tma_probe3.cu)
+          (void)bx;
+          if (rm) {  // per horizontal tap offset s: image rows h0-1 .. h0+Ht, columns shifted by s-1 (OOB = zero padding)
+            if (leader) {
+              mbar_expect_tx_relaxed(&full[stage], 3 * box_bytes);
+              tma_load_5d(dst, &mapA, &full[stage], 0, -1, h0 - 1, n0, 0);
+              tma_load_5d(dst + box_bytes, &mapA, &full[stage], 0, 0, h0 - 1, n0, 0);
+              tma_load_5d(dst + 2 * box_bytes, &mapA, &full[stage], 0, 1, h0 - 1, n0, 0);
+            }
+          } else {
+            const int tap_lo = g * tps;
+            const int ntap = min(tps, taps - tap_lo);
+            if (leader) mbar_expect_tx_relaxed(&full[stage], ntap * a_bytes);
+            for (int j = 0; j < ntap; ++j) {
+              int c0, c1, c2, c3, c4;
+              tap_coords(taps, p.stride, tap_lo + j, p.kc, h0, n0, c0, c1, c2, c3, c4);
+              if (leader) tma_load_5d(dst + j * a_bytes, &mapA, &full[stage], c0, c1, c2, c3, c4);
+            }
+          }
+#endif
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -412,9 +435,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         // an mbarrier try_wait costs ~270 cycles even when the phase has completed (tma_probe3.cu): the two waits of a
         // tile go out from the two halves of the warp at the same time
         if (timing) dbg_t = clock64();
+#ifdef WACIL_SERIAL_WAITS
+        mbar_wait(&accempty[as], aphase ^ 1);
+        mbar_wait(&full[stage], phase);
+#else
         if (lane < 16) mbar_wait(&accempty[as], aphase ^ 1);
         else mbar_wait(&full[stage], phase);
         __syncwarp();
+#endif
         if (timing) dbg_wait += clock64() - dbg_t;
         const uint32_t d_tmem = tmem_base + as * nc;
         for (int g = 0; g < groups; ++g) {

@@ -153,11 +153,22 @@ struct Offsets {
 
 constexpr int kSyncCounters = 64;  // grid-barrier counters (one per chain launch) at the head of a sync region
 
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
 // Grid of the weight-gradient kernel of a layer (pixel tiles are split into contiguous chunks, one per CTA) — also the
 // number of partial-sum slots its workspace holds.
 int wgrad_grid(int num_tiles) {
+  static const int cap_env = env_int("WACIL_WGRAD_CTAS", 0, 0, 4096);  // experiment: CTAs (pixel chunks) per launch
   int g = (num_tiles + 1) / 2;
-  if (g > 2 * num_sms()) g = 2 * num_sms();
+  // at most one CTA per SM: a second resident weight-gradient CTA (75 KB of shared memory each) leaves no room for the
+  // CTA of the cooperative data-gradient launch that has to fit on every SM at once
+  const int cap = cap_env > 0 ? cap_env : num_sms();
+  if (g > cap) g = cap;
   return g < 1 ? 1 : g;
 }
 
@@ -436,12 +447,6 @@ int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
 //   WACIL_CHAIN_FWD    layers per forward launch (a launch never crosses a resolution change)
 //   WACIL_CHAIN_BWD    layers per backward launch (the weight gradients of a launch's layers start when it ends)
 //   WACIL_CHAIN_SMEM   shared-memory budget of a chain CTA in KB (<= 227)
-int env_int(const char* name, int dflt, int lo, int hi) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  int v = atoi(e);
-  return v < lo ? lo : (v > hi ? hi : v);
-}
 int chain_ew() { static int v = env_int("WACIL_CHAIN_EW", 4, 4, 8); return v == 8 ? 8 : 4; }
 // WACIL_ENGINE = layer | chain: one cooperative conv_gemm_kernel launch per layer (programmatic dependent launches hide
 // the prologues; kernels of the teacher / weight-gradient branches interleave between them), or several layers per
@@ -526,7 +531,9 @@ struct wacil_net {
   bool fwd_done = false;
   cudaStream_t side = nullptr;            // optional second stream: weight gradients run beside the data-gradient chain
   std::vector<cudaEvent_t> ev_chain;      // backward chain i finished (main stream)
-  cudaEvent_t ev_join = nullptr;          // all weight gradients reduced (side stream)
+  cudaEvent_t ev_join = nullptr;          // all weight gradients reduced
+  cudaStream_t red = nullptr;             // third branch (owned by the plan): the ordered reductions of the weight-gradient slots,
+  std::vector<cudaEvent_t> ev_wg;         // so that a reduction never sits between two weight-gradient launches of the side stream
   const float* last_feats = nullptr;
   bool folded = false;
   int launches = 0;
@@ -899,7 +906,9 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
 void wacil_net_destroy(wacil_net_t* net) {
   if (!net) return;
   for (cudaEvent_t e : net->ev_chain) cudaEventDestroy(e);
+  for (cudaEvent_t e : net->ev_wg) cudaEventDestroy(e);
   if (net->ev_join) cudaEventDestroy(net->ev_join);
+  if (net->red) cudaStreamDestroy(net->red);
   delete net;
 }
 
@@ -908,7 +917,11 @@ int wacil_net_set_side_stream(wacil_net_t* n, void* side_stream) {
   n->side = static_cast<cudaStream_t>(side_stream);
   if (n->side != nullptr && n->ev_join == nullptr) {
     n->ev_chain.resize(n->bchains.size() + 1);
+    n->ev_wg.resize(n->L.size() / 4 + 2);
     cudaError_t e = cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&n->red, cudaStreamNonBlocking);
+    for (size_t i = 0; i < n->ev_wg.size() && e == cudaSuccess; ++i)
+      e = cudaEventCreateWithFlags(&n->ev_wg[i], cudaEventDisableTiming);
     for (size_t i = 0; i < n->ev_chain.size() && e == cudaSuccess; ++i)
       e = cudaEventCreateWithFlags(&n->ev_chain[i], cudaEventDisableTiming);
     if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
@@ -1099,16 +1112,25 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     cudaError_t ce_ = (call);                                  \
     if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
   } while (0)
+  static const int xp = env_int("WACIL_XP", 0, 0, 7);  // experiments: 1 skip wgrad kernels, 2 skip reductions, 4 skip the data-gradient launches
   int pending = 0;  // weight gradients whose partial slots have not been reduced yet: layers l_lo .. l_lo + pending - 1
+  size_t nred = 0;  // reductions launched so far
   auto wgrads = [&](int l_hi, int l_lo) -> int {  // weight gradients of layers l_hi .. l_lo (descending) + ordered reduction
-    for (int l = l_hi; l >= l_lo; --l) {
+    for (int l = l_hi; l >= l_lo && !(xp & 1); --l) {
       int e2 = launch_wgrad(n->wgrad[l], ws);
       if (e2) return e2;
       ++launches;
     }
     pending += l_hi - l_lo + 1;
-    if (pending >= 4 || l_lo == 0) {  // a few layers per reduction launch
-      wgrad_reduce_kernel<<<dim3(148, static_cast<unsigned>(pending)), 256, 0, ws>>>(n->at<WgradReduceDesc>(n->off.wred) + l_lo);
+    if ((pending >= 4 || l_lo == 0) && !(xp & 2)) {  // a few layers per reduction launch, on the third branch
+      cudaStream_t rs = par && n->red ? n->red : ws;
+      if (rs != ws) {
+        cudaError_t e_ = cudaEventRecord(n->ev_wg[nred], ws);
+        if (e_ == cudaSuccess) e_ = cudaStreamWaitEvent(rs, n->ev_wg[nred], 0);
+        if (e_ != cudaSuccess) return cuda_fail(e_, "event record / wait");
+        ++nred;
+      }
+      wgrad_reduce_kernel<<<dim3(148, static_cast<unsigned>(pending)), 256, 0, rs>>>(n->at<WgradReduceDesc>(n->off.wred) + l_lo);
       cudaError_t e_ = cudaGetLastError();
       if (e_ != cudaSuccess) return cuda_fail(e_, "wgrad_reduce_kernel");
       ++launches;
@@ -1123,7 +1145,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   if ((e = wgrads(nl - 1, nl - 1))) return e;
   for (size_t ci = 0; ci < n->bchains.size(); ++ci) {
     const ChainPlan& c = n->bchains[ci];
-    if ((e = n->engine == ENGINE_LAYER ? launch_conv(n->dgrad[nl - 1 - c.first], st) : launch_chain(c, st))) return e;
+    if (!(xp & 4) && (e = n->engine == ENGINE_LAYER ? launch_conv(n->dgrad[nl - 1 - c.first], st) : launch_chain(c, st))) return e;
     ++launches;
     if (par) {
       WACIL_EV(cudaEventRecord(n->ev_chain[ci + 1], st), "event record");
@@ -1133,9 +1155,9 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     const int l_hi = nl - 1 - c.first - 1, l_lo = nl - 1 - (c.first + c.count - 1) - 1;
     if ((e = wgrads(l_hi, l_lo))) return e;
   }
-  if (par) {
-    WACIL_EV(cudaEventRecord(n->ev_join, ws), "event record");
-    WACIL_EV(cudaStreamWaitEvent(st, n->ev_join, 0), "event wait");  // join (the side stream is in order)
+  if (par) {  // join: the reductions are in order on their branch and each of them follows its weight gradients
+    WACIL_EV(cudaEventRecord(n->ev_join, n->red ? n->red : ws), "event record");
+    WACIL_EV(cudaStreamWaitEvent(st, n->ev_join, 0), "event wait");
   }
 #undef WACIL_EV
   n->launches = launches;

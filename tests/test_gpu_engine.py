@@ -383,3 +383,17 @@ def test_training_is_bit_reproducible(w):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     # the captured graph launches the same kernels with the same grids
     assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+
+
+def test_chain_engine_stays_under_parity():
+    """WACIL_ENGINE=chain (several layers per persistent conv_chain_kernel launch instead of one cooperative launch per
+    layer; the default is the per-layer engine, profiles/r02_chain_experiments.md) runs the layer-by-layer parity, the
+    golden two-step and the bit-reproducibility tests in a subprocess (the switch is read once per process)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, WACIL_ENGINE="chain")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", __file__, "-k",
+                        "(train_forward_backward and not 110 and not 56) or two_training_steps or infer_forward or "
+                        "bit_reproducible or full_batch_step"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
