@@ -508,16 +508,35 @@ __global__ void __launch_bounds__(256) allreduce_sgd_kernel(const AllreduceSgdPa
 }
 
 // ------------------------------------------------------------------------------------------------ weight align
-// Cooperative launch (all CTAs co-resident).  bar[0], bar[1]: grid barrier counters, left at zero.
-__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+// CilModel.weight_align (template.py:156-166): gamma = mean ||w_old row|| / mean ||w_new row||, new rows *= gamma.
+// One persistent cooperative launch, one 1024-thread CTA per SM:
+//   phase 1  a warp streams a row with 16-byte loads, eight in flight per lane (131 KB in flight per SM); the OLD rows
+//            are dealt round-robin over all warps with evict-first loads (read once), the NEW rows are dealt round-robin
+//            over the CTAs and parked in shared memory while their norm is taken (8.4 MB of [8192,2048] fp32 / 148 SMs =
+//            57 KB per CTA), so that phase 3 neither re-reads them from L2 nor from HBM;
+//   phase 2  per-CTA partial sums of the two groups of norms (fixed order inside the CTA) -> [grid][2] table -> grid
+//            barrier (release add + acquire poll) -> every CTA adds the table in CTA order: gamma is bit-identical
+//            everywhere and reproducible (the first version had every CTA re-read all C_total norms: 38 MB of L2 reads
+//            at [8192,2048] behind an atomicAdd-polling barrier — 33 % of the HBM roofline);
+//   phase 3  scale the parked rows, streaming stores.
+// Rows that do not fit the shared-memory budget (n_new / grid > cap) are re-read in phase 3.
+// bar[0], bar[1]: grid barrier counters, zero at rest.
+constexpr int kWaThreads = 1024;
+
+__device__ __forceinline__ void wa_grid_barrier(unsigned* bar) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (atomicAdd(bar, 0u) < gridDim.x) {
-    }
-    __threadfence();
-    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned seen;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (seen < gridDim.x && clock64() - t0 > 4000000000LL) {
+        printf("wacil: weight_align grid barrier timeout (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    } while (seen < gridDim.x);
+    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {  // last one out: every CTA has left the polling loop
       bar[1] = 0u;
       __threadfence();
       bar[0] = 0u;
@@ -533,80 +552,132 @@ template <typename T> __device__ __forceinline__ void wa_st(T* p, float v);
 template <> __device__ __forceinline__ void wa_st<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void wa_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-template <typename T>
-__global__ void __launch_bounds__(256) weight_align_kernel(T* __restrict__ W, int C_total, int D, int n_new,
-                                                           float* __restrict__ norms, unsigned* bar,
-                                                           float* __restrict__ gamma_out) {
-  __shared__ float s_red[2][8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * 8;
-  constexpr int VW = 16 / sizeof(T);  // elements per 16-byte vector
-  const bool vec = (D % VW) == 0;
-  // phase 1: row norms, one warp per row
-  for (int r = blockIdx.x * 8 + warp; r < C_total; r += warps_total) {
-    const T* row = W + static_cast<long long>(r) * D;
-    float ss = 0.f;
-    if (vec) {
-      for (int k0 = lane * VW; k0 < D; k0 += 4 * 32 * VW) {
-        uint4 q[4];
+template <typename T> __device__ __forceinline__ float wa_sumsq16(const uint4& q) {
+  constexpr int VW = 16 / sizeof(T);
+  const T* e = reinterpret_cast<const T*>(&q);
+  float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = k0 + j * 32 * VW;
-          q[j] = k < D ? __ldcs(reinterpret_cast<const uint4*>(row + k)) : make_uint4(0u, 0u, 0u, 0u);
-        }
+  for (int i = 0; i < VW; ++i) {
+    const float f = wa_ld<T>(e + i);
+    ss += f * f;
+  }
+  return ss;
+}
+
+// Sum of squares of one row by one warp.  PARK: also copy the row to `park` (shared memory).  VEC: 16-byte path.
+template <typename T, bool PARK, bool STREAM>
+__device__ __forceinline__ float wa_row_sumsq(const T* __restrict__ row, int D, int lane, bool vec, T* park) {
+  constexpr int VW = 16 / sizeof(T);
+  float ss = 0.f;
+  if (vec) {
+    const int nv = D / VW;  // 16-byte vectors in the row
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    for (int v0 = lane; v0 < nv; v0 += 32 * 8) {
+      uint4 q[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const T* e = reinterpret_cast<const T*>(&q[j]);
-#pragma unroll
-          for (int i = 0; i < VW; ++i) {
-            const float f = wa_ld<T>(e + i);
-            ss += f * f;
-          }
-        }
+      for (int j = 0; j < 8; ++j) {
+        const int v = v0 + 32 * j;
+        if (v < nv) q[j] = STREAM ? __ldcs(src + v) : __ldg(src + v);
+        else q[j] = make_uint4(0u, 0u, 0u, 0u);
       }
-    } else {
-      for (int k = lane; k < D; k += 32) {
-        const float f = wa_ld<T>(row + k);
-        ss += f * f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int v = v0 + 32 * j;
+        ss += wa_sumsq16<T>(q[j]);
+        if (PARK && v < nv) reinterpret_cast<uint4*>(park)[v] = q[j];
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) norms[r] = sqrtf(ss);
+  } else {
+    for (int k = lane; k < D; k += 32) {
+      const float f = wa_ld<T>(row + k);
+      ss += f * f;
+      if (PARK) park[k] = row[k];
+    }
   }
-  grid_barrier(bar);
-  // phase 2: every CTA forms gamma with the same fixed summation order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  return ss;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWaThreads, 1) weight_align_kernel(T* __restrict__ W, int C_total, int D, int n_new,
+                                                                    float* __restrict__ partial, unsigned* bar,
+                                                                    float* __restrict__ gamma_out, int park_rows) {
+  extern __shared__ __align__(16) uint8_t wa_smem[];
+  __shared__ float s_old[32], s_new[32], s_tot[2][32];
+  T* parked = reinterpret_cast<T*>(wa_smem);  // [park_rows][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  constexpr int VW = 16 / sizeof(T);
+  const bool vec = (D % VW) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
   const int C_old = C_total - n_new;
-  float so = 0.f, sn = 0.f;
-  for (int r = threadIdx.x; r < C_total; r += blockDim.x) {
-    const float v = __ldcg(norms + r);
-    if (r < C_old) so += v; else sn += v;
+  const size_t rowlen = static_cast<size_t>(D);
+  // ---- phase 1a: the NEW rows of this CTA (row C_old + b + k*G), parked in shared memory while they fit
+  float sn = 0.f;
+  {
+    int k = warp;
+    for (int i = static_cast<int>(blockIdx.x) + warp * G; i < n_new; i += 32 * G, k += 32) {
+      const T* row = W + (static_cast<size_t>(C_old) + i) * rowlen;
+      const float ss = k < park_rows ? wa_row_sumsq<T, true, false>(row, D, lane, vec, parked + static_cast<size_t>(k) * rowlen)
+                                     : wa_row_sumsq<T, false, false>(row, D, lane, vec, nullptr);
+      sn += sqrtf(ss);  // every lane holds the row total after the butterfly: lane 0's copy is used below
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    so += __shfl_xor_sync(0xffffffffu, so, o);
-    sn += __shfl_xor_sync(0xffffffffu, sn, o);
-  }
-  if (lane == 0) { s_red[0][warp] = so; s_red[1][warp] = sn; }
+  // ---- phase 1b: the OLD rows, round-robin over all warps of the grid, read once (evict-first)
+  float so = 0.f;
+  for (int r = static_cast<int>(blockIdx.x) * 32 + warp; r < C_old; r += G * 32)
+    so += sqrtf(wa_row_sumsq<T, false, true>(W + static_cast<size_t>(r) * rowlen, D, lane, vec, nullptr));
+  if (lane == 0) { s_old[warp] = so; s_new[warp] = sn; }
   __syncthreads();
-  so = 0.f; sn = 0.f;
+  if (threadIdx.x == 0) {  // fixed order inside the CTA
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 32; ++i) { a += s_old[i]; b += s_new[i]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = b;
+  }
+  wa_grid_barrier(bar);
+  // ---- phase 2: every CTA adds the [G][2] table in CTA order (warp 0: lanes take CTAs lane, lane + 32, ... then a
+  // fixed shuffle tree) -> the same gamma everywhere
+  if (warp == 0) {
+    float a = 0.f, b = 0.f;
+    for (int c0 = lane; c0 < G; c0 += 32 * 4) {
+      float2 t[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { so += s_red[0][i]; sn += s_red[1][i]; }
-  const float gamma = (so / static_cast<float>(C_old)) / (sn / static_cast<float>(n_new));
-  if (blockIdx.x == 0 && threadIdx.x == 0) *gamma_out = gamma;
-  // phase 3: scale the new rows (they are still L2 resident from phase 1)
-  for (int r = C_old + blockIdx.x * 8 + warp; r < C_total; r += warps_total) {
-    T* row = W + static_cast<long long>(r) * D;
-    if (vec) {
-      for (int k = lane * VW; k < D; k += 32 * VW) {
-        uint4 q = *reinterpret_cast<const uint4*>(row + k);
-        T* e = reinterpret_cast<T*>(&q);
-#pragma unroll
-        for (int i = 0; i < VW; ++i) wa_st<T>(e + i, gamma * wa_ld<T>(e + i));
-        *reinterpret_cast<uint4*>(row + k) = q;
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + 32 * j;
+        t[j] = c < G ? __ldcg(reinterpret_cast<const float2*>(partial) + c) : make_float2(0.f, 0.f);
       }
-    } else {
-      for (int k = lane; k < D; k += 32) wa_st<T>(row + k, gamma * wa_ld<T>(row + k));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a += t[j].x; b += t[j].y; }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { s_tot[0][0] = a; s_tot[1][0] = b; }
+  }
+  __syncthreads();
+  const float gamma = (s_tot[0][0] / static_cast<float>(C_old)) / (s_tot[1][0] / static_cast<float>(n_new));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *gamma_out = gamma;
+  // ---- phase 3: scale this CTA's new rows (from shared memory where parked), streaming stores
+  {
+    int k = warp;
+    for (int i = static_cast<int>(blockIdx.x) + warp * G; i < n_new; i += 32 * G, k += 32) {
+      T* row = W + (static_cast<size_t>(C_old) + i) * rowlen;
+      const T* src = k < park_rows ? parked + static_cast<size_t>(k) * rowlen : row;
+      if (vec) {
+        const int nv = D / VW;
+        for (int v = lane; v < nv; v += 32) {
+          uint4 q = reinterpret_cast<const uint4*>(src)[v];
+          T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+          for (int j = 0; j < VW; ++j) wa_st<T>(e + j, gamma * wa_ld<T>(e + j));
+          __stcs(reinterpret_cast<uint4*>(row) + v, q);
+        }
+      } else {
+        for (int j = lane; j < D; j += 32) wa_st<T>(row + j, gamma * wa_ld<T>(src + j));
+      }
     }
   }
 }

@@ -1307,26 +1307,35 @@ int wacil_ce_kd_fwd_bwd_w(const float* logits, int64_t l_ld, const int64_t* targ
   return 0;
 }
 
-size_t wacil_weight_align_workspace_bytes(int C_total) { return 64 + static_cast<size_t>(C_total > 0 ? C_total : 0) * 4; }
+size_t wacil_weight_align_workspace_bytes(int C_total) {
+  return 64 + (static_cast<size_t>(C_total > 0 ? C_total : 0) + 2 * 1024) * 4;  // barrier counters + [CTAs][2] partial sums
+}
 
 extern "C++" {
 namespace {
 template <typename T>
 int wa_launch(void* W, int C_total, int D, int n_new, float* gamma_out, void* ws, cudaStream_t st) {
-  static int occ = 0;  // per instantiation
+  static bool attr_set = false;
+  constexpr size_t kParkMax = 200 * 1024;  // shared memory for the parked new rows
   cudaError_t e = cudaSuccess;
-  if (occ == 0) {
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weight_align_kernel<T>, 256, 0);
-    if (e != cudaSuccess || occ < 1) { occ = 0; return cuda_fail(e, "occupancy(weight_align_kernel)"); }
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(weight_align_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kParkMax));
+    if (e != cudaSuccess) return cuda_fail(e, "weight_align_kernel smem attribute");
+    attr_set = true;
   }
-  int grid = (C_total + 7) / 8;
-  const int cap = occ * num_sms();
-  if (grid > cap) grid = cap;
+  int grid = (C_total + 31) / 32;  // a warp per row: no more CTAs than 32-row groups
+  if (grid > num_sms()) grid = num_sms();
+  if (grid > 1024) grid = 1024;
+  const size_t rowbytes = static_cast<size_t>(D) * sizeof(T);
+  int park_rows = (n_new + grid - 1) / grid;
+  if (static_cast<size_t>(park_rows) * rowbytes > kParkMax) park_rows = static_cast<int>(kParkMax / rowbytes);
+  if ((rowbytes & 15) != 0) park_rows = 0;  // rows must stay 16-byte aligned in shared memory
+  const size_t smem = static_cast<size_t>(park_rows) * rowbytes;
   T* Wp = static_cast<T*>(W);
   unsigned* bar = static_cast<unsigned*>(ws);
-  float* norms = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
-  void* args[] = {&Wp, &C_total, &D, &n_new, &norms, &bar, &gamma_out};
-  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(weight_align_kernel<T>), dim3(grid), dim3(256), args, 0, st);
+  float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
+  void* args[] = {&Wp, &C_total, &D, &n_new, &partial, &bar, &gamma_out, &park_rows};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(weight_align_kernel<T>), dim3(grid), dim3(kWaThreads), args, smem, st);
   if (e != cudaSuccess) return cuda_fail(e, "weight_align_kernel");
   return 0;
 }
