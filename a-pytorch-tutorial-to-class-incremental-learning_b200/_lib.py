@@ -65,6 +65,7 @@ SIGNATURES = {
     "wacil_conv3x3_bn_relu": (I, [P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, I, P, P]),
     "wacil_conv3x3_wgrad_workspace_bytes": (Z, [I, I, I, I, I]),
     "wacil_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P, P]),
+    "wacil_net_set_optimizer": (I, [P, P, P, F, F, I, I, P, P, P]),
     "wacil_net_chain_count": (I, [P, I]),
     "wacil_net_chain_info": (I, [P, I, I, C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(I), C.POINTER(Z)]),
     "wacil_net_run_chain": (I, [P, I, I, P, P]),

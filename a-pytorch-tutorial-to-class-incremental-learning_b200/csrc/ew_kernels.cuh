@@ -430,7 +430,9 @@ struct AllreduceSgdParams {
   int world, rank;
   float* p;
   float* v;
-  long long n;
+  long long n;            // elements of segment 0 (starting at seg_off[0])
+  long long seg_off[2];   // up to two segments of the arenas per launch (the optimiser runs in two instalments: the
+  long long seg_n1;       // gradients that are complete early go first, while the backward is still running)
   const float* lr_dev;
   float mom, wd;
   unsigned* epoch;       // [0] epoch, [1] blocks-done counter (local device memory, zero initially)
@@ -470,23 +472,26 @@ __global__ void __launch_bounds__(256) allreduce_sgd_kernel(const AllreduceSgdPa
   __syncthreads();
   const float lr = __ldg(q.lr_dev);
   const float gscale = 1.f / static_cast<float>(q.world);
-  const long long n4 = q.n / 4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int seg = 0; seg < 2; ++seg) {
+    const long long n4 = (seg == 0 ? q.n : q.seg_n1) / 4, o4 = q.seg_off[seg] / 4;
+    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < n4;
+         j += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long i = o4 + j;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-    for (int r = 0; r < q.world; ++r) {
-      const float4 t = __ldcv(reinterpret_cast<const float4*>(q.grads[r]) + i);  // peer read, never from a stale L1 line
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      for (int r = 0; r < q.world; ++r) {
+        const float4 t = __ldcv(reinterpret_cast<const float4*>(q.grads[r]) + i);  // peer read, never from a stale L1 line
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      float4 pp = reinterpret_cast<float4*>(q.p)[i];
+      float4 vv = reinterpret_cast<float4*>(q.v)[i];
+      vv.x = q.mom * vv.x + (g.x * gscale + q.wd * pp.x); pp.x -= lr * vv.x;
+      vv.y = q.mom * vv.y + (g.y * gscale + q.wd * pp.y); pp.y -= lr * vv.y;
+      vv.z = q.mom * vv.z + (g.z * gscale + q.wd * pp.z); pp.z -= lr * vv.z;
+      vv.w = q.mom * vv.w + (g.w * gscale + q.wd * pp.w); pp.w -= lr * vv.w;
+      reinterpret_cast<float4*>(q.p)[i] = pp;
+      reinterpret_cast<float4*>(q.v)[i] = vv;
     }
-    float4 pp = reinterpret_cast<float4*>(q.p)[i];
-    float4 vv = reinterpret_cast<float4*>(q.v)[i];
-    vv.x = q.mom * vv.x + (g.x * gscale + q.wd * pp.x); pp.x -= lr * vv.x;
-    vv.y = q.mom * vv.y + (g.y * gscale + q.wd * pp.y); pp.y -= lr * vv.y;
-    vv.z = q.mom * vv.z + (g.z * gscale + q.wd * pp.z); pp.z -= lr * vv.z;
-    vv.w = q.mom * vv.w + (g.w * gscale + q.wd * pp.w); pp.w -= lr * vv.w;
-    reinterpret_cast<float4*>(q.p)[i] = pp;
-    reinterpret_cast<float4*>(q.v)[i] = vv;
   }
   // n is a multiple of 4 by construction of the arena layout (wacil_net_layout)
   __syncthreads();
@@ -577,7 +582,7 @@ __device__ __forceinline__ float wa_row_sumsq(const T* __restrict__ row, int D, 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int v = v0 + 32 * j;
-        if (v < nv) q[j] = STREAM ? __ldcs(src + v) : __ldg(src + v);
+        if (v < nv) q[j] = __ldcs(src + v);  // every row is read exactly once
         else q[j] = make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
@@ -612,6 +617,10 @@ __global__ void __launch_bounds__(kWaThreads, 1) weight_align_kernel(T* __restri
   const bool vec = (D % VW) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
   const int C_old = C_total - n_new;
   const size_t rowlen = static_cast<size_t>(D);
+  // programmatic dependent launch: everything above ran under the previous kernel's tail; its writes (W may have been
+  // produced by it) are visible from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- phase 1a: the NEW rows of this CTA (row C_old + b + k*G), parked in shared memory while they fit
   float sn = 0.f;
   {

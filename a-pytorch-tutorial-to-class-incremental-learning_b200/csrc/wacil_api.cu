@@ -532,6 +532,17 @@ struct wacil_net {
   cudaStream_t side = nullptr;            // optional second stream: weight gradients run beside the data-gradient chain
   std::vector<cudaEvent_t> ev_chain;      // backward chain i finished (main stream)
   cudaEvent_t ev_join = nullptr;          // all weight gradients reduced
+  // optional fused optimiser (wacil_net_set_optimizer): backward applies gradient mean + SGD itself, in two instalments
+  struct {
+    bool on = false;
+    float* v = nullptr;
+    const float* lr_dev = nullptr;
+    float mom = 0.f, wd = 0.f;
+    int world = 1, rank = 0;
+    const float* grads[kMaxRanks] = {};
+    unsigned* pads[kMaxRanks] = {};
+    unsigned* epoch = nullptr;
+  } opt;
   cudaStream_t red = nullptr;             // third branch (owned by the plan): the ordered reductions of the weight-gradient slots,
   std::vector<cudaEvent_t> ev_wg;         // so that a reduction never sits between two weight-gradient launches of the side stream
   const float* last_feats = nullptr;
@@ -931,6 +942,32 @@ int wacil_net_set_side_stream(wacil_net_t* n, void* side_stream) {
 
 int wacil_net_last_launches(const wacil_net_t* net) { return net ? net->launches : 0; }
 
+int wacil_net_set_optimizer(wacil_net_t* n, float* momentum_buf, const float* lr_dev, float momentum, float weight_decay,
+                            int world, int rank, const void* const* grad_ptrs, void* const* pad_ptrs, void* epoch_ws) {
+  if (!n) return fail(WACIL_E_NULL, "net is NULL");
+  if (n->mode != WACIL_NET_TRAIN) return fail(WACIL_E_STATE, "the optimiser belongs to a TRAIN plan");
+  if (momentum_buf == nullptr) {  // detach
+    n->opt.on = false;
+    return 0;
+  }
+  if (!lr_dev) return fail(WACIL_E_NULL, "lr_dev is NULL");
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(WACIL_E_SHAPE, "world=%d rank=%d", world, rank);
+  if (reinterpret_cast<uintptr_t>(momentum_buf) & 15) return fail(WACIL_E_ALIGN, "momentum arena must be 16-byte aligned");
+  if (world > 1) {
+    if (!grad_ptrs || !pad_ptrs || !epoch_ws) return fail(WACIL_E_NULL, "peer pointers / epoch workspace missing");
+    for (int r = 0; r < world; ++r) {
+      if (!grad_ptrs[r] || !pad_ptrs[r]) return fail(WACIL_E_NULL, "peer pointer %d is NULL", r);
+      n->opt.grads[r] = static_cast<const float*>(grad_ptrs[r]);
+      n->opt.pads[r] = static_cast<unsigned*>(pad_ptrs[r]);
+    }
+    if (n->opt.grads[rank] != n->grads) return fail(WACIL_E_STATE, "grad_ptrs[rank] is not this plan's gradient arena");
+  }
+  n->opt.v = momentum_buf; n->opt.lr_dev = lr_dev; n->opt.mom = momentum; n->opt.wd = weight_decay;
+  n->opt.world = world; n->opt.rank = rank; n->opt.epoch = static_cast<unsigned*>(epoch_ws);
+  n->opt.on = true;
+  return 0;
+}
+
 int wacil_net_chain_count(const wacil_net_t* n, int backward) {
   if (!n) return 0;
   return static_cast<int>(backward ? n->bchains.size() : n->fchains.size());
@@ -1138,6 +1175,43 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     }
     return 0;
   };
+  // Fused optimiser: gradient mean over the ranks (NVLink peer reads in rank order) + SGD, in two instalments.  The first
+  // covers the convolution weights whose gradients are complete once the 8x8 layers are done (80 % of the arena for
+  // ResNet-32) and runs on the reduction branch beside the rest of the backward — nothing later in the backward reads
+  // the fp32 master weights (the kernels use the bf16 operand copies); the second covers the rest, after the join.
+  const long long conv_end = n->L[0].gamma_off;  // end of the convolution weights in the arena
+  long long early_from = conv_end;               // set when the first instalment has been launched
+  auto optimise = [&](long long off0, long long n0, long long off1, long long n1, cudaStream_t os) -> int {
+    if (n0 <= 0 && n1 <= 0) return 0;
+    if (n0 <= 0) { off0 = off1; n0 = n1; n1 = 0; }
+    if (n->opt.world == 1) {
+      for (int sgm = 0; sgm < 2; ++sgm) {
+        const long long o = sgm ? off1 : off0, len = sgm ? n1 : n0;
+        if (len <= 0) continue;
+        sgd_step_kernel<<<ew_grid(len / 4 + 1), 256, 0, os>>>(n->params + o, n->grads + o, n->opt.v + o, len, n->opt.lr_dev,
+                                                             n->opt.mom, n->opt.wd, 1.f);
+        cudaError_t e_ = cudaGetLastError();
+        if (e_ != cudaSuccess) return cuda_fail(e_, "sgd_step_kernel");
+        ++launches;
+      }
+      return 0;
+    }
+    AllreduceSgdParams q{};
+    for (int r = 0; r < n->opt.world; ++r) { q.grads[r] = n->opt.grads[r]; q.pads[r] = n->opt.pads[r]; }
+    q.world = n->opt.world; q.rank = n->opt.rank; q.p = n->params; q.v = n->opt.v; q.lr_dev = n->opt.lr_dev;
+    q.mom = n->opt.mom; q.wd = n->opt.wd; q.epoch = n->opt.epoch;
+    q.seg_off[0] = off0; q.n = n0; q.seg_off[1] = off1; q.seg_n1 = n1;
+    int grid = ew_grid((n0 + n1) / 4);
+    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    allreduce_sgd_kernel<<<grid, 256, 0, os>>>(q);
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return cuda_fail(e_, "allreduce_sgd_kernel");
+    ++launches;
+    return 0;
+  };
+  int split_layer = nl;  // first layer of the last resolution group (its weights and everything after: first instalment)
+  for (int l = nl - 1; l >= 1; --l)
+    if (n->L[l].cout == n->L[nl - 1].cout) split_layer = l;
   if (par) {
     WACIL_EV(cudaEventRecord(n->ev_chain[0], st), "event record");
     WACIL_EV(cudaStreamWaitEvent(ws, n->ev_chain[0], 0), "event wait");
@@ -1154,12 +1228,20 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     // elements first .. first+count-1 are layers l = nl-1-first .. ; they produced GY_{l-1}
     const int l_hi = nl - 1 - c.first - 1, l_lo = nl - 1 - (c.first + c.count - 1) - 1;
     if ((e = wgrads(l_hi, l_lo))) return e;
+    if (n->opt.on && early_from == conv_end && pending == 0 && l_lo <= split_layer && l_lo > 0) {
+      // every layer >= l_lo has its reduced gradient: first instalment on the reduction branch, right behind that reduction
+      early_from = n->L[l_lo].w_off;
+      if ((e = optimise(early_from, conv_end - early_from, 0, 0, par && n->red ? n->red : ws))) return e;
+    }
   }
   if (par) {  // join: the reductions are in order on their branch and each of them follows its weight gradients
     WACIL_EV(cudaEventRecord(n->ev_join, n->red ? n->red : ws), "event record");
     WACIL_EV(cudaStreamWaitEvent(st, n->ev_join, 0), "event wait");
   }
 #undef WACIL_EV
+  if (n->opt.on) {  // second instalment: the remaining convolution weights, BatchNorm parameters and the classifier
+    if ((e = optimise(0, early_from, conv_end, n->lay.param_elems - conv_end, st))) return e;
+  }
   n->launches = launches;
   return 0;
 }
@@ -1334,8 +1416,19 @@ int wa_launch(void* W, int C_total, int D, int n_new, float* gamma_out, void* ws
   T* Wp = static_cast<T*>(W);
   unsigned* bar = static_cast<unsigned*>(ws);
   float* partial = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 64);
-  void* args[] = {&Wp, &C_total, &D, &n_new, &partial, &bar, &gamma_out, &park_rows};
-  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(weight_align_kernel<T>), dim3(grid), dim3(kWaThreads), args, smem, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;  // grid barrier between the norms and the scaling: all CTAs co-resident
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue under the tail of the previous kernel
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  e = cudaLaunchKernelEx(&cfg, weight_align_kernel<T>, Wp, C_total, D, n_new, partial, bar, gamma_out, park_rows);
   if (e != cudaSuccess) return cuda_fail(e, "weight_align_kernel");
   return 0;
 }
@@ -1377,6 +1470,7 @@ int wacil_allreduce_sgd(float* p, float* v, const void* const* grad_ptrs, void* 
     q.pads[r] = static_cast<unsigned*>(pad_ptrs[r]);
   }
   q.world = world; q.rank = rank; q.p = p; q.v = v; q.n = n; q.lr_dev = lr_dev; q.mom = momentum; q.wd = weight_decay;
+  q.seg_off[0] = 0; q.seg_off[1] = 0; q.seg_n1 = 0;
   q.epoch = static_cast<unsigned*>(epoch_ws);
   int grid = ew_grid(n / 4);
   if (grid > num_sms() * 4) grid = num_sms() * 4;

@@ -146,6 +146,16 @@ class Plan:
         check(lib().wacil_net_set_side_stream(self.handle, stream.cuda_stream if stream is not None else None),
               "wacil_net_set_side_stream")
 
+    def set_optimizer(self, mom, lr_dev, momentum, weight_decay, world=1, rank=0, grad_ptrs=None, pad_ptrs=None, epoch=None):
+        """Fuse gradient mean (NVLink peer reads, world > 1) + SGD into backward(): the convolution weights of the last
+        resolution group are updated while the rest of the backward still runs, everything else right after it
+        (template.py:243-244,269-271).  mom=None detaches the optimiser."""
+        self._opt_keep = (mom, lr_dev, grad_ptrs, pad_ptrs, epoch)
+        check(lib().wacil_net_set_optimizer(self.handle, mom.data_ptr() if mom is not None else None,
+                                            lr_dev.data_ptr() if lr_dev is not None else None, float(momentum),
+                                            float(weight_decay), int(world), int(rank), grad_ptrs, pad_ptrs,
+                                            epoch.data_ptr() if epoch is not None else None), "wacil_net_set_optimizer")
+
     def tensor(self, what, layer=0):
         """A view of a tensor the TRAIN plan keeps after a forward (parity tests): 0 packed input, 1 conv output,
         2 activation (all bf16 NHWC), 3 BatchNorm batch mean / rstd (fp32 [2, C])."""

@@ -290,6 +290,7 @@ class CilModel(nn.Module):
         new.register_buffer("bn_running", new._arena.bn)
         new.backbone = _Backbone(new)
         new._plans, new._param_version, new._num_batches_tracked = {}, 0, self._num_batches_tracked
+        new._frozen = set(getattr(self, "_frozen", set()))
         new.fc = None
         if self.fc is not None:
             fc = CilClassifier.__new__(CilClassifier)
@@ -304,18 +305,36 @@ class CilModel(nn.Module):
         return self.copy()
 
     def freeze(self, names=["all"]):
-        """template.py:128-144."""
+        """template.py:128-144.  The model is one flat parameter, so partial freezing is kept as a trainable element range
+        of the arena that the optimiser honours (TaskTrainer): "fc" pins the classifier rows, "backbone" the convolution
+        and BatchNorm parameters.  The reference also switches the frozen part to eval(): a frozen backbone then
+        normalises with its running statistics — that forward is the inference plan; training through it is not offered
+        (the script only ever freezes "all", template.py:290)."""
         freeze_parameters(self, requires_grad=True)
         self.train()
+        self._frozen = set()
         for name in names:
             if name in ("fc", "backbone"):
-                raise NotImplementedError("partial freezing is not supported: the model is one flat parameter")
+                self._frozen.add(name)
             elif name == "all":
+                self._frozen = {"fc", "backbone"}
                 freeze_parameters(self)
                 self.eval()
             else:
                 raise NotImplementedError(f"Unknown module name to freeze {name}")
         return self
+
+    def trainable_range(self):
+        """[lo, hi) element range of the flat arena the optimiser may update (see freeze)."""
+        fz = getattr(self, "_frozen", set())
+        n, cut = self._arena.params.numel(), self._arena.layout.fc_weight_off
+        if "fc" in fz and "backbone" in fz:
+            return (0, 0)
+        if "fc" in fz:
+            return (0, cut)
+        if "backbone" in fz:
+            return (cut, n)
+        return (0, n)
 
     def prev_model_adaption(self, nb_classes):
         """template.py:146-150."""

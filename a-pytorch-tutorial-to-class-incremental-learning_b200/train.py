@@ -176,6 +176,13 @@ class _StepState:
         self.plan_s = tr.model._plan(_lib.NET_TRAIN, batch)
         if tr.overlap:
             self.plan_s.set_side_stream(tr.side_w)
+        if tr.fused_opt:  # gradient mean + SGD inside backward(), in two instalments (see Plan.set_optimizer)
+            pr = tr.peer
+            self.plan_s.set_optimizer(tr.mom, tr.lr_dev, tr.momentum, tr.weight_decay, tr.world_size,
+                                      pr["rank"] if pr else 0, pr["grad_ptrs"] if pr else None,
+                                      pr["pad_ptrs"] if pr else None, pr["epoch"] if pr else None)
+        else:
+            self.plan_s.set_optimizer(None, None, 0.0, 0.0)
         self.plan_t = None
         if tr.teacher is not None:
             self.plan_t = tr.teacher._plan(_lib.NET_INFER, batch)
@@ -211,6 +218,11 @@ class TaskTrainer:
         if world_size > 1 and fused_allreduce:
             self.peer = self._setup_peer_memory(process_group)
         self.mom = torch.zeros_like(model._arena.params)
+        # The optimiser is fused into the backward (C side) when the whole arena trains and the exchange is either local
+        # or over NVLink peer memory; the NCCL fallback and partially frozen models (template.py:128-144) use _opt().
+        self.train_range = model.trainable_range()
+        whole = self.train_range == (0, model._arena.params.numel())
+        self.fused_opt = whole and (world_size == 1 or self.peer is not None)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
         self.acc = torch.zeros(4, dtype=torch.float32, device=self.device)  # running sums of [ce, kd, loss, top1]
         self.steps_done = 0
@@ -282,6 +294,14 @@ class TaskTrainer:
 
     def _opt(self):
         a = self.model._arena
+        if self.fused_opt:
+            return 0  # applied inside plan_s.backward()
+        lo, hi = self.train_range
+        if (lo, hi) != (0, a.params.numel()):  # freeze(["fc"]) / freeze(["backbone"]): only the trainable range moves
+            if hi > lo:
+                ops.sgd_step_(a.params[lo:hi], a.grads[lo:hi], self.mom[lo:hi], self.lr_dev, self.momentum,
+                              self.weight_decay, 1.0 / self.world_size)
+            return 1
         if self.peer is not None:  # gradient mean over NVLink peer memory + SGD in one kernel
             ops.allreduce_sgd_(a.params, self.mom, self.peer["grad_ptrs"], self.peer["pad_ptrs"], self.world_size,
                                self.peer["rank"], self.lr_dev, self.peer["epoch"], self.momentum, self.weight_decay)
@@ -291,7 +311,7 @@ class TaskTrainer:
         return 1
 
     def _run(self, st):
-        single = self.world_size == 1 or self.peer is not None  # one graph holds the whole step
+        single = self.world_size == 1 or self.fused_opt  # one graph holds the whole step
         if not self.use_graph or st.warm < 2:
             n = self._fwd_bwd(st)
             if not single:

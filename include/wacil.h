@@ -90,7 +90,8 @@ int wacil_eval_rows(const float* logits, int64_t l_ld, const int64_t* targets, i
  *   W[C_total-n_new:, :] *= gamma     (in place; bias untouched)
  * W: [C_total][D] row-major contiguous (the classifier arena; heads are row ranges).  gamma_out: one float on the
  * device (the reference prints it, template.py:165; the host decides whether to read it back).
- * workspace: wacil_weight_align_workspace_bytes(C_total) bytes. */
+ * workspace: wacil_weight_align_workspace_bytes(C_total) bytes whose first 64 bytes are zero (grid barrier counters,
+ * left zero). */
 size_t wacil_weight_align_workspace_bytes(int C_total);
 int wacil_weight_align(void* W, int C_total, int D, int n_new, float* gamma_out, int dtype, void* workspace,
                        void* stream);
@@ -203,6 +204,19 @@ int wacil_net_forward(wacil_net_t* net, const float* x, int C_seen, float* feats
 /* Backward of the last TRAIN forward: dlogits fp32 [batch][C_seen] -> grads arena (overwritten, not
  * accumulated: the arena is zeroed inside).  feats/logits of that forward must still be intact. */
 int wacil_net_backward(wacil_net_t* net, const float* dlogits, int C_seen, void* stream);
+
+/* Optional fused optimiser.  Once set, wacil_net_backward also applies the DDP gradient mean (template.py:243-244,270)
+ * and the SGD update (template.py:246-247,271) of wacil_allreduce_sgd / wacil_sgd_step itself, in two instalments: the
+ * convolution weights of the last resolution group (80 % of the arena for ResNet-32; complete after a third of the
+ * backward) on the plan's reduction branch while the rest of the backward still runs, everything else after the join —
+ * the exchange no longer sits behind the last gradient kernel.  Nothing later in the backward reads the fp32 master
+ * weights (the kernels use the bf16 operand copies written by the forward).  momentum_buf: fp32 arena like params
+ * (NULL detaches the optimiser); lr_dev: device float; world / rank / grad_ptrs / pad_ptrs / epoch_ws as in
+ * wacil_allreduce_sgd (world = 1: no exchange, the pointers may be NULL).  All ranks must call backward the same
+ * number of times. */
+int wacil_net_set_optimizer(wacil_net_t* net, float* momentum_buf, const float* lr_dev, float momentum,
+                            float weight_decay, int world, int rank, const void* const* grad_ptrs,
+                            void* const* pad_ptrs, void* epoch_ws);
 
 /* Optional second stream for wacil_net_backward: weight-gradient kernels are issued on it and ordered against the
  * data-gradient chain with events (captured as parallel graph branches).  NULL restores single-stream order. */

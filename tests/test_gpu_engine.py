@@ -385,6 +385,31 @@ def test_training_is_bit_reproducible(w):
     assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
 
 
+@pytest.mark.parametrize("names", [["fc"], ["backbone"]])
+def test_partial_freeze_pins_its_range(w, names):
+    """CilModel.freeze(["fc"]) / freeze(["backbone"]) (template.py:128-144): the optimiser leaves the frozen element range
+    of the flat arena bit-identical and moves the rest."""
+    depth, heads = 20, [10, 10]
+    sd = _mild_state(depth, heads, 41)
+    m = _model_from(w, depth, sd)
+    m.freeze(names)
+    assert m.training and m.arena.requires_grad
+    cut = m._arena.layout.fc_weight_off
+    before = m.arena.detach().clone()
+    tr = w.TaskTrainer(m, None, 0, lr=0.05, use_graph=False)
+    assert not tr.fused_opt
+    gen = torch.Generator().manual_seed(8)
+    for _ in range(3):
+        tr.step(torch.randn(16, 3, 32, 32, generator=gen).cuda(), torch.randint(0, 20, (16,), generator=gen).cuda())
+    after = m.arena.detach()
+    frozen = slice(cut, None) if names == ["fc"] else slice(0, cut)
+    moving = slice(0, cut) if names == ["fc"] else slice(cut, cut + 20 * 64)
+    assert torch.equal(after[frozen], before[frozen])
+    assert not torch.equal(after[moving], before[moving])
+    assert m.copy().trainable_range() == m.trainable_range()
+    assert m.freeze(["all"]).trainable_range() == (0, 0) and not m.training
+
+
 def test_chain_engine_stays_under_parity():
     """WACIL_ENGINE=chain (several layers per persistent conv_chain_kernel launch instead of one cooperative launch per
     layer; the default is the per-layer engine, profiles/r02_chain_experiments.md) runs the layer-by-layer parity, the
