@@ -28,6 +28,11 @@ def main(args, log=print):
     init_seed(args)
     rank = getattr(args, "rank", 0)
     say = log if rank == 0 else (lambda *a, **k: None)
+    if rank == 0 and (str(getattr(args, "aa", "none")).lower() not in ("none", "") or getattr(args, "reprob", 0.0) > 0):
+        # utils.py:217-226: the reference's default train transform also applies timm RandAugment (--aa), colour jitter and
+        # random erasing on the host (PIL); the device data path covers RandomCrop(32, 4) + flip + ToTensor + Normalize
+        log("note: --aa / --color_jitter / --reprob are accepted for command-line compatibility but NOT applied: the device "
+            "data path runs RandomCrop(32, padding=4) + RandomHorizontalFlip + Normalize only (pass --aa none to silence)")
     args.class_order = CIFAR100_CLASS_ORDER                                   # template.py:201-202
     dev = torch.device("cuda", getattr(args, "gpu", 0))
     scenario_train, args.nb_classes = build_dataset(True, args, device=dev)   # template.py:203

@@ -82,15 +82,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_states():
+def make_states(heads=None):
     import wa_oracle as wo
-    return wo.make_state(DEPTH, HEADS, 0, perturb_bn=False), wo.make_state(DEPTH, HEADS[:1], 1, perturb_bn=False)
+    heads = HEADS if heads is None else heads
+    return wo.make_state(DEPTH, heads, 0, perturb_bn=False), wo.make_state(DEPTH, heads[:-1], 1, perturb_bn=False)
 
 
-def synthetic_pool(n_batches, seed):
+def synthetic_pool(n_batches, seed, n_classes=None):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(n_batches, BATCH, 3, 32, 32, generator=g)
-    y = torch.randint(0, sum(HEADS), (n_batches, BATCH), generator=g)
+    y = torch.randint(0, n_classes or sum(HEADS), (n_batches, BATCH), generator=g)
     return x, y
 
 
@@ -130,6 +131,66 @@ def cpu_steps(n_steps, warmup, budget_s=None):
     return done * BATCH / dt, done, threads, dt
 
 
+def _gloo_worker(rank, k, port, threads, n_steps, q):
+    """One gloo rank of the reference's DDP step on the CPU (template.py:258-272: forward, losses, backward, gradient
+    all-reduce, SGD, per-step barrier), through the oracle port."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(k))
+    import wa_oracle as wo
+    torch.set_num_threads(threads)
+    dist.init_process_group("gloo", rank=rank, world_size=k)
+    sd, tsd = make_states()
+    x, y = synthetic_pool(2, 1234 + rank)
+    names = wo.trainable_names(sd)
+    bufs = {}
+
+    def step(i):
+        r = wo.train_step(sd, tsd, x[i % 2], y[i % 2], DEPTH, KNOWN, 0.1, bufs, apply_update=False)
+        flat = torch.cat([r["grads"][n].reshape(-1) for n in names])
+        dist.all_reduce(flat)  # DDP's gradient mean (template.py:243-244)
+        flat /= k
+        o = 0
+        grads = {}
+        for n in names:
+            m = r["grads"][n].numel()
+            grads[n] = flat[o: o + m].view_as(r["grads"][n])
+            o += m
+        wo.sgd_step({n: sd[n] for n in names}, grads, bufs, 0.1, 0.9, 5e-4)
+        dist.barrier()  # template.py:272
+
+    step(0)
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        q.put(dt)
+    dist.destroy_process_group()
+
+
+def cpu_gloo_baseline(ks=(1, 2, 4), n_steps=5):
+    """BASELINE.md B1 / SURVEY 8(d): the reference step under torch.distributed gloo with k CPU ranks on this box's cores."""
+    import torch.multiprocessing as mp
+    cores = os.cpu_count() or 1
+    out = {"os_cpu_count": cores, "steps": n_steps, "runs": []}
+    ctx = mp.get_context("spawn")
+    for k in ks:
+        threads = max(1, min(16, cores // k))
+        q = ctx.Queue()
+        port = 29800 + (os.getpid() % 500) + k
+        procs = [ctx.Process(target=_gloo_worker, args=(r, k, port, threads, n_steps, q)) for r in range(k)]
+        for p_ in procs:
+            p_.start()
+        try:
+            dt = q.get(timeout=300)
+            out["runs"].append({"ranks": k, "threads_per_rank": threads, "img_s": k * n_steps * BATCH / dt,
+                                "ms_per_step": 1e3 * dt / n_steps})
+        except Exception as ex:  # a baseline must never take the bench line down
+            out["runs"].append({"ranks": k, "error": str(ex)[:120]})
+        for p_ in procs:
+            p_.join(timeout=30)
+    return out
+
+
 def gpu_eager_steps(n_steps, autocast):
     """the reference's step sequence as PyTorch eager on this GPU (cuDNN/cuBLAS/ATen), through the oracle
     port of template.py:255-271 with CUDA tensors — the incumbent GPU path next to which the native kernels are read.
@@ -163,7 +224,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "images/sec per CIL training step", "value": ips, "unit": "img/s",
             "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH, "note": "CPU arm runs one rank's batch"},
+            "config": {"workload": WORKLOAD, "global_batch": BATCH,
+                       "note": "the CPU arm is ONE process on rank 0 stepping one rank's 128-image batch whatever N is: at "
+                               "N > 1 the driver's ratio compares N GPUs with one CPU process (the gloo k-rank CPU runs are in the "
+                               "N = 1 line of the GPU arm: cpu_gloo)"},
             "cpu_baseline": {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",
                              "sample": f"{done} steps of one 128-image batch, oracle/wa_oracle.train_step"},
             "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -257,7 +321,121 @@ def kernel_rooflines(w, pk):
     out["kd"] = {"kernel": "kd_stream_kernel fp32 B=1024 C=8192 T=2 (TMA-streamed, 60 back-to-back launches over 6 "
                            "rotating buffer sets, PDL)", "us": us, "gbs": bytes_alg / us / 1e3,
                  "frac": bytes_alg / us / 1e3 / pk["hbm_gbs"], "bytes": bytes_alg}
+    del ss, ts, gs
+    # weight-align kernel (north star): [8192, 2048] fp32, 1024 new rows: reads every row once, writes the new rows
+    Cw, Dw, nn = 8192, 2048, 1024
+    nbw = 5  # 5 x 67 MB > L2
+    Ws = [torch.randn(Cw, Dw, device=dev) * 0.1 for _ in range(nbw)]
+    gam_out = torch.empty((), device=dev)
+    wws = torch.zeros(lib.wacil_weight_align_workspace_bytes(Cw), dtype=torch.uint8, device=dev)
+    for i in range(3):
+        lib.wacil_weight_align(Ws[i].data_ptr(), Cw, Dw, nn, gam_out.data_ptr(), 0, wws.data_ptr(), st)
+    torch.cuda.synchronize()
+    reps = 40
+    e0.record()
+    for i in range(reps):
+        lib.wacil_weight_align(Ws[i % nbw].data_ptr(), Cw, Dw, nn, gam_out.data_ptr(), 0, wws.data_ptr(), st)
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / reps
+    bytes_alg = (Cw + nn) * Dw * 4
+    out["wa"] = {"kernel": "weight_align_kernel fp32 [8192,2048] n_new=1024 (persistent, new rows parked in shared memory, "
+                           "40 launches over 5 rotating matrices)", "us": us, "gbs": bytes_alg / us / 1e3,
+                 "frac": bytes_alg / us / 1e3 / pk["hbm_gbs"], "bytes": bytes_alg}
     return out
+
+
+def ncu_traffic(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first matching kernel in a committed `ncu --page raw --csv`
+    export under profiles/ (the capture is taken with the same entry point, see profiles/README.md); None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    if len(rows) < 3:
+        return None
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        if kernel_substr in r[ix["Kernel Name"]]:
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[ix[key]]) * mult.get(units[ix[key]], 1)
+            return int(tot)
+    return None
+
+
+def per_task_block(w, model, teacher):
+    """The per-task path (not per step): feature extraction for herding (template.py:292-299), herding itself
+    (template.py:300-302), eval() (template.py:169-188) and weight align in situ (template.py:156-166)."""
+    out = {}
+    dev = "cuda"
+    n = 7000  # a task set of the 10x10 protocol: 5000 new + 2000 exemplars
+    x = torch.randn(n, 3, 32, 32, device=dev)
+    for _ in range(2):
+        f = w.extract_features(model, x, BATCH)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    f = w.extract_features(model, x, BATCH)
+    torch.cuda.synchronize()
+    out["feature_extraction_img_s"] = n / (time.perf_counter() - t0)
+    model.train()
+    import numpy as np
+    for name, (k, per, quota) in {"herding_20x500x64_ms": (20, 500, 100), "herding_100x70x64_ms": (100, 70, 20)}.items():
+        feats = torch.relu(torch.randn(k * per, 64, device=dev) * 0.3 + 0.5)
+        yy = torch.arange(k, device=dev).repeat_interleave(per)
+        w.rehearsal.herd_indices(feats, yy, quota)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        w.rehearsal.herd_indices(feats, yy, quota)
+        torch.cuda.synchronize()
+        out[name] = 1e3 * (time.perf_counter() - t0)
+    xv = torch.randn(2000, 3, 32, 32, device=dev)
+    yv = torch.randint(0, sum(HEADS), (2000,), device=dev)
+    loader = [(xv[i: i + BATCH], yv[i: i + BATCH], None) for i in range(0, 2000, BATCH)]
+    w.eval(model, loader)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    w.eval(model, loader)
+    torch.cuda.synchronize()
+    out["eval_img_s"] = 2000 / (time.perf_counter() - t0)
+    model.train()
+    m2 = model.copy()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m2.weight_align(HEADS[-1], verbose=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        m2.weight_align(HEADS[-1], verbose=False)
+    e1.record()
+    torch.cuda.synchronize()
+    out["weight_align_in_situ_us"] = 1e3 * e0.elapsed_time(e1) / 20
+    out["note"] = ("ResNet-32, 20 seen classes; features / eval through the folded-BN inference plan at batch 128, host timer "
+                   "around whole calls (one sync each); weight align on the [20,64] classifier (launch-latency bound)")
+    return out
+
+
+def task9_point(w, world, rank, steps):
+    """The same step at task 9 of the protocol (100 seen / 90 known classes)."""
+    heads = [10] * 10
+    sd, tsd = make_states(heads)
+    model = w.CilModel(f"resnet{DEPTH}")
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    teacher = w.CilModel(f"resnet{DEPTH}")
+    teacher.load_state_dict(tsd)
+    teacher = teacher.cuda().copy().freeze()
+    tr = w.TaskTrainer(model, teacher, 90, lr=0.05, lambda_kd=0.5, T=2.0, world_size=world, use_graph=True)
+    x, y = synthetic_pool(16, 4321 + rank, n_classes=100)
+    x, y = x.cuda(), y.cuda()
+    for i in range(30):
+        tr.step(x[i % 16], y[i % 16])
+    ms = timed(lambda i: tr.step(x[i % 16], y[i % 16]), steps, world)
+    return {"workload": "resnet32-cifar100-10x10-task9-b128", "classes_seen": 100, "classes_known": 90, "steps": steps,
+            "ms_per_step": ms / steps, "img_s": steps * BATCH * world / (ms / 1e3)}
+
 
 
 def _dbg(msg):
@@ -310,6 +488,7 @@ def run_ours(args, rank, local_rank, world):
         ms_e2e = timed(step_e2e, args.steps, world)
     _dbg('e2e done')
     launches_per_step = tr.launches_per_step
+    t9 = task9_point(w, world, rank, min(args.steps, 50))
     # data-parallel replicas must stay in lock step (DDP semantics, template.py:243-244): compare the whole parameter
     # arena, the momentum buffer and (after rank 0's broadcast, what the reference's DDP does) nothing else — the
     # BatchNorm running statistics are per-rank by design until a task boundary
@@ -327,6 +506,7 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     roof = kernel_rooflines(w, pk) if world == 1 else None
+    per_task = per_task_block(w, model, teacher) if world == 1 else None
     _dbg('rooflines done; cpu baseline')
     cpu = None
     if world == 1:
@@ -350,21 +530,30 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clk.summary(),
         "step_tensor_frac": value / world * F_STEP / (pk["tflops"] * 1e12),
         "final_losses": final_loss,
+        "task9": t9,
     }
+    if per_task is not None:
+        line["per_task"] = per_task
     if replicas_identical is not None:
         line["replicas_identical"] = replicas_identical
     if roof is not None:
         c = roof["conv"]
         line["roofline"] = {"bound": "hbm", "achieved": c["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": c["gbs"] / pk["hbm_gbs"], "traffic": 8464640, "kernel": c["kernel"], "us": c["us"],
-                            "traffic_note": "dram__bytes_read+write of one launch, ncu --set full (profiles/r01_ncu_full_fused_"
-                                            "stage1.csv): the 8.4 MB of outputs stay in the 126 MB L2 (write-back), inputs "
-                                            "are read once from DRAM; L2->SM reads are 23.8 MB (row-merged loads: 3 boxes of 6 image "
-                                            "rows per 4-row tile; 42.7 MB with one box per tap)",
+                            "frac": c["gbs"] / pk["hbm_gbs"],
+                            "traffic": ncu_traffic("r02_ncu_full_fused_stage1.csv", "conv_gemm_kernel"),
+                            "kernel": c["kernel"], "us": c["us"],
+                            "traffic_note": "dram__bytes_read+write of one launch, parsed from the committed ncu --set full export "
+                                            "profiles/r02_ncu_full_fused_stage1.csv (same entry point): outputs stay in the 126 MB L2 "
+                                            "(write-back), inputs are read once from DRAM",
                             "algorithmic_bytes": c["bytes"], "tflops": c["tflops"], "peak_src": pk["src"]}
         line["kd_kernel"] = roof["kd"]
+        line["weight_align_kernel"] = roof["wa"]
     if cpu is not None:
         line["cpu_baseline"] = cpu
+        try:
+            line["cpu_gloo"] = cpu_gloo_baseline()
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_gloo"] = {"error": str(ex)[:200]}
     if world == 1:
         try:
             line["gpu_eager_baseline"] = {"fp32_img_s": gpu_eager_steps(20, False), "bf16_autocast_img_s": gpu_eager_steps(20, True),
@@ -378,7 +567,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
