@@ -163,12 +163,11 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 // Grid of the weight-gradient kernel of a layer (pixel tiles are split into contiguous chunks, one per CTA) — also the
 // number of partial-sum slots its workspace holds.
 int wgrad_grid(int num_tiles) {
-  static const int cap_env = env_int("WACIL_WGRAD_CTAS", 0, 0, 4096);  // experiment: CTAs (pixel chunks) per launch
   int g = (num_tiles + 1) / 2;
   // at most one CTA per SM: a second resident weight-gradient CTA (75 KB of shared memory each) leaves no room for the
-  // CTA of the cooperative data-gradient launch that has to fit on every SM at once
-  const int cap = cap_env > 0 ? cap_env : num_sms();
-  if (g > cap) g = cap;
+  // CTA of the cooperative data-gradient launch that has to fit on every SM at once (1.128 vs 1.185 ms per step with
+  // 296 CTAs, profiles/r02_xp3.log)
+  if (g > num_sms()) g = num_sms();
   return g < 1 ? 1 : g;
 }
 
@@ -463,7 +462,6 @@ int engine_kind() {
 }
 int chain_fwd_len() { static int v = env_int("WACIL_CHAIN_FWD", 64, 1, 1000); return v; }
 int chain_bwd_len() { static int v = env_int("WACIL_CHAIN_BWD", 4, 1, 1000); return v; }
-int chain_grid_cap() { static int v = env_int("WACIL_CHAIN_GRID", 1 << 20, 1, 1 << 20); return v; }  // experiments only
 size_t chain_smem_budget() { static int v = env_int("WACIL_CHAIN_SMEM", 113, 48, 227); return static_cast<size_t>(v) * 1024; }
 
 struct ChainPlan {
@@ -494,12 +492,9 @@ int launch_chain(const ChainPlan& c, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
-  static int coop = env_int("WACIL_CHAIN_COOP", 1, 0, 1);  // experiment: 0 = plain launch
-  if (coop) {
-    attrs[na].id = cudaLaunchAttributeCooperative;  // grid barriers and cross-CTA ready flags: all CTAs co-resident
-    attrs[na].val.cooperative = 1;
-    ++na;
-  }
+  attrs[na].id = cudaLaunchAttributeCooperative;  // grid barriers and cross-CTA ready flags: all CTAs co-resident
+  attrs[na].val.cooperative = 1;
+  ++na;
   if (c.cp.pdl) {
     attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
@@ -766,7 +761,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     ChainPlan cpn;
     cpn.first = first; cpn.count = count; cpn.ew = fwd_ew;
     cpn.fused = mode == WACIL_NET_TRAIN;
-    cpn.grid = std::min(std::min(max_tiles, num_sms()), chain_grid_cap());
+    cpn.grid = std::min(max_tiles, num_sms());
     uint32_t cols = 0;
     for (int l = first; l < first + count; ++l) {
       const ConvLaunch& c = n->fprop[l];
@@ -871,7 +866,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       ChainPlan cpn;
       cpn.first = first; cpn.count = count; cpn.ew = ew_fused;
-      cpn.grid = std::min(std::min(max_tiles, num_sms()), chain_grid_cap());
+      cpn.grid = std::min(max_tiles, num_sms());
       uint32_t cols = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el);
@@ -1149,17 +1144,16 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     cudaError_t ce_ = (call);                                  \
     if (ce_ != cudaSuccess) return cuda_fail(ce_, what);       \
   } while (0)
-  static const int xp = env_int("WACIL_XP", 0, 0, 7);  // experiments: 1 skip wgrad kernels, 2 skip reductions, 4 skip the data-gradient launches
   int pending = 0;  // weight gradients whose partial slots have not been reduced yet: layers l_lo .. l_lo + pending - 1
   size_t nred = 0;  // reductions launched so far
   auto wgrads = [&](int l_hi, int l_lo) -> int {  // weight gradients of layers l_hi .. l_lo (descending) + ordered reduction
-    for (int l = l_hi; l >= l_lo && !(xp & 1); --l) {
+    for (int l = l_hi; l >= l_lo; --l) {
       int e2 = launch_wgrad(n->wgrad[l], ws);
       if (e2) return e2;
       ++launches;
     }
     pending += l_hi - l_lo + 1;
-    if ((pending >= 4 || l_lo == 0) && !(xp & 2)) {  // a few layers per reduction launch, on the third branch
+    if (pending >= 4 || l_lo == 0) {  // a few layers per reduction launch, on the third branch
       cudaStream_t rs = par && n->red ? n->red : ws;
       if (rs != ws) {
         cudaError_t e_ = cudaEventRecord(n->ev_wg[nred], ws);
@@ -1219,7 +1213,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   if ((e = wgrads(nl - 1, nl - 1))) return e;
   for (size_t ci = 0; ci < n->bchains.size(); ++ci) {
     const ChainPlan& c = n->bchains[ci];
-    if (!(xp & 4) && (e = n->engine == ENGINE_LAYER ? launch_conv(n->dgrad[nl - 1 - c.first], st) : launch_chain(c, st))) return e;
+    if ((e = n->engine == ENGINE_LAYER ? launch_conv(n->dgrad[nl - 1 - c.first], st) : launch_chain(c, st))) return e;
     ++launches;
     if (par) {
       WACIL_EV(cudaEventRecord(n->ev_chain[ci + 1], st), "event record");
