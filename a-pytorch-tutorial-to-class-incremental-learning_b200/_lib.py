@@ -35,6 +35,8 @@ P, I, L, F, Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "wacil_version": (I, []),
     "wacil_last_error": (C.c_char_p, []),
+    "wacil_fc_forward": (I, [P, L, P, L, P, P, L, I, I, I, P]),
+    "wacil_fc_backward": (I, [P, L, P, L, P, L, P, L, P, L, P, I, I, I, P]),
     "wacil_kd_workspace_bytes": (Z, [I]),
     "wacil_kd_fwd_bwd": (I, [P, L, P, L, I, I, F, F, P, P, L, I, I, P, P]),
     "wacil_ce_kd_fwd_bwd": (I, [P, L, P, P, L, I, I, I, F, F, F, P, P, L, P, P]),

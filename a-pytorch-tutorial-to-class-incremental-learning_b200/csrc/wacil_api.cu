@@ -12,6 +12,7 @@
 #include "loss_kernels.cuh"
 #include "tc_conv.cuh"
 #include "tc_chain.cuh"
+#include "tc_fc.cuh"
 
 using namespace wacil;
 
@@ -441,7 +442,7 @@ int launch_wgrad(const WgradLaunch& w, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------- chain launches
-// Tuning knobs of the chain launches (host side only; the defaults are the measured best, profiles/r02_chain_ab.md):
+// Tuning knobs of the chain launches (host side only; the defaults are the measured best, profiles/r02_chain_experiments.md):
 //   WACIL_CHAIN_EW     epilogue warps of the fused (BatchNorm) chains: 4 | 8
 //   WACIL_CHAIN_FWD    layers per forward launch (a launch never crosses a resolution change)
 //   WACIL_CHAIN_BWD    layers per backward launch (the weight gradients of a launch's layers start when it ends)
@@ -1438,6 +1439,77 @@ int wacil_weight_align(void* W, int C_total, int D, int n_new, float* gamma_out,
   if (dtype == WACIL_F32) return wa_launch<float>(W, C_total, D, n_new, gamma_out, workspace, S(stream));
   if (dtype == WACIL_BF16) return wa_launch<__nv_bfloat16>(W, C_total, D, n_new, gamma_out, workspace, S(stream));
   return fail(WACIL_E_DTYPE, "dtype %d", dtype);
+}
+
+// ---------------------------------------------------------------------------------------- classifier head (tcgen05)
+namespace {
+int fc_gemm_launch(const float* A, long long lda, int a_mn, const float* Bm, long long ldb, int b_mn, int M, int N,
+                   int K, float* out, long long ldo, const float* bias, cudaStream_t st) {
+  static bool attr_set = false;
+  FcGemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.bn = std::min(128, (N + 31) / 32 * 32);
+  p.out = out; p.ldo = ldo; p.bias = bias;
+  CUtensorMap mapA, mapB;
+  // K-major: rows = the M (N) extent, columns = K;  MN-major: rows = K, columns = the M (N) extent
+  int e = a_mn ? make_f32_map(&mapA, A, K, M, lda, kFcKTile, true) : make_f32_map(&mapA, A, M, K, lda, 128, false);
+  if (e) return fail(WACIL_E_DRIVER, "classifier GEMM: tensor map of A (%dx%d, pitch %lld): %d", M, K, lda, e);
+  e = b_mn ? make_f32_map(&mapB, Bm, K, N, ldb, kFcKTile, true) : make_f32_map(&mapB, Bm, N, K, ldb, p.bn, false);
+  if (e) return fail(WACIL_E_DRIVER, "classifier GEMM: tensor map of B (%dx%d, pitch %lld): %d", N, K, ldb, e);
+  const size_t smem = fc_gemm_smem_bytes(128);
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(fc_gemm_kernel)");
+    attr_set = true;
+  }
+  const dim3 grid(static_cast<unsigned>((M + 127) / 128), static_cast<unsigned>((N + p.bn - 1) / p.bn));
+  fc_gemm_kernel<<<grid, 192, fc_gemm_smem_bytes(p.bn), st>>>(mapA, mapB, p);
+  WACIL_LAUNCH_CHECK("fc_gemm_kernel");
+  return 0;
+}
+int fc_check(const void* ptr, long long ld, const char* what) {
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(WACIL_E_ALIGN, "%s must be 16-byte aligned", what);
+  if (ld & 3) return fail(WACIL_E_ALIGN, "row pitch of %s (%lld floats) must be a multiple of 4", what, ld);
+  return 0;
+}
+}  // namespace
+
+int wacil_fc_forward(const float* feats, int64_t f_ld, const float* W, int64_t w_ld, const float* bias, float* logits,
+                     int64_t l_ld, int B, int D, int C, void* stream) {
+  if (!feats || !W || !logits) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || D <= 0 || C <= 0 || f_ld < D || w_ld < D || l_ld < C)
+    return fail(WACIL_E_SHAPE, "B=%d D=%d C=%d pitches %lld %lld %lld", B, D, C, (long long)f_ld, (long long)w_ld, (long long)l_ld);
+  int e = fc_check(feats, f_ld, "feats");
+  if (!e) e = fc_check(W, w_ld, "W");
+  if (e) return e;
+  return fc_gemm_launch(feats, f_ld, 0, W, w_ld, 0, B, C, D, logits, l_ld, bias, S(stream));
+}
+
+int wacil_fc_backward(const float* dlogits, int64_t g_ld, const float* feats, int64_t f_ld, const float* W,
+                      int64_t w_ld, float* dfeats, int64_t df_ld, float* dW, int64_t dw_ld, float* db, int B, int D,
+                      int C, void* stream) {
+  if (!dlogits || !feats || !W) return fail(WACIL_E_NULL, "NULL argument");
+  if (B <= 0 || D <= 0 || C <= 0 || g_ld < C || f_ld < D || w_ld < D || (dfeats && df_ld < D) || (dW && dw_ld < D))
+    return fail(WACIL_E_SHAPE, "B=%d D=%d C=%d", B, D, C);
+  int e = fc_check(dlogits, g_ld, "dlogits");
+  if (!e) e = fc_check(feats, f_ld, "feats");
+  if (!e) e = fc_check(W, w_ld, "W");
+  if (e) return e;
+  cudaStream_t st = S(stream);
+  if (dfeats) {  // dfeats[b][d] = sum_c dlogits[b][c] W[c][d]
+    e = fc_gemm_launch(dlogits, g_ld, 0, W, w_ld, 1, B, D, C, dfeats, df_ld, nullptr, st);
+    if (e) return e;
+  }
+  if (dW) {  // dW[c][d] = sum_b dlogits[b][c] feats[b][d]
+    e = fc_gemm_launch(dlogits, g_ld, 1, feats, f_ld, 1, C, D, B, dW, dw_ld, nullptr, st);
+    if (e) return e;
+  }
+  if (db) {
+    fc_bias_grad_kernel<<<(C + 31) / 32, 256, 0, st>>>(dlogits, g_ld, B, C, db);
+    WACIL_LAUNCH_CHECK("fc_bias_grad_kernel");
+  }
+  return 0;
 }
 
 int wacil_sgd_step(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,

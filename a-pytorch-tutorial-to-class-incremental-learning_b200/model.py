@@ -63,6 +63,28 @@ class SoftTarget(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------- classifier
+class _LinearFn(torch.autograd.Function):
+    """x @ W.T + b on the tcgen05 classifier kernels (wacil_fc_forward / wacil_fc_backward, kind::tf32)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        return ops.fc_forward(x.detach(), W.detach(), b.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dx, dW, db = ops.fc_backward(g, x, W, need_dfeats=need[0], need_dW=need[1], need_db=need[2])
+        return dx, dW, db
+
+
+def _linear(x, W, b):
+    lead = x.shape[:-1]
+    out = _LinearFn.apply(x.reshape(-1, x.shape[-1]), W, b)
+    return out.reshape(*lead, W.shape[0])
+
+
 class _Head:
     """What `fc[i]` returns: live views of the classifier arena rows of task i (nn.Linear-like)."""
 
@@ -79,7 +101,7 @@ class _Head:
         return self._owner._arena.fc_bias()[self.lo: self.hi]
 
     def __call__(self, x):
-        return torch.nn.functional.linear(x, self.weight, self.bias)
+        return _linear(x, self.weight, self.bias)
 
 
 class CilClassifier(nn.Module):
@@ -119,7 +141,7 @@ class CilClassifier(nn.Module):
     def forward(self, x):
         # convenience entry (not on the training hot path: CilModel.forward fuses pool + classifier natively)
         c = self.num_classes
-        return torch.nn.functional.linear(x, self._arena.fc_weight()[:c], self._arena.fc_bias()[:c])
+        return _linear(x, self._arena.fc_weight()[:c], self._arena.fc_bias()[:c])
 
     def adaption(self, nb_classes):
         lo = self._bounds[-1]

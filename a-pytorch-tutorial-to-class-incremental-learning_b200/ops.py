@@ -85,6 +85,54 @@ def ce_kd_fwd_bwd(logits, targets, t_logits, known, T=2.0, lambda_kd=0.5, smooth
     return losses, dlogits
 
 
+def _rows_f32(t, what):
+    """fp32 2-D tensor whose rows TMA can address: unit column stride, pitch a multiple of 4 floats, 16-byte base."""
+    if t.dim() != 2 or t.dtype != torch.float32:
+        raise _lib.WacilError(f"{what}: 2-D fp32 tensor expected")
+    if t.stride(1) != 1 or t.stride(0) % 4 or t.stride(0) < t.shape[1] or t.data_ptr() % 16:
+        pitch = (t.shape[1] + 3) // 4 * 4
+        buf = torch.zeros((t.shape[0], pitch), dtype=torch.float32, device=t.device)
+        buf[:, : t.shape[1]].copy_(t)
+        t = buf[:, : t.shape[1]]
+    return t
+
+
+def fc_forward(feats, W, bias=None, out=None):
+    """CilClassifier.forward (template.py:99-101) as tcgen05 tf32 tiles: logits = feats @ W.T + bias.
+    feats [B,D], W [C,D] (a row range of the classifier arena), bias [C] or None.  Returns logits [B,C] fp32."""
+    _need_cuda(feats, W, bias)
+    feats, W = _rows_f32(feats, "feats"), _rows_f32(W, "W")
+    B, D = feats.shape
+    Cn = W.shape[0]
+    if W.shape[1] != D or (bias is not None and (bias.dtype != torch.float32 or bias.numel() != Cn or not bias.is_contiguous())):
+        raise _lib.WacilError("fc_forward: W [C,D] and contiguous fp32 bias [C] expected")
+    if out is None:
+        out = torch.empty((B, Cn), dtype=torch.float32, device=feats.device)
+    check(lib().wacil_fc_forward(feats.data_ptr(), feats.stride(0), W.data_ptr(), W.stride(0),
+                                 bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), B, D, Cn,
+                                 _stream()), "wacil_fc_forward")
+    return out
+
+
+def fc_backward(dlogits, feats, W, need_dfeats=True, need_dW=True, need_db=True):
+    """Backward of fc_forward: returns (dfeats [B,D] | None, dW [C,D] | None, db [C] | None)."""
+    _need_cuda(dlogits, feats, W)
+    dlogits, feats, W = _rows_f32(dlogits, "dlogits"), _rows_f32(feats, "feats"), _rows_f32(W, "W")
+    B, D = feats.shape
+    Cn = W.shape[0]
+    if dlogits.shape != (B, Cn) or W.shape[1] != D:
+        raise _lib.WacilError("fc_backward: dlogits [B,C], feats [B,D], W [C,D] expected")
+    dev = feats.device
+    df = torch.empty((B, D), dtype=torch.float32, device=dev) if need_dfeats else None
+    dW = torch.empty((Cn, D), dtype=torch.float32, device=dev) if need_dW else None
+    db = torch.empty((Cn,), dtype=torch.float32, device=dev) if need_db else None
+    check(lib().wacil_fc_backward(dlogits.data_ptr(), dlogits.stride(0), feats.data_ptr(), feats.stride(0), W.data_ptr(),
+                                  W.stride(0), df.data_ptr() if df is not None else None, D,
+                                  dW.data_ptr() if dW is not None else None, D,
+                                  db.data_ptr() if db is not None else None, B, D, Cn, _stream()), "wacil_fc_backward")
+    return df, dW, db
+
+
 def weight_align_(W, n_new, gamma_out=None):
     """In-place WA on the contiguous classifier matrix W [C_total, D] (template.py:156-166); returns gamma (0-dim)."""
     _need_cuda(W)

@@ -85,6 +85,23 @@ int wacil_eval_rows(const float* logits, int64_t l_ld, const int64_t* targets, i
                     void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Classifier head as tensor-core tiles  (CilClassifier.forward, template.py:99-101: the heads' nn.Linear outputs
+ * concatenated = ONE product over the contiguous [C][D] arena; backward = what autograd derives for it)
+ *   forward : logits[b][c] = sum_d feats[b][d] W[c][d] + bias[c]
+ *   backward: dfeats[b][d] = sum_c dlogits[b][c] W[c][d];  dW[c][d] = sum_b dlogits[b][c] feats[b][d];
+ *             db[c] = sum_b dlogits[b][c]      (each output optional: pass NULL to skip)
+ * fp32 tensors, row-major with explicit row pitches in floats (*_ld; multiples of 4, bases 16-byte aligned: TMA).
+ * Arithmetic: tcgen05.mma kind::tf32 (operands read as tf32, fp32 accumulation in TMEM) — relative error 1e-3 of
+ * |feats|.|W|; tests/test_gpu_ops.py states the tolerance.  Any B, D, C (tiles are zero-filled at the edges); sized
+ * for the large heads of BASELINE configs 3-5 (D = 512 / 2048, C = 100 ... 8192).  The D = 64 CIFAR head inside
+ * wacil_net_forward stays a CUDA-core kernel fused with the 8x8 pooling. */
+int wacil_fc_forward(const float* feats, int64_t f_ld, const float* W, int64_t w_ld, const float* bias, float* logits,
+                     int64_t l_ld, int B, int D, int C, void* stream);
+int wacil_fc_backward(const float* dlogits, int64_t g_ld, const float* feats, int64_t f_ld, const float* W,
+                      int64_t w_ld, float* dfeats, int64_t df_ld, float* dW, int64_t dw_ld, float* db, int B, int D,
+                      int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * Weight aligning  (CilModel.weight_align, template.py:156-166)
  *   norms = ||W[r,:]||_2 ; gamma = mean(norms[:C_total-n_new]) / mean(norms[C_total-n_new:])
  *   W[C_total-n_new:, :] *= gamma     (in place; bias untouched)

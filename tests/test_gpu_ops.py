@@ -254,3 +254,52 @@ def test_fused_conv_bn_relu_vs_torch(w, N, H, cin, cout, stride, res_mode):
     assert ((ag - aref).abs() <= aref.abs().clamp_min(1e-2) * 2.0 ** -7).all()
     np.testing.assert_allclose(rm_d.cpu().numpy(), (0.9 * rm + 0.1 * mean).numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(rv_d.cpu().numpy(), (0.9 * rv + 0.1 * var * m / (m - 1)).numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ classifier head
+@pytest.mark.parametrize("B,D,C", [(128, 64, 20), (128, 512, 100), (1024, 2048, 1000), (96, 520, 36), (7, 64, 10),
+                                   (200, 2048, 300)])
+def test_fc_tensor_core_head_vs_fp64(w, B, D, C):
+    """wacil_fc_forward / wacil_fc_backward (tcgen05 kind::tf32, fp32 accumulation) against the fp64 product of
+    CilClassifier.forward (template.py:99-101) and its autograd backward.  tf32 keeps 10 mantissa bits of each
+    operand, so every term carries a relative error <= 2^-10 (two truncations): the bound asserted per element is
+    1.5e-3 * sum_k |a_k||b_k| (a layout bug is an O(1) error).  Covers ragged tiles (B, D, C not multiples of the
+    128 x 128 x 32 tile) and a dlogits pitch that is not TMA-addressable (C = 10: the wrapper re-pitches it)."""
+    gen = torch.Generator().manual_seed(B * 7 + D + C)
+    feats = torch.randn(B, D, generator=gen)
+    W = torch.randn(C, D, generator=gen) * 0.1
+    b = torch.randn(C, generator=gen)
+    g = torch.randn(B, C, generator=gen) * 0.05
+    fd, Wd, gd = feats.double(), W.double(), g.double()
+    tol = 1.5e-3
+
+    got = w.ops.fc_forward(feats.cuda(), W.cuda(), b.cuda()).cpu().double()
+    ref = fd @ Wd.T + b.double()
+    assert ((got - ref).abs() <= tol * (fd.abs() @ Wd.abs().T) + 1e-6).all()
+
+    dx, dW, db = w.ops.fc_backward(g.cuda(), feats.cuda(), W.cuda())
+    assert ((dx.cpu().double() - gd @ Wd).abs() <= tol * (gd.abs() @ Wd.abs()) + 1e-6).all()
+    assert ((dW.cpu().double() - gd.T @ fd).abs() <= tol * (gd.abs().T @ fd.abs()) + 1e-6).all()
+    np.testing.assert_allclose(db.cpu().numpy(), g.sum(0).numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_classifier_module_runs_on_the_tensor_core_head(w):
+    """CilClassifier.forward / fc[i](x) (template.py:99-104) go through the same kernels with autograd: the gradient
+    lands in the flat arena, heads are row ranges."""
+    torch.manual_seed(3)
+    model = w.CilModel("resnet20")
+    model.prev_model_adaption(10)
+    model.prev_model_adaption(10)
+    model = model.cuda()
+    x = torch.randn(33, 64, device="cuda", requires_grad=True)
+    out = model.fc(x)
+    assert out.shape == (33, 20)
+    Wt, bt = model.fc[1].weight.detach(), model.fc[1].bias.detach()
+    head1 = model.fc[1](x)
+    ref = torch.nn.functional.linear(x.detach().double(), Wt.double(), bt.double())
+    assert (head1.detach().double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-5
+    assert torch.equal(out[:, 10:], head1)
+    out.square().sum().backward()
+    full_W = torch.cat([model.fc[0].weight, model.fc[1].weight]).detach().double()
+    dlog = 2 * out.detach().double()
+    assert (x.grad.double() - dlog @ full_W).abs().max().item() <= 2e-3 * (dlog.abs() @ full_W.abs()).max().item()
