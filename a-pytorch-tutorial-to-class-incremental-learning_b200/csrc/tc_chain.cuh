@@ -575,20 +575,20 @@ __global__ void __maxnreg__(FUSED ? (EW == 4 ? WACIL_CHAIN_REGS : 96) : 128) con
       // ---------------- per-channel constants from the per-CTA partial rows, added in CTA order by every CTA
       const float cnt = static_cast<float>(npix);
       {
-        const int V = 2 * nc, S = ET / V;  // 32/64/128 values -> ET/V row slices
-        const int v = tid % V, sl = tid / V;
-        // scratch over the (already consumed) per-warp partials
-        if (sl < S) s_part[sl * 128 + v] = ordered_row_sum(L->stats, V, v, sl, S, G);
+        const int V = 2 * nc, Q = V / 4, S = ET / Q;  // 8/16/32 column groups of 4 values -> ET/Q row slices
+        const int cg = tid % Q, sl = tid / Q;
+        // scratch [S][V] over the (already consumed) per-warp partials
+        *reinterpret_cast<float4*>(s_part + sl * V + 4 * cg) = ordered_row_sum4(L->stats, V, cg, sl, S, G);
       }
       if (cp.dbg != nullptr && tid == 0) cp.dbg[(static_cast<size_t>(blockIdx.x) * nl + l) * 48 + 8] = clock64();
       asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       if (tid < nc) {
         const int c = tid;
-        const int S = ET / (2 * nc);
+        const int V = 2 * nc, S = 4 * ET / V;
         float t0 = 0.f, t1 = 0.f;
         for (int sl = 0; sl < S; ++sl) {
-          t0 += s_part[sl * 128 + c];
-          t1 += s_part[sl * 128 + nc + c];
+          t0 += s_part[sl * V + c];
+          t1 += s_part[sl * V + nc + c];
         }
         if (epi == EPI_BN_TRAIN) {
           const float mean = t0 / cnt;

@@ -235,21 +235,29 @@ __device__ __forceinline__ void issue_tap_group(bool leader, uint32_t d_tmem, ui
 
 constexpr int kConvThreads = 192;
 
-// Fixed-order sum of rows first, first + step, ... (< rows) of a [rows][V] fp32 table, column v.  The loads of a batch
-// of 32 rows are independent and issued together (one L2 round trip per batch instead of one per row); the additions
-// keep the row order, so the result is the same on every CTA and every run.
-__device__ __forceinline__ float ordered_row_sum(const float* __restrict__ table, int V, int v, int first, int step,
-                                                 int rows) {
-  float acc = 0.f;
-  for (int r0 = first; r0 < rows; r0 += step * 32) {
-    float t[32];
+// Fixed-order sum of rows first, first + step, ... (< rows) of a [rows][V] fp32 table, columns [4 cg, 4 cg + 4).  The
+// 16-byte loads of a batch of 10 rows are independent and issued together (one L2 round trip per batch: the whole
+// 148 x 32 table of a 16-channel layer is ONE batch for 128 threads); the additions keep the row order, so the result
+// is the same on every CTA and every run.
+__device__ __forceinline__ float4 ordered_row_sum4(const float* __restrict__ table, int V, int cg, int first, int step,
+                                                   int rows) {
+  constexpr int NB = 10;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r0 = first; r0 < rows; r0 += step * NB) {
+    float4 t[NB];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < NB; ++j) {
       const int r = r0 + j * step;
-      t[j] = r < rows ? __ldcg(table + static_cast<size_t>(r) * V + v) : 0.f;
+      t[j] = r < rows ? __ldcg(reinterpret_cast<const float4*>(table + static_cast<size_t>(r) * V) + cg)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc += t[j];
+    for (int j = 0; j < NB; ++j) {
+      acc.x += t[j].x;
+      acc.y += t[j].y;
+      acc.z += t[j].z;
+      acc.w += t[j].w;
+    }
   }
   return acc;
 }
@@ -632,20 +640,22 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels);
     {
-      // every CTA sums the per-CTA partial rows in the same fixed order: thread (slice, value) takes rows slice,
-      // slice + S, ... (coalesced 4*V-byte rows, all loads independent), the S slice sums are combined in order
-      const int V = 2 * p.nc, S = ET / V;  // 32/64/128 values -> 4/2/1 row slices
-      const int v = tid128 % V, sl = tid128 / V;
-      // (the per-warp partials are dead after the stores above: their rows serve as scratch)
-      s_part[sl * 128 + v] = ordered_row_sum(p.stats, V, v, sl, S, static_cast<int>(gridDim.x));
+      // every CTA sums the per-CTA partial rows in the same fixed order: thread (slice, 4 values) takes rows slice,
+      // slice + S, ... (16-byte loads, all independent), the S slice sums are combined in order below
+      const int V = 2 * p.nc, Q = V / 4, S = ET / Q;  // 8/16/32 column groups -> 16/8/4 row slices
+      const int cg = tid128 % Q, sl = tid128 / Q;
+      // (the per-warp partials are dead after the stores above: their 512 floats serve as the [S][V] scratch)
+      *reinterpret_cast<float4*>(s_part + sl * V + 4 * cg) =
+          ordered_row_sum4(p.stats, V, cg, sl, S, static_cast<int>(gridDim.x));
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 < p.nc) {
       const int c = tid128;
       float t0 = 0.f, t1 = 0.f;
-      for (int sl = 0; sl < ET / (2 * p.nc); ++sl) {
-        t0 += s_part[sl * 128 + c];
-        t1 += s_part[sl * 128 + p.nc + c];
+      const int V = 2 * p.nc, S = 4 * ET / V;
+      for (int sl = 0; sl < S; ++sl) {
+        t0 += s_part[sl * V + c];
+        t1 += s_part[sl * V + p.nc + c];
       }
       if (p.epi == EPI_BN_TRAIN) {
         const float mean = t0 / cnt;

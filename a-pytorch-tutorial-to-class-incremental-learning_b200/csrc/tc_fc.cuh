@@ -12,7 +12,10 @@
 //     dfeats      dfeats [B][D] = dlogits[B][C] . W[C][D]         A = dlogits (K-major),  B = W     (MN-major)
 //     dW          dW     [C][D] = dlogits[B][C]^T . feats[B][D]   A = dlogits (MN-major), B = feats (MN-major)
 //
-// Tiles: 128 rows of M x bn <= 128 columns of N per CTA, K in steps of 32 floats (one 128-byte swizzled row).
+// Tiles: 128 rows of M x bn <= 256 columns of N per CTA; a pipeline stage holds kb x 32 floats of K (32 floats = one
+// 128-byte swizzled row).  The producer's fixed cost per stage (~700 cycles of mbarrier round trip + TMA issue,
+// profiles/r02_chain_experiments.md) sets the tile shape: bn = 256 x one K box when the grid still fills the SMs,
+// otherwise narrower tiles with two K boxes per stage (fc_gemm_shape).
 //   K-major operand : one TMA box {32 floats of K, rows} -> canonical K-major SW128 (SBO = 1 KB per 8 rows); the four
 //                     K = 8 steps of a stage advance the descriptor start by 32 bytes.
 //   MN-major operand: one TMA box {32 floats of MN, 32 rows of K} per 32-float chunk of the tile, chunks 4 KB apart
@@ -28,14 +31,16 @@
 
 namespace wacil {
 
-constexpr int kFcStages = 4;
-constexpr int kFcKTile = 32;                      // floats of K per stage = one 128-byte row
-constexpr int kFcABytes = 128 * kFcKTile * 4;     // 16 KB
+constexpr int kFcMaxStages = 4;
+constexpr int kFcKTile = 32;                      // floats of K per box = one 128-byte row
+constexpr int kFcABytes = 128 * kFcKTile * 4;     // 16 KB: the A operand of one K box
 
 struct FcGemmParams {
   int M, N, K;
   int a_mn, b_mn;      // 0 = K-major, 1 = MN-major
-  int bn;              // N tile: multiple of 32, <= 128
+  int bn;              // N tile: multiple of 32, <= 256
+  int kb;              // K boxes (of 32 floats) per pipeline stage
+  int stages;          // <= kFcMaxStages
   float* out;
   long long ldo;       // floats between rows of out
   const float* bias;   // [N] or nullptr
@@ -65,9 +70,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-inline size_t fc_gemm_smem_bytes(int bn) {
-  return 1024 + static_cast<size_t>(kFcStages) * (kFcABytes + static_cast<size_t>(bn) * kFcKTile * 4) +
-         (2 * kFcStages + 1) * 8 + 16;
+inline size_t fc_gemm_smem_bytes(int bn, int kb, int stages) {
+  return 1024 + static_cast<size_t>(stages) * kb * (kFcABytes + static_cast<size_t>(bn) * kFcKTile * 4) +
+         (2 * kFcMaxStages + 1) * 8 + 16;
+}
+// Tile shape for an M x N x K product on `sms` SMs (see the header comment); every choice keeps the ring at 192 KB.
+inline void fc_gemm_shape(int M, int N, int sms, int& bn, int& kb, int& stages) {
+  const long long tm = (M + 127) / 128;
+  if (tm * ((N + 255) / 256) * 5 >= 4LL * sms) { bn = 256; kb = 1; stages = 4; return; }
+  if (tm * ((N + 127) / 128) * 5 >= 4LL * sms) { bn = 128; kb = 2; stages = 3; return; }
+  bn = N >= 64 ? 64 : (N + 31) / 32 * 32;
+  kb = 2;
+  stages = 4;
 }
 
 __global__ void __launch_bounds__(192)
@@ -75,23 +89,26 @@ __global__ void __launch_bounds__(192)
                    const FcGemmParams p) {
   extern __shared__ uint8_t fc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fc_smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * kFcKTile * 4;
-  const uint32_t stage_bytes = kFcABytes + b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kFcStages * stage_bytes);
-  uint64_t* empty = full + kFcStages;
-  uint64_t* accfull = empty + kFcStages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * kFcKTile * 4;  // the B operand of one K box
+  const uint32_t a_stage = static_cast<uint32_t>(p.kb) * kFcABytes;
+  const uint32_t stage_bytes = a_stage + static_cast<uint32_t>(p.kb) * b_bytes;
+  const int nstages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
+  uint64_t* empty = full + kFcMaxStages;
+  uint64_t* accfull = empty + kFcMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * p.bn;
-  const int nkt = (p.K + kFcKTile - 1) / kFcKTile;
+  const int kstage = kFcKTile * p.kb;  // floats of K per stage
+  const int nkt = (p.K + kstage - 1) / kstage;
   const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(p.bn));
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
-      for (int s = 0; s < kFcStages; ++s) {
+      for (int s = 0; s < kFcMaxStages; ++s) {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
@@ -115,22 +132,23 @@ __global__ void __launch_bounds__(192)
       mbar_wait(&empty[stage], phase ^ 1);
       if (leader) {
         uint8_t* a_s = smem + stage * stage_bytes;
-        uint8_t* b_s = a_s + kFcABytes;
-        const int k0 = kt * kFcKTile;
+        uint8_t* b_s = a_s + a_stage;
+        const int k0 = kt * kstage;
         mbar_expect_tx(&full[stage], stage_bytes);
+        // K-major: kb boxes {32 floats of K, rows};  MN-major: one box {32 floats of MN, kb * 32 rows of K} per chunk
         if (!p.a_mn) {
-          tma_load_2d(a_s, &mapA, &full[stage], k0, m0);
+          for (int q = 0; q < p.kb; ++q) tma_load_2d(a_s + q * kFcABytes, &mapA, &full[stage], k0 + q * kFcKTile, m0);
         } else {
-          for (int c = 0; c < 4; ++c) tma_load_2d(a_s + c * 4096, &mapA, &full[stage], m0 + 32 * c, k0);
+          for (int c = 0; c < 4; ++c) tma_load_2d(a_s + c * p.kb * 4096, &mapA, &full[stage], m0 + 32 * c, k0);
         }
         if (!p.b_mn) {
-          tma_load_2d(b_s, &mapB, &full[stage], k0, n0);
+          for (int q = 0; q < p.kb; ++q) tma_load_2d(b_s + q * b_bytes, &mapB, &full[stage], k0 + q * kFcKTile, n0);
         } else {
-          for (int c = 0; c < p.bn / 32; ++c) tma_load_2d(b_s + c * 4096, &mapB, &full[stage], n0 + 32 * c, k0);
+          for (int c = 0; c < p.bn / 32; ++c) tma_load_2d(b_s + c * p.kb * 4096, &mapB, &full[stage], n0 + 32 * c, k0);
         }
       }
       __syncwarp();
-      if (++stage == kFcStages) {
+      if (++stage == nstages) {
         stage = 0;
         phase ^= 1;
       }
@@ -140,10 +158,15 @@ __global__ void __launch_bounds__(192)
     const bool leader = elect_one_sync();
     const uint32_t idesc = umma_idesc_tf32(128, p.bn, p.a_mn, p.b_mn);
     // K-major (SW128, type 2): LBO unused (16), SBO = 8 rows x 128 B;  MN-major (SW128 with 32-byte atoms, type 1):
-    // LBO = chunk stride (4 KB), SBO = next 4 K rows (512 B)
-    const uint64_t a_hi = p.a_mn ? umma_smem_desc(0, 4096, 512, 1) : umma_smem_desc(0, 16, 1024, 2);
-    const uint64_t b_hi = p.b_mn ? umma_smem_desc(0, 4096, 512, 1) : umma_smem_desc(0, 16, 1024, 2);
+    // LBO = chunk stride (kb x 4 KB), SBO = next 4 K rows (512 B)
+    const uint32_t lbo_mn = static_cast<uint32_t>(p.kb) * 4096u;
+    const uint64_t a_hi = p.a_mn ? umma_smem_desc(0, lbo_mn, 512, 1) : umma_smem_desc(0, 16, 1024, 2);
+    const uint64_t b_hi = p.b_mn ? umma_smem_desc(0, lbo_mn, 512, 1) : umma_smem_desc(0, 16, 1024, 2);
+    // a K = 8 step: K-major +32 B inside the box (4 per box, then the next box); MN-major +8 rows = 1 KB throughout
     const uint32_t a_step16 = (p.a_mn ? 1024u : 32u) >> 4, b_step16 = (p.b_mn ? 1024u : 32u) >> 4;
+    const uint32_t a_box16 = (p.a_mn ? 4096u : static_cast<uint32_t>(kFcABytes)) >> 4;
+    const uint32_t b_box16 = (p.b_mn ? 4096u : b_bytes) >> 4;
+    const int kb = p.kb;
     int stage = 0;
     uint32_t phase = 0;
     for (int kt = 0; kt < nkt; ++kt) {
@@ -151,14 +174,18 @@ __global__ void __launch_bounds__(192)
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
       const uint64_t a0 = a_hi | ((a_addr >> 4) & 0x3FFF);
-      const uint64_t b0 = b_hi | (((a_addr + kFcABytes) >> 4) & 0x3FFF);
+      const uint64_t b0 = b_hi | (((a_addr + a_stage) >> 4) & 0x3FFF);
+      for (int q = 0; q < kb; ++q) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (leader) umma_tf32(tmem_base, a0 + j * a_step16, b0 + j * b_step16, idesc, (kt | j) != 0 ? 1u : 0u);
+        for (int j = 0; j < 4; ++j) {
+          if (leader)
+            umma_tf32(tmem_base, a0 + q * a_box16 + j * a_step16, b0 + q * b_box16 + j * b_step16, idesc,
+                      (kt | q | j) != 0 ? 1u : 0u);
+        }
       }
       if (leader) umma_commit(&empty[stage]);
       __syncwarp();
-      if (++stage == kFcStages) {
+      if (++stage == nstages) {
         stage = 0;
         phase ^= 1;
       }

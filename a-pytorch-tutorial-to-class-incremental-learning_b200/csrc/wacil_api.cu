@@ -1449,22 +1449,22 @@ int fc_gemm_launch(const float* A, long long lda, int a_mn, const float* Bm, lon
   FcGemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.a_mn = a_mn; p.b_mn = b_mn;
-  p.bn = std::min(128, (N + 31) / 32 * 32);
+  fc_gemm_shape(M, N, num_sms(), p.bn, p.kb, p.stages);
   p.out = out; p.ldo = ldo; p.bias = bias;
   CUtensorMap mapA, mapB;
   // K-major: rows = the M (N) extent, columns = K;  MN-major: rows = K, columns = the M (N) extent
-  int e = a_mn ? make_f32_map(&mapA, A, K, M, lda, kFcKTile, true) : make_f32_map(&mapA, A, M, K, lda, 128, false);
+  int e = a_mn ? make_f32_map(&mapA, A, K, M, lda, kFcKTile * p.kb, true) : make_f32_map(&mapA, A, M, K, lda, 128, false);
   if (e) return fail(WACIL_E_DRIVER, "classifier GEMM: tensor map of A (%dx%d, pitch %lld): %d", M, K, lda, e);
-  e = b_mn ? make_f32_map(&mapB, Bm, K, N, ldb, kFcKTile, true) : make_f32_map(&mapB, Bm, N, K, ldb, p.bn, false);
+  e = b_mn ? make_f32_map(&mapB, Bm, K, N, ldb, kFcKTile * p.kb, true) : make_f32_map(&mapB, Bm, N, K, ldb, p.bn, false);
   if (e) return fail(WACIL_E_DRIVER, "classifier GEMM: tensor map of B (%dx%d, pitch %lld): %d", N, K, ldb, e);
-  const size_t smem = fc_gemm_smem_bytes(128);
+  const size_t smem = fc_gemm_smem_bytes(256, 1, 4);  // the largest of the three shapes
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(fc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaFuncSetAttribute(fc_gemm_kernel)");
     attr_set = true;
   }
   const dim3 grid(static_cast<unsigned>((M + 127) / 128), static_cast<unsigned>((N + p.bn - 1) / p.bn));
-  fc_gemm_kernel<<<grid, 192, fc_gemm_smem_bytes(p.bn), st>>>(mapA, mapB, p);
+  fc_gemm_kernel<<<grid, 192, fc_gemm_smem_bytes(p.bn, p.kb, p.stages), st>>>(mapA, mapB, p);
   WACIL_LAUNCH_CHECK("fc_gemm_kernel");
   return 0;
 }
