@@ -82,36 +82,6 @@ struct ConvGemmParams {
                                 // loads of Ht rows: the L2->SM traffic of the main loop halves (stage 1) / drops 2.4x (stage 2)
 };
 
-// Grid-wide barrier among the epilogue thread groups (128 threads, named barrier 1) of all CTAs.  Needs a
-// cooperative launch (all CTAs co-resident).  bar[0], bar[1] are zero at rest; bounded spin (a bug must trap, not hang).
-template <int ET>
-__device__ __forceinline__ void grid_barrier_epi(unsigned* bar, int tid128) {
-  asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-  if (tid128 == 0) {
-    // arrive with release semantics (cumulative over the partner threads' writes ordered by the bar.sync above),
-    // then poll with acquire loads: two L2 round trips instead of fence + atomic + atomic polling
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    const long long t0 = clock64();
-    unsigned seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-      if (seen < gridDim.x && clock64() - t0 > 4000000000LL) {
-        printf("wacil: grid barrier timeout (block %d)\n", blockIdx.x);
-        __trap();
-      }
-    } while (seen < gridDim.x);
-  }
-  asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-  if (tid128 == 0) {
-    // self-reset, off the critical path: the last CTA to check out knows every CTA has left the polling loop
-    if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) {
-      bar[1] = 0u;
-      __threadfence();
-      bar[0] = 0u;
-    }
-  }
-}
-
 #define WACIL_STAMP(slot)                                                        \
   do {                                                                           \
     if (p.dbg != nullptr) p.dbg[blockIdx.x * 16 + (slot)] = clock64();           \
@@ -257,6 +227,53 @@ __device__ __forceinline__ float4 ordered_row_sum4(const float* __restrict__ tab
       acc.y += t[j].y;
       acc.z += t[j].z;
       acc.w += t[j].w;
+    }
+  }
+  return acc;
+}
+
+// The statistics exchange of the fused kernels without a barrier: a CTA publishes its partial sums as 8-byte words
+// {value, tag} (one 64-bit store each: single-copy atomic, so a reader that sees the tag sees the value) and every CTA
+// polls the rows of all CTAs until they carry this launch's tag.  No release fence, no arrival counter, no separate
+// "barrier passed -> now read the data" round trip: publishing costs one store, the wait IS the read.
+// Fixed-order sum of rows first, first + step, ... (< rows) of a [rows][V] table of such words, values 2u and 2u + 1;
+// NB rows are in flight together (one L2 round trip per batch once they are published).
+template <int NB>
+__device__ __forceinline__ float2 tagged_row_sum2(const unsigned long long* __restrict__ table, int V, int u, int first,
+                                                  int step, int rows, unsigned tag) {
+  float2 acc = make_float2(0.f, 0.f);
+  const unsigned long long filler = static_cast<unsigned long long>(tag) << 32;  // value +0.0f under the right tag
+  for (int r0 = first; r0 < rows; r0 += step * NB) {
+    unsigned long long a[NB], b[NB];
+    const long long t0 = clock64();
+    bool ok;
+    do {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int r = r0 + j * step;
+        if (r < rows) {
+          asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];"
+                       : "=l"(a[j]), "=l"(b[j])
+                       : "l"(table + static_cast<size_t>(r) * V + 2 * u)
+                       : "memory");
+        } else {
+          a[j] = filler;
+          b[j] = filler;
+        }
+      }
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        ok = ok && static_cast<unsigned>(a[j] >> 32) == tag && static_cast<unsigned>(b[j] >> 32) == tag;
+      if (!ok && clock64() - t0 > 4000000000LL) {  // a bug must trap, not hang
+        printf("wacil: statistics exchange timeout (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    } while (!ok);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      acc.x += __uint_as_float(static_cast<unsigned>(a[j]));
+      acc.y += __uint_as_float(static_cast<unsigned>(b[j]));
     }
   }
   return acc;
@@ -610,10 +627,15 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
+    // this launch's tag: the launch counter p.grid_bar[0] (bumped by the last CTA to leave, below) + 1
+    unsigned tag;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(p.grid_bar) : "memory");
+    ++tag;
+    unsigned long long* const rows64 = reinterpret_cast<unsigned long long*>(p.stats);
     {
-      // this CTA's partial sums -> its own row of the [grid][2*nc] table (plain stores, released by the grid barrier):
-      // no atomics anywhere on the BatchNorm sums, so the statistics are bit-reproducible run to run
-      float* g0 = p.stats + static_cast<size_t>(blockIdx.x) * (2 * ncr);
+      // this CTA's partial sums -> its own row of the [grid][2*nc] table of {value, tag} words.  No atomics anywhere on
+      // the BatchNorm sums, so the statistics are bit-reproducible run to run.
+      unsigned long long* g0 = rows64 + static_cast<size_t>(blockIdx.x) * (2 * ncr);
       for (int c = tid128; c < p.nc; c += ET) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -621,8 +643,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           a0 += s_part[(2 * wv + 0) * 64 + c];
           a1 += s_part[(2 * wv + 1) * 64 + c];
         }
-        g0[c] = a0;
-        g0[ncr + c] = a1;
+        const unsigned long long hi = static_cast<unsigned long long>(tag) << 32;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g0 + c), "l"(hi | __float_as_uint(a0)) : "memory");
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g0 + ncr + c), "l"(hi | __float_as_uint(a1)) : "memory");
       }
     }
     // what the per-channel constants need besides the grid-wide sums is fetched before the barrier (nc <= 64 <= 128
@@ -635,27 +658,34 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       rmean = p.running_mean[tid128];
       rvar = p.running_var[tid128];
     }
-    grid_barrier_epi<ET>(p.grid_bar, tid128);
-    if (tid128 == 0) WACIL_STAMP(8);  // grid barrier passed
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels);
+    float* s_scr = s_stats + (2 * EW + 5) * 64;  // [S][V] = 2 * ET floats, beside the per-warp partials still being read
     {
-      // every CTA sums the per-CTA partial rows in the same fixed order: thread (slice, 4 values) takes rows slice,
-      // slice + S, ... (16-byte loads, all independent), the S slice sums are combined in order below
-      const int V = 2 * p.nc, Q = V / 4, S = ET / Q;  // 8/16/32 column groups -> 16/8/4 row slices
-      const int cg = tid128 % Q, sl = tid128 / Q;
-      // (the per-warp partials are dead after the stores above: their 512 floats serve as the [S][V] scratch)
-      *reinterpret_cast<float4*>(s_part + sl * V + 4 * cg) =
-          ordered_row_sum4(p.stats, V, cg, sl, S, static_cast<int>(gridDim.x));
+      // every CTA sums the per-CTA rows in the same fixed order: thread (slice, 2 values) takes rows slice, slice + S,
+      // ... (16-byte loads of two tagged words, all independent), the S slice sums are combined in order below
+      const int V = 2 * p.nc, Q = V / 2, S = ET / Q;  // 16/32/64 word pairs per row -> 8/4/2 row slices
+      const int u = tid128 % Q, sl = tid128 / Q;
+      const float2 t = tagged_row_sum2<10>(rows64, V, u, sl, S, static_cast<int>(gridDim.x), tag);
+      *reinterpret_cast<float2*>(s_scr + sl * V + 2 * u) = t;
     }
+    if (tid128 == 0) WACIL_STAMP(8);  // every CTA's sums seen
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+    if (tid128 == 0) {
+      // launch counter, off the critical path: the last CTA to check out knows every CTA has read every row
+      if (atomicAdd(p.grid_bar + 1, 1u) == gridDim.x - 1) {
+        p.grid_bar[1] = 0u;
+        __threadfence();
+        p.grid_bar[0] = tag;
+      }
+    }
     if (tid128 < p.nc) {
       const int c = tid128;
       float t0 = 0.f, t1 = 0.f;
-      const int V = 2 * p.nc, S = 4 * ET / V;
+      const int V = 2 * p.nc, S = 2 * ET / V;
       for (int sl = 0; sl < S; ++sl) {
-        t0 += s_part[sl * V + c];
-        t1 += s_part[sl * V + p.nc + c];
+        t0 += s_scr[sl * V + c];
+        t1 += s_scr[sl * V + p.nc + c];
       }
       if (p.epi == EPI_BN_TRAIN) {
         const float mean = t0 / cnt;
@@ -1179,6 +1209,7 @@ inline void conv_pick_rmerge_pipeline(int kc, int nc, int Ht, int Wo, int& tps, 
 // those variants are as fast or faster in isolation: the kernels are latency-bound, a second resident CTA hides it.
 // (The occupancy API reports 1 CTA/SM for any tcgen05 kernel — csrc/occ_probe.cu — so a cooperative grid is <= #SMs.)
 constexpr size_t kConvSmemMax = 113 * 1024;  // 2 x (113 KB + 1 KB reserved) = 228 KB per SM
+constexpr size_t kConvSmemWide = 208 * 1024;  // launches on <= half of the SMs (they do not share an SM with a side branch)
 inline void conv_pick_pipeline(int kc, int nc, int taps, int& tps, int& stages, size_t total_budget = kConvSmemMax) {
   const size_t w = ((size_t)taps * nc * kc * 2 + 1023) & ~size_t(1023);
   const size_t budget = total_budget - 6144 - w;  // alignment slack, barriers, per-channel scratch

@@ -97,13 +97,13 @@ static int run_conv(const Case& c) {
   CK(cudaMalloc(&dx, nx * 2));
   CK(cudaMalloc(&dw, nw * 2));
   CK(cudaMalloc(&dy, ny * 2));
-  CK(cudaMalloc(&dstats, 296 * 2 * c.nc * 4));  // room for the fused kernels' per-CTA partial rows
+  CK(cudaMalloc(&dstats, 296 * 2 * c.nc * 8));  // room for the fused kernels' per-CTA partial rows
   CK(cudaMalloc(&dbias, c.nc * 4));
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, wb.data(), nw * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dbias, bias.data(), c.nc * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dy, 0xFF, ny * 2));
-  CK(cudaMemset(dstats, 0, 296 * 2 * c.nc * 4));
+  CK(cudaMemset(dstats, 0, 296 * 2 * c.nc * 8));
   if (c.res_mode) {
     CK(cudaMalloc(&dres, rb.size() * 2));
     CK(cudaMemcpy(dres, rb.data(), rb.size() * 2, cudaMemcpyHostToDevice));

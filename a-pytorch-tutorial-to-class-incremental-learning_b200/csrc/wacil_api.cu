@@ -188,8 +188,8 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.wbuf = c.take(wel * 2);
   o.bias = c.take(sel * 4);
   // per layer [CTAs][2*cout] partial BatchNorm sums of the fused kernels (forward: sum / sumsq; backward: d-beta / d-gamma)
-  o.stats = c.take(sel * 4 * num_sms());
-  o.bstats = c.take(sel * 4 * num_sms());
+  o.stats = c.take(sel * 8 * num_sms());   // per layer [CTAs][2*cout] x {value, tag} words (fused forward)
+  o.bstats = c.take(sel * 8 * num_sms());  // the same for the fused backward
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
@@ -312,7 +312,7 @@ int conv_attrs() {
   static bool set = false;
   if (set) return 0;
   cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kConvSmemMax));
+                                       static_cast<int>(kConvSmemWide));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -347,7 +347,7 @@ int conv_max_resident(size_t smem) {
 }
 
 int launch_conv(const ConvLaunch& c, cudaStream_t st) {
-  if (c.smem > kConvSmemMax) return fail(WACIL_E_SHAPE, "conv configuration needs %zu bytes of shared memory", c.smem);
+  if (c.smem > kConvSmemWide) return fail(WACIL_E_SHAPE, "conv configuration needs %zu bytes of shared memory", c.smem);
   { int e0 = conv_attrs(); if (e0) return e0; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c.grid);
@@ -658,9 +658,14 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   const bool pdl = pdl_enabled();
   n->engine = engine_kind();
   const bool per_layer = n->engine == ENGINE_LAYER;
+  const bool wide_ok = !per_layer || env_int("WACIL_WIDE", 1, 0, 1) != 0;
   const int fwd_len = per_layer ? 1 : chain_fwd_len(), bwd_len = per_layer ? 1 : chain_bwd_len();
   ce = cudaMemset(n->ws + n->off.gbar, 0, 64);
-  if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "grid barrier clear"); }
+  // the tagged statistics rows: tag 0 = "never written" (the launch counter in gbar starts at 0, the first tag is 1);
+  // a recycled workspace may hold rows of an older plan whose small tags would otherwise be taken for this plan's
+  if (ce == cudaSuccess) ce = cudaMemset(n->ws + n->off.stats, 0, n->off.stat_elems * 8 * num_sms());
+  if (ce == cudaSuccess) ce = cudaMemset(n->ws + n->off.bstats, 0, n->off.stat_elems * 8 * num_sms());
+  if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "launch counter / statistics rows clear"); }
   // ENGINE_LAYER: finish a chain element as a stand-alone conv_gemm_kernel launch
   auto finish_layer_launch = [&](ConvLaunch& c, int grid, bool first_of_forward) -> int {
     c.grid = grid;
@@ -671,11 +676,14 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     c.p.pdl = pdl ? 1 : 0;
     c.p.w_early = first_of_forward ? 0 : 1;  // the operand copies are older than the upstream kernel, except right after cast_weights
     c.smem = conv_smem_bytes(c.p);
-    while (c.smem > kConvSmemMax && c.p.stages > 2) {  // the ring was sized for the chain kernel's slightly larger budget
+    // a launch on at most half of the SMs (the 8x8 layers: 64 tiles) does not share its SMs with the side branches'
+    // CTAs, so the half-SM footprint rule (kConvSmemMax) does not bind it
+    const size_t cap = wide_ok && grid * 2 <= num_sms() ? kConvSmemWide : kConvSmemMax;
+    while (c.smem > cap && c.p.stages > 2) {  // the ring was sized for the chain kernel's slightly larger budget
       --c.p.stages;
       c.smem = conv_smem_bytes(c.p);
     }
-    if (c.smem > kConvSmemMax) return fail(WACIL_E_SHAPE, "layer launch needs %zu bytes of shared memory", c.smem);
+    if (c.smem > cap) return fail(WACIL_E_SHAPE, "layer launch needs %zu bytes of shared memory", c.smem);
     return 0;
   };
   std::vector<size_t> so(nl);
@@ -704,7 +712,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     for (int l = first; l < first + count; ++l) w_max = std::max(w_max, w_tile_bytes(n->L[l].cin_pad, n->L[l].cout));
     int group_tiles = 0;
     for (int l = first; l < first + count; ++l) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[l].H_out));
-    const size_t ring = chain_ring_bytes(w_max, fwd_ew, !per_layer && group_tiles * 2 <= num_sms());
+    const size_t ring = chain_ring_bytes(w_max, fwd_ew, wide_ok && group_tiles * 2 <= num_sms());
     int max_tiles = 0;
     for (int l = first; l < first + count; ++l) {
       const LayerDesc& d = n->L[l];
@@ -715,7 +723,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         if (e) { delete n; return e; }
         c.p.out = n->at<__nv_bfloat16>(n->off.y[l]);
         c.p.act_out = n->at<__nv_bfloat16>(n->off.a[l]);
-        c.p.stats = n->at<float>(n->off.stats) + so[l] * num_sms();  // [grid <= SMs][2*cout] partial sums
+        c.p.stats = n->at<float>(n->off.stats) + 2 * so[l] * num_sms();  // [grid <= SMs][2*cout] tagged partial sums
         c.p.saved = n->at<float>(n->off.saved) + so[l];
         c.p.gamma = n->params + d.gamma_off;
         c.p.beta = n->params + d.beta_off;
@@ -835,7 +843,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       int group_tiles = 0;
       for (int el = first; el < first + count; ++el) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[layer_of(el)].H_in));
-      const size_t ring = chain_ring_bytes(w_max, ew_fused, !per_layer && group_tiles * 2 <= num_sms());
+      const size_t ring = chain_ring_bytes(w_max, ew_fused, wide_ok && group_tiles * 2 <= num_sms());
       int max_tiles = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el), pl = l - 1;
@@ -859,7 +867,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
         g.p.gamma = n->params + pd.gamma_off;
         g.p.dgamma = n->grads + pd.gamma_off;
         g.p.dbeta = n->grads + pd.beta_off;
-        g.p.stats = n->at<float>(n->off.bstats) + so[pl] * num_sms();
+        g.p.stats = n->at<float>(n->off.bstats) + 2 * so[pl] * num_sms();
         g.p.gy = n->at<__nv_bfloat16>(n->off.gy[pl]);
         g.p.gy_up = pd.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[pl]) : nullptr;
         g.p.gz = (pl >= 2 && pl % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((pl - 2) / 2) % 2]) : nullptr;
@@ -1127,7 +1135,7 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     const int lanes = 256 / (d.cout / 8);
     int rgrid = static_cast<int>((bp.num_pixels + lanes - 1) / lanes);
     if (rgrid > num_sms()) rgrid = num_sms();
-    bp.part = n->at<float>(n->off.bstats) + soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no chain element uses them)
+    bp.part = n->at<float>(n->off.bstats) + 2 * soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no chain element uses them)
     bp.nparts = rgrid;
     bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
     WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
@@ -1623,7 +1631,7 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
 }
 
 size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout) {
-  return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 8 * num_sms();  // grid barrier + [CTAs][2*cout] partial sums
+  return 64 + static_cast<size_t>(cout > 0 ? cout : 0) * 16 * num_sms();  // launch counter + [CTAs][2*cout] tagged sums
 }
 
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,

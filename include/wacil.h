@@ -273,10 +273,12 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
                         int cout, int stride, void* stream);
 /* The fused forward kernel of one layer (resnet.py:43-53): y = conv3x3(x, w) (bf16), batch statistics of y,
  * a = ReLU(BatchNorm(y) + shortcut) (bf16), running statistics updated (momentum 0.1, unbiased variance), in ONE
- * cooperative launch (grid barrier between the statistics and the normalisation; accumulators stay in TMEM).
+ * cooperative launch (the CTAs exchange their per-channel partial sums between the statistics and the normalisation;
+ * accumulators stay in TMEM).
  * res_mode: 0 none, 1 res has the shape of a, 2 option-A shortcut (res is [N][2Ho][2Wo][cout/2], resnet.py:15-17).
  * mean_rstd: fp32 [2*cout] batch mean and 1/sqrt(var+eps) out.  workspace: wacil_conv3x3_bn_relu_workspace_bytes(cout)
- * bytes whose first 64 bytes are zero (barrier counters, left zero). */
+ * bytes, ALL zero before the first call and afterwards written by this function only (a launch counter and the
+ * tagged partial-sum rows: a launch recognises its own rows by the counter value, so nothing is cleared per call). */
 size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout);
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
                           int res_mode, void* y, void* a, float* mean_rstd, float* running_mean, float* running_var,
