@@ -54,7 +54,7 @@ struct ConvGemmParams {
   int res_c;                 // residual channels (<= nc); channels >= res_c get no residual (zero pad)
   // ---- fused modes ----
   int acc_stages;            // TMEM accumulator stages: 2 (ring) or >= tiles per CTA (fused modes)
-  unsigned* grid_bar;        // [2] self-resetting grid barrier counters (zero at rest)
+  unsigned* grid_bar;        // [2] this layer's launch counter + check-out counter (zero before the first launch)
   // EPI_BN_TRAIN: out = y (raw), act_out = a; stats/gamma/beta/running/saved as in bn_apply_fwd
   __nv_bfloat16* act_out;
   const float* gamma;
@@ -232,19 +232,20 @@ __device__ __forceinline__ float4 ordered_row_sum4(const float* __restrict__ tab
   return acc;
 }
 
-// The statistics exchange of the fused kernels without a barrier: a CTA publishes its partial sums as 8-byte words
-// {value, tag} (one 64-bit store each: single-copy atomic, so a reader that sees the tag sees the value) and every CTA
-// polls the rows of all CTAs until they carry this launch's tag.  No release fence, no arrival counter, no separate
-// "barrier passed -> now read the data" round trip: publishing costs one store, the wait IS the read.
-// Fixed-order sum of rows first, first + step, ... (< rows) of a [rows][V] table of such words, values 2u and 2u + 1;
-// NB rows are in flight together (one L2 round trip per batch once they are published).
+// The statistics exchange of the fused kernels without a barrier.  A CTA publishes its per-channel partial sums as
+// complemented fp32 words (~bits: an all-zero word = "not written yet"; 32-bit stores are single-copy atomic, so every
+// word validates itself) into its own row of a [CTAs][V] table, and every CTA polls all rows until no word is zero.
+// No release fence, no arrival counter, no separate "barrier passed -> now read the data" round trip: publishing costs
+// one store, the wait IS the read.  The table is double-buffered on the parity of the layer's launch counter: a launch
+// clears its row of the OTHER buffer (last read one launch ago, next written one launch ahead).
+// Fixed-order sum of rows first, first + step, ... (< rows), words [4 cg, 4 cg + 4); NB rows are in flight together
+// (one L2 round trip per batch once they are published: the whole 148 x 32 table of a 16-channel layer is ONE batch).
 template <int NB>
-__device__ __forceinline__ float2 tagged_row_sum2(const unsigned long long* __restrict__ table, int V, int u, int first,
-                                                  int step, int rows, unsigned tag) {
-  float2 acc = make_float2(0.f, 0.f);
-  const unsigned long long filler = static_cast<unsigned long long>(tag) << 32;  // value +0.0f under the right tag
+__device__ __forceinline__ float4 published_row_sum4(const unsigned* __restrict__ table, int V, int cg, int first,
+                                                     int step, int rows) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r0 = first; r0 < rows; r0 += step * NB) {
-    unsigned long long a[NB], b[NB];
+    uint4 t[NB];
     const long long t0 = clock64();
     bool ok;
     do {
@@ -252,19 +253,17 @@ __device__ __forceinline__ float2 tagged_row_sum2(const unsigned long long* __re
       for (int j = 0; j < NB; ++j) {
         const int r = r0 + j * step;
         if (r < rows) {
-          asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];"
-                       : "=l"(a[j]), "=l"(b[j])
-                       : "l"(table + static_cast<size_t>(r) * V + 2 * u)
+          asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(t[j].x), "=r"(t[j].y), "=r"(t[j].z), "=r"(t[j].w)
+                       : "l"(table + static_cast<size_t>(r) * V + 4 * cg)
                        : "memory");
         } else {
-          a[j] = filler;
-          b[j] = filler;
+          t[j] = make_uint4(~0u, ~0u, ~0u, ~0u);  // +0.0f, published
         }
       }
       ok = true;
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        ok = ok && static_cast<unsigned>(a[j] >> 32) == tag && static_cast<unsigned>(b[j] >> 32) == tag;
+      for (int j = 0; j < NB; ++j) ok = ok && t[j].x != 0u && t[j].y != 0u && t[j].z != 0u && t[j].w != 0u;
       if (!ok && clock64() - t0 > 4000000000LL) {  // a bug must trap, not hang
         printf("wacil: statistics exchange timeout (block %d)\n", blockIdx.x);
         __trap();
@@ -272,8 +271,10 @@ __device__ __forceinline__ float2 tagged_row_sum2(const unsigned long long* __re
     } while (!ok);
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      acc.x += __uint_as_float(static_cast<unsigned>(a[j]));
-      acc.y += __uint_as_float(static_cast<unsigned>(b[j]));
+      acc.x += __uint_as_float(~t[j].x);
+      acc.y += __uint_as_float(~t[j].y);
+      acc.z += __uint_as_float(~t[j].z);
+      acc.w += __uint_as_float(~t[j].w);
     }
   }
   return acc;
@@ -627,15 +628,18 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
     if (tid128 == 0) WACIL_STAMP(7);  // phase 1 done
-    // this launch's tag: the launch counter p.grid_bar[0] (bumped by the last CTA to leave, below) + 1
-    unsigned tag;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"(p.grid_bar) : "memory");
-    ++tag;
-    unsigned long long* const rows64 = reinterpret_cast<unsigned long long*>(p.stats);
+    // this layer's launch counter p.grid_bar[0] (bumped by the last CTA to leave, below) picks the table buffer
+    unsigned launch_no;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(launch_no) : "l"(p.grid_bar) : "memory");
+    const size_t table_words = static_cast<size_t>(gridDim.x) * (2 * ncr);
+    unsigned* const rows_cur = reinterpret_cast<unsigned*>(p.stats) + (launch_no & 1u) * table_words;
     {
-      // this CTA's partial sums -> its own row of the [grid][2*nc] table of {value, tag} words.  No atomics anywhere on
-      // the BatchNorm sums, so the statistics are bit-reproducible run to run.
-      unsigned long long* g0 = rows64 + static_cast<size_t>(blockIdx.x) * (2 * ncr);
+      // this CTA's partial sums -> its own row of the [grid][2*nc] table (complemented words, see published_row_sum4);
+      // its row of the other buffer back to "not written".  No atomics anywhere on the BatchNorm sums, so the
+      // statistics are bit-reproducible run to run.
+      unsigned* g0 = rows_cur + static_cast<size_t>(blockIdx.x) * (2 * ncr);
+      unsigned* z0 = reinterpret_cast<unsigned*>(p.stats) + ((launch_no & 1u) ^ 1u) * table_words +
+                     static_cast<size_t>(blockIdx.x) * (2 * ncr);
       for (int c = tid128; c < p.nc; c += ET) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -643,9 +647,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           a0 += s_part[(2 * wv + 0) * 64 + c];
           a1 += s_part[(2 * wv + 1) * 64 + c];
         }
-        const unsigned long long hi = static_cast<unsigned long long>(tag) << 32;
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g0 + c), "l"(hi | __float_as_uint(a0)) : "memory");
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(g0 + ncr + c), "l"(hi | __float_as_uint(a1)) : "memory");
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(g0 + c), "r"(~__float_as_uint(a0)) : "memory");
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(g0 + ncr + c), "r"(~__float_as_uint(a1)) : "memory");
+        z0[c] = 0u;
+        z0[ncr + c] = 0u;
       }
     }
     // what the per-channel constants need besides the grid-wide sums is fetched before the barrier (nc <= 64 <= 128
@@ -660,14 +665,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     // ---------------- per-channel constants from the grid-wide sums
     const float cnt = static_cast<float>(p.num_pixels);
-    float* s_scr = s_stats + (2 * EW + 5) * 64;  // [S][V] = 2 * ET floats, beside the per-warp partials still being read
+    float* s_scr = s_stats + (2 * EW + 5) * 64;  // [S][V] = 4 * ET floats, beside the per-warp partials still being read
     {
-      // every CTA sums the per-CTA rows in the same fixed order: thread (slice, 2 values) takes rows slice, slice + S,
-      // ... (16-byte loads of two tagged words, all independent), the S slice sums are combined in order below
-      const int V = 2 * p.nc, Q = V / 2, S = ET / Q;  // 16/32/64 word pairs per row -> 8/4/2 row slices
-      const int u = tid128 % Q, sl = tid128 / Q;
-      const float2 t = tagged_row_sum2<10>(rows64, V, u, sl, S, static_cast<int>(gridDim.x), tag);
-      *reinterpret_cast<float2*>(s_scr + sl * V + 2 * u) = t;
+      // every CTA sums the per-CTA rows in the same fixed order: thread (slice, 4 values) takes rows slice, slice + S,
+      // ... (16-byte loads, all independent), the S slice sums are combined in order below
+      const int V = 2 * p.nc, Q = V / 4, S = ET / Q;  // 8/16/32 column groups -> 16/8/4 row slices
+      const int cg = tid128 % Q, sl = tid128 / Q;
+      *reinterpret_cast<float4*>(s_scr + sl * V + 4 * cg) =
+          published_row_sum4<10>(rows_cur, V, cg, sl, S, static_cast<int>(gridDim.x));
     }
     if (tid128 == 0) WACIL_STAMP(8);  // every CTA's sums seen
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
@@ -676,13 +681,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       if (atomicAdd(p.grid_bar + 1, 1u) == gridDim.x - 1) {
         p.grid_bar[1] = 0u;
         __threadfence();
-        p.grid_bar[0] = tag;
+        p.grid_bar[0] = launch_no + 1u;
       }
     }
     if (tid128 < p.nc) {
       const int c = tid128;
       float t0 = 0.f, t1 = 0.f;
-      const int V = 2 * p.nc, S = 2 * ET / V;
+      const int V = 2 * p.nc, S = 4 * ET / V;
       for (int sl = 0; sl < S; ++sl) {
         t0 += s_scr[sl * V + c];
         t1 += s_scr[sl * V + p.nc + c];

@@ -188,12 +188,12 @@ void carve_workspace(const std::vector<LayerDesc>& L, int batch, int mode, Offse
   o.wbuf = c.take(wel * 2);
   o.bias = c.take(sel * 4);
   // per layer [CTAs][2*cout] partial BatchNorm sums of the fused kernels (forward: sum / sumsq; backward: d-beta / d-gamma)
-  o.stats = c.take(sel * 8 * num_sms());   // per layer [CTAs][2*cout] x {value, tag} words (fused forward)
+  o.stats = c.take(sel * 8 * num_sms());   // per layer two buffers of [CTAs][2*cout] words (fused forward)
   o.bstats = c.take(sel * 8 * num_sms());  // the same for the fused backward
   o.saved = c.take(sel * 4);
   o.a0 = c.take(static_cast<size_t>(batch) * 32 * 32 * 16 * 2);
   o.dfeats = c.take(static_cast<size_t>(batch) * kFeatDim * 4);
-  o.gbar = c.take(64);
+  o.gbar = c.take(64 + 16 * nl);  // per fused launch {launch counter, check-out counter}: forward layer l at word 2 l, backward at 2 (nl + l)
   // chain tables: one ChainLayer + two tensor maps per chain element (forward: nl; backward: nl - 1)
   o.ctab = c.take(2 * nl * sizeof(ChainLayer));
   o.cmaps = c.take(2 * nl * 2 * sizeof(CUtensorMap));
@@ -660,17 +660,16 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   const bool per_layer = n->engine == ENGINE_LAYER;
   const bool wide_ok = !per_layer || env_int("WACIL_WIDE", 1, 0, 1) != 0;
   const int fwd_len = per_layer ? 1 : chain_fwd_len(), bwd_len = per_layer ? 1 : chain_bwd_len();
-  ce = cudaMemset(n->ws + n->off.gbar, 0, 64);
-  // the tagged statistics rows: tag 0 = "never written" (the launch counter in gbar starts at 0, the first tag is 1);
-  // a recycled workspace may hold rows of an older plan whose small tags would otherwise be taken for this plan's
+  ce = cudaMemset(n->ws + n->off.gbar, 0, 64 + 16 * nl);
+  // the published statistics rows: a zero word = "not written" (a recycled workspace may hold an older plan's rows)
   if (ce == cudaSuccess) ce = cudaMemset(n->ws + n->off.stats, 0, n->off.stat_elems * 8 * num_sms());
   if (ce == cudaSuccess) ce = cudaMemset(n->ws + n->off.bstats, 0, n->off.stat_elems * 8 * num_sms());
   if (ce != cudaSuccess) { delete n; return cuda_fail(ce, "launch counter / statistics rows clear"); }
   // ENGINE_LAYER: finish a chain element as a stand-alone conv_gemm_kernel launch
-  auto finish_layer_launch = [&](ConvLaunch& c, int grid, bool first_of_forward) -> int {
+  auto finish_layer_launch = [&](ConvLaunch& c, int grid, bool first_of_forward, int counter_slot) -> int {
     c.grid = grid;
     c.p.acc_stages = c.p.epi >= EPI_BN_TRAIN ? (c.p.num_tiles + grid - 1) / grid : 2;
-    c.p.grid_bar = n->at<unsigned>(n->off.gbar);
+    c.p.grid_bar = n->at<unsigned>(n->off.gbar) + 2 * counter_slot;
     c.p.eps = kBnEps;
     c.p.momentum = kBnMomentum;
     c.p.pdl = pdl ? 1 : 0;
@@ -801,7 +800,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     cpn.cp.dbg = nullptr;
     cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), fwd_ew);
     if (!per_layer && static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
-    if (per_layer && (e = finish_layer_launch(n->fprop[first], cpn.grid, mode == WACIL_NET_TRAIN && first == 0))) { delete n; return e; }
+    if (per_layer && (e = finish_layer_launch(n->fprop[first], cpn.grid, mode == WACIL_NET_TRAIN && first == 0, first))) { delete n; return e; }
     n->fchains.push_back(cpn);
   }
 
@@ -907,7 +906,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       cpn.cp.dbg = nullptr;
       cpn.smem = chain_smem_bytes(w_max, static_cast<uint32_t>(ring), ew_fused);
       if (!per_layer && static_cast<int>(ci) >= kSyncCounters) { delete n; return fail(WACIL_E_SHAPE, "too many chain launches"); }
-      if (per_layer && (e = finish_layer_launch(n->dgrad[layer_of(first)], cpn.grid, false))) { delete n; return e; }
+      if (per_layer && (e = finish_layer_launch(n->dgrad[layer_of(first)], cpn.grid, false, nl + layer_of(first)))) { delete n; return e; }
       n->bchains.push_back(cpn);
     }
   }

@@ -256,7 +256,9 @@ def conv3x3_bn_relu(x, w, gamma, beta, running_mean, running_var, res=None, res_
     y = torch.empty((N, H // stride, W_ // stride, cout), dtype=torch.bfloat16, device=x.device)
     a = torch.empty_like(y)
     saved = torch.empty((2, cout), dtype=torch.float32, device=x.device)
-    ws = _workspace("convbn", lib().wacil_conv3x3_bn_relu_workspace_bytes(cout), x.device)
+    # one workspace per problem shape: the kernel's published-sum rows are laid out by (grid, cout) and only ever
+    # cleared by the launches themselves
+    ws = _workspace(("convbn", N, H, cin, cout, stride), lib().wacil_conv3x3_bn_relu_workspace_bytes(cout), x.device)
     check(lib().wacil_conv3x3_bn_relu(x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                       res.data_ptr() if res is not None else None, int(res_mode), y.data_ptr(),
                                       a.data_ptr(), saved.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),

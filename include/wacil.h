@@ -277,8 +277,9 @@ int wacil_conv3x3_fprop(const void* x, const void* w, void* y, float* stats, int
  * accumulators stay in TMEM).
  * res_mode: 0 none, 1 res has the shape of a, 2 option-A shortcut (res is [N][2Ho][2Wo][cout/2], resnet.py:15-17).
  * mean_rstd: fp32 [2*cout] batch mean and 1/sqrt(var+eps) out.  workspace: wacil_conv3x3_bn_relu_workspace_bytes(cout)
- * bytes, ALL zero before the first call and afterwards written by this function only (a launch counter and the
- * tagged partial-sum rows: a launch recognises its own rows by the counter value, so nothing is cleared per call). */
+ * bytes, ALL zero before the first call and afterwards used by calls of this function with the same problem shape
+ * only (a launch counter and two buffers of published partial-sum rows; every launch clears the buffer the next one
+ * writes, so nothing is cleared per call). */
 size_t wacil_conv3x3_bn_relu_workspace_bytes(int cout);
 int wacil_conv3x3_bn_relu(const void* x, const void* w, const float* gamma, const float* beta, const void* res,
                           int res_mode, void* y, void* a, float* mean_rstd, float* running_mean, float* running_var,
