@@ -676,14 +676,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     if (tid128 == 0) WACIL_STAMP(8);  // every CTA's sums seen
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
-    if (tid128 == 0) {
-      // launch counter, off the critical path: the last CTA to check out knows every CTA has read every row
-      if (atomicAdd(p.grid_bar + 1, 1u) == gridDim.x - 1) {
-        p.grid_bar[1] = 0u;
-        __threadfence();
-        p.grid_bar[0] = launch_no + 1u;
-      }
-    }
+    // check-out ticket: taken now (this CTA has read every row), looked at after phase 2 — the atomic's round trip
+    // then lies neither on the path to the constants nor between the last store and the end of the kernel
+    unsigned ticket = 0;
+    if (tid128 == 0) ticket = atomicAdd(p.grid_bar + 1, 1u);
     if (tid128 < p.nc) {
       const int c = tid128;
       float t0 = 0.f, t1 = 0.f;
@@ -717,6 +713,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+    if (tid128 == 0) WACIL_STAMP(13);  // per-channel constants ready
     // ---------------- phase 2: normalise (forward) / BN backward, from TMEM only (accumulator or gz, and the stash)
     as = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
@@ -769,7 +766,15 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         }
       }
     }
-    if (tid128 == 0) WACIL_STAMP(9);  // phase 2 done
+    if (tid128 == 0) {
+      WACIL_STAMP(9);  // phase 2 done
+      // launch counter: the last CTA to check out knows that every CTA has read every row of this launch's table
+      if (ticket == gridDim.x - 1) {
+        p.grid_bar[1] = 0u;
+        __threadfence();
+        p.grid_bar[0] = launch_no + 1u;
+      }
+    }
   } else if (warp < 6) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;
@@ -861,7 +866,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   if (threadIdx.x == 0) WACIL_STAMP(10);  // teardown done
 }
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __maxnreg__(128)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {
   conv_gemm_body(mapA, mapW, p);

@@ -196,6 +196,7 @@ static int run_conv(const Case& c) {
         printf("   cta %3d:", b);
         for (int k = 1; k <= 10; ++k)
           if (h[b * 16 + k]) printf(" %s %lld", names[k], h[b * 16 + k] - h[b * 16]);
+        if (h[b * 16 + 13]) printf(" [constants %lld]", h[b * 16 + 13] - h[b * 16]);
         printf("  | producer blocked on free slots %lld, MMA thread blocked on operands %lld  (cycles)\n", h[b * 16 + 11],
                h[b * 16 + 12]);
       }
