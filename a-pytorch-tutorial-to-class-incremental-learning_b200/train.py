@@ -191,6 +191,29 @@ class _StepState:
         self.graph_fb = None   # forward + loss + backward (+ SGD when world_size == 1)
         self.graph_opt = None  # SGD after the all-reduce (world_size > 1)
         self.warm = 0
+        self.stage = None      # host-fed steps: two device staging buffers filled by the copy stream (see stage_in)
+        self.flip = 0
+
+    def stage_in(self, tr, x, y):
+        """Host batch -> the step's input buffers without stalling the compute stream on PCIe: the host-to-device copy
+        goes to a staging buffer on the trainer's copy stream (it runs under the previous step, which the host has
+        already queued), the compute stream only waits for its event and moves the batch device-to-device."""
+        if self.stage is None:
+            self.stage = [(torch.empty_like(self.x), torch.empty_like(self.y), torch.cuda.Event(), torch.cuda.Event())
+                          for _ in range(2)]
+        sx, sy, ready, free = self.stage[self.flip]
+        self.flip ^= 1
+        cur = torch.cuda.current_stream()
+        cs = tr.copy_stream
+        cs.wait_event(free)  # the device-to-device read of this buffer two steps ago (recorded below; no-op at first)
+        with torch.cuda.stream(cs):
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+            ready.record(cs)
+        cur.wait_event(ready)
+        self.x.copy_(sx, non_blocking=True)
+        self.y.copy_(sy, non_blocking=True)
+        free.record(cur)
 
 
 class TaskTrainer:
@@ -214,6 +237,7 @@ class TaskTrainer:
         self.overlap = overlap
         self.side_t = torch.cuda.Stream(device=self.device) if overlap else None
         self.side_w = torch.cuda.Stream(device=self.device) if overlap else None
+        self.copy_stream = torch.cuda.Stream(device=self.device)  # host-fed steps: H2D under the previous step
         self.peer = None
         if world_size > 1 and fused_allreduce:
             self.peer = self._setup_peer_memory(process_group)
@@ -358,8 +382,11 @@ class TaskTrainer:
         in pinned host memory (copied asynchronously) or on the device.  Returns the device tensor [ce, kd, loss, top1
         count] of this step (no host sync)."""
         st = self._state(x.shape[0])
-        st.x.copy_(x, non_blocking=True)
-        st.y.copy_(y, non_blocking=True)
+        if x.is_cuda:
+            st.x.copy_(x, non_blocking=True)
+            st.y.copy_(y, non_blocking=True)
+        else:
+            st.stage_in(self, x, y)
         return self._execute(st)
 
     def step_from_store(self, taskset, idx, aug=None):

@@ -385,6 +385,26 @@ def test_training_is_bit_reproducible(w):
     assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
 
 
+def test_host_fed_steps_equal_device_fed_steps(w):
+    """TaskTrainer.step with pinned host batches (the reference's loader hands the loop host tensors,
+    template.py:255-257) stages them through two device buffers on a copy stream; five steps — more than the two
+    staging buffers, so both are reused — must leave exactly the parameters the device-fed steps leave."""
+    depth, heads = 20, [10, 10]
+    sd, tsd = _mild_state(depth, heads, 51), _mild_state(depth, heads[:1], 52)
+    gen = torch.Generator().manual_seed(9)
+    xs = [torch.randn(64, 3, 32, 32, generator=gen).pin_memory() for _ in range(5)]
+    ys = [torch.randint(0, 20, (64,), generator=gen).pin_memory() for _ in range(5)]
+    outs = []
+    for host in (False, True):
+        m = _model_from(w, depth, sd).train()
+        t = _model_from(w, depth, tsd).copy().freeze()
+        tr = w.TaskTrainer(m, t, 10, lr=0.05, lambda_kd=0.5, use_graph=True)
+        ls = [tr.step(x if host else x.cuda(), y if host else y.cuda()).clone() for x, y in zip(xs, ys)]
+        torch.cuda.synchronize()
+        outs.append((m.arena.data.clone(), torch.stack(ls)))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("names", [["fc"], ["backbone"]])
 def test_partial_freeze_pins_its_range(w, names):
     """CilModel.freeze(["fc"]) / freeze(["backbone"]) (template.py:128-144): the optimiser leaves the frozen element range
