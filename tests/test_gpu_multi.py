@@ -106,7 +106,7 @@ def _main_worker(rank, world, port, q, tmp):
     p = argparse.ArgumentParser(parents=[w.get_args_parser()])
     w.train.add_runner_args(p)
     args = p.parse_args(["--data_set", "synthetic", "--nb_classes", "6", "--num_bases", "2", "--increment", "2",
-                         "--backbone", "resnet20", "--batch_size", "32", "--num_epochs", "10", "--lr", "0.05",
+                         "--backbone", "resnet20", "--batch_size", "16", "--num_epochs", "10", "--lr", "0.05",
                          "--memory_size", "40", "--synthetic_per_class", "96", "--synthetic_val_per_class", "32",
                          "--eval_every_epoch", "5", "--max_tasks", "2", "--checkpoint_dir", os.path.join(tmp, "ck")])
     captured = {}
@@ -157,4 +157,6 @@ def test_template_main_keeps_ranks_identical(tmp_path):
         assert all(ok.values()), (rank, ok)   # teacher, herding features and exemplar memory identical on every rank
         assert len(acc) == 2 and nmem > 0
     assert accs[0] == accs[1]  # the meter is all-reduced: same numbers everywhere
-    assert accs[0][0] > 60.0, accs  # two separable classes, 30 steps per rank: far above the 50 % of chance
+    # two separable classes, global batch 32 (the single-GPU run of this configuration reaches 100 %; at global batch 64
+    # the 30 steps are too few: 53 %, tools/synthetic_run.py): far above the 50 % of chance
+    assert accs[0][0] > 60.0, accs
