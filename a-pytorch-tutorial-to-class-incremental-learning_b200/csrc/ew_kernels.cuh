@@ -431,8 +431,8 @@ struct AllreduceSgdParams {
   float* p;
   float* v;
   long long n;            // elements of segment 0 (starting at seg_off[0])
-  long long seg_off[2];   // up to two segments of the arenas per launch (the optimiser runs in two instalments: the
-  long long seg_n1;       // gradients that are complete early go first, while the backward is still running)
+  long long seg_off[2];   // up to two segments of the arenas per launch (a partially frozen model updates the ranges
+  long long seg_n1;       // on either side of the frozen one)
   const float* lr_dev;
   float mom, wd;
   unsigned* epoch;       // [0] epoch, [1] blocks-done counter (local device memory, zero initially)

@@ -528,7 +528,7 @@ struct wacil_net {
   cudaStream_t side = nullptr;            // optional second stream: weight gradients run beside the data-gradient chain
   std::vector<cudaEvent_t> ev_chain;      // backward chain i finished (main stream)
   cudaEvent_t ev_join = nullptr;          // all weight gradients reduced
-  // optional fused optimiser (wacil_net_set_optimizer): backward applies gradient mean + SGD itself, in two instalments
+  // optional fused optimiser (wacil_net_set_optimizer): backward applies gradient mean + SGD itself, after the join
   struct {
     bool on = false;
     float* v = nullptr;
@@ -1177,12 +1177,11 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     }
     return 0;
   };
-  // Fused optimiser: gradient mean over the ranks (NVLink peer reads in rank order) + SGD, in two instalments.  The first
-  // covers the convolution weights whose gradients are complete once the 8x8 layers are done (80 % of the arena for
-  // ResNet-32) and runs on the reduction branch beside the rest of the backward — nothing later in the backward reads
-  // the fp32 master weights (the kernels use the bf16 operand copies); the second covers the rest, after the join.
-  const long long conv_end = n->L[0].gamma_off;  // end of the convolution weights in the arena
-  long long early_from = conv_end;               // set when the first instalment has been launched
+  // Fused optimiser: gradient mean over the ranks (NVLink peer reads in rank order) + SGD, one launch after the join.
+  // (An early instalment for the 8x8 layers' weights — 80 % of the arena, complete a third of the way into the backward
+  // — was measured slower in every form: on the reduction branch, on its own branch, with 8 / 32 / all blocks, at one
+  // and at two GPUs: 1.044 vs 1.032 ms and 1.066 vs 1.055 ms, profiles/r02_early_instalment_ab.log.  The step graph
+  // is a chain of latency-bound launches; any extra kernel beside it costs more than the 20 us tail it saves.)
   auto optimise = [&](long long off0, long long n0, long long off1, long long n1, cudaStream_t os) -> int {
     if (n0 <= 0 && n1 <= 0) return 0;
     if (n0 <= 0) { off0 = off1; n0 = n1; n1 = 0; }
@@ -1211,9 +1210,6 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     ++launches;
     return 0;
   };
-  int split_layer = nl;  // first layer of the last resolution group (its weights and everything after: first instalment)
-  for (int l = nl - 1; l >= 1; --l)
-    if (n->L[l].cout == n->L[nl - 1].cout) split_layer = l;
   if (par) {
     WACIL_EV(cudaEventRecord(n->ev_chain[0], st), "event record");
     WACIL_EV(cudaStreamWaitEvent(ws, n->ev_chain[0], 0), "event wait");
@@ -1230,19 +1226,14 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     // elements first .. first+count-1 are layers l = nl-1-first .. ; they produced GY_{l-1}
     const int l_hi = nl - 1 - c.first - 1, l_lo = nl - 1 - (c.first + c.count - 1) - 1;
     if ((e = wgrads(l_hi, l_lo))) return e;
-    if (n->opt.on && early_from == conv_end && pending == 0 && l_lo <= split_layer && l_lo > 0) {
-      // every layer >= l_lo has its reduced gradient: first instalment on the reduction branch, right behind that reduction
-      early_from = n->L[l_lo].w_off;
-      if ((e = optimise(early_from, conv_end - early_from, 0, 0, par && n->red ? n->red : ws))) return e;
-    }
   }
   if (par) {  // join: the reductions are in order on their branch and each of them follows its weight gradients
     WACIL_EV(cudaEventRecord(n->ev_join, n->red ? n->red : ws), "event record");
     WACIL_EV(cudaStreamWaitEvent(st, n->ev_join, 0), "event wait");
   }
 #undef WACIL_EV
-  if (n->opt.on) {  // second instalment: the remaining convolution weights, BatchNorm parameters and the classifier
-    if ((e = optimise(0, early_from, conv_end, n->lay.param_elems - conv_end, st))) return e;
+  if (n->opt.on) {
+    if ((e = optimise(0, n->lay.param_elems, 0, 0, st))) return e;
   }
   n->launches = launches;
   return 0;

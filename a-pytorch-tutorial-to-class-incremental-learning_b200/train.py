@@ -176,7 +176,7 @@ class _StepState:
         self.plan_s = tr.model._plan(_lib.NET_TRAIN, batch)
         if tr.overlap:
             self.plan_s.set_side_stream(tr.side_w)
-        if tr.fused_opt:  # gradient mean + SGD inside backward(), in two instalments (see Plan.set_optimizer)
+        if tr.fused_opt:  # gradient mean + SGD inside backward() (see Plan.set_optimizer)
             pr = tr.peer
             self.plan_s.set_optimizer(tr.mom, tr.lr_dev, tr.momentum, tr.weight_decay, tr.world_size,
                                       pr["rank"] if pr else 0, pr["grad_ptrs"] if pr else None,

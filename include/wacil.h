@@ -223,11 +223,9 @@ int wacil_net_forward(wacil_net_t* net, const float* x, int C_seen, float* feats
 int wacil_net_backward(wacil_net_t* net, const float* dlogits, int C_seen, void* stream);
 
 /* Optional fused optimiser.  Once set, wacil_net_backward also applies the DDP gradient mean (template.py:243-244,270)
- * and the SGD update (template.py:246-247,271) of wacil_allreduce_sgd / wacil_sgd_step itself, in two instalments: the
- * convolution weights of the last resolution group (80 % of the arena for ResNet-32; complete after a third of the
- * backward) on the plan's reduction branch while the rest of the backward still runs, everything else after the join —
- * the exchange no longer sits behind the last gradient kernel.  Nothing later in the backward reads the fp32 master
- * weights (the kernels use the bf16 operand copies written by the forward).  momentum_buf: fp32 arena like params
+ * and the SGD update (template.py:246-247,271) of wacil_allreduce_sgd / wacil_sgd_step itself, as the last launch of the
+ * backward (one launch, inside the same CUDA graph; an earlier instalment for the weights that are complete early was
+ * measured slower, profiles/r02_early_instalment_ab.log).  momentum_buf: fp32 arena like params
  * (NULL detaches the optimiser); lr_dev: device float; world / rank / grad_ptrs / pad_ptrs / epoch_ws as in
  * wacil_allreduce_sgd (world = 1: no exchange, the pointers may be NULL).  All ranks must call backward the same
  * number of times. */
