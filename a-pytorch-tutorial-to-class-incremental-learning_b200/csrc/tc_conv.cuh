@@ -280,7 +280,12 @@ __device__ __forceinline__ float4 published_row_sum4(const unsigned* __restrict_
   return acc;
 }
 
+// EPI_T >= 0: the epilogue mode as a compile-time constant (the two fused modes are their own kernels: each gets its own
+// register allocation and a third of the code); EPI_T < 0: p.epi at run time (RAW / STATS / INFER).
+template <int EPI_T>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CUtensorMap& mapW, const ConvGemmParams& p) {
+  // (the run-time flavour never runs a fused mode: launch_conv sends those to their own kernels)
+  const int epi = EPI_T >= 0 ? EPI_T : (p.epi < EPI_BN_TRAIN ? p.epi : EPI_RAW);
   constexpr int EW = 4;        // epilogue warps (one per TMEM lane quarter)
   constexpr int ET = EW * 32;  // epilogue threads
   extern __shared__ uint8_t smem_raw[];
@@ -316,9 +321,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   // Fused modes keep a second TMEM region beside the accumulators (same tile/column indexing, offset stash_col): what the
   // post-barrier phase needs besides the accumulator (BN_TRAIN: the shortcut; BNBWD: x-hat) is staged there in phase 1,
   // while the main loop still runs, so that phase 2 touches no global memory but its stores.
-  const bool stash = (p.epi == EPI_BNBWD) || (p.epi == EPI_BN_TRAIN && p.res != nullptr);
+  const bool stash = (epi == EPI_BNBWD) || (epi == EPI_BN_TRAIN && p.res != nullptr);
   const uint32_t stash_col = static_cast<uint32_t>(nacc * p.nc);
-  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (stash ? 2u : 1u));
+  // BNBWD with a shortcut gradient: a third region holds it (fp32) when three regions fit half of the tensor memory
+  // (the 16x16 and 8x8 layers); the 32x32 layers (7 tiles x 16 columns x 3 > 256) carry it in registers instead
+  const bool gres3 = epi == EPI_BNBWD && p.g_res != nullptr && 3u * static_cast<uint32_t>(nacc * p.nc) <= 256u;
+  const uint32_t gres_col = 2u * stash_col;
+  const uint32_t tmem_cols = next_pow2_cols(static_cast<uint32_t>(nacc * p.nc) * (gres3 ? 3u : (stash ? 2u : 1u)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -516,7 +525,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         if (timing) p.dbg[blockIdx.x * 16 + 12] = dbg_wait;
       }
     }
-  } else if (p.epi >= EPI_BN_TRAIN) {
+  } else if (EPI_T >= 0 && epi >= EPI_BN_TRAIN) {
     // ------------------------------------------------------------ fused epilogues (accumulators stay in TMEM)
     const int quarter = warp & 3;
     const int ew = warp - 2;          // epilogue warp index
@@ -530,7 +539,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     float* s_mean = s_stats + EW * 128 + 192;   // [nc]
     float* s_rstd = s_stats + EW * 128 + 256;   // [nc]
     const int ncr = p.nc;
-    if (p.epi == EPI_BNBWD) {
+    if (epi == EPI_BNBWD) {
       for (int c = tid128; c < p.nc; c += ET) {
         s_mean[c] = p.saved[c % ncr];
         s_rstd[c] = p.saved[ncr + c % ncr];
@@ -539,23 +548,133 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     }
     // ---------------- phase 1: per-channel reductions (and the raw conv output in BN_TRAIN); stages phase 2's operands
     int as = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++as) {
+    if (epi == EPI_BNBWD) {
+      // Everything phase 1 needs from global memory — the activation (ReLU mask), the raw conv output (x-hat) and the
+      // shortcut gradient — does not depend on this launch's MMAs, so it is fetched ONE TILE AHEAD of the accumulator
+      // (the first tile: under the operand loads and the main loop): the mask goes to a 64-bit register, x-hat to the
+      // stash region, the shortcut gradient to the third TMEM region (or, for the single-chunk 32x32 layers, stays in
+      // 8 registers).  What follows the accumulator then touches tensor memory only.  (Fetched after the
+      // accumulator, chunk by chunk, these loads were 1.2-1.6 k cycles of exposed latency per 16-channel chunk: 6-8 k
+      // cycles behind the last MMA of an 8x8 layer, profiles/r02_layer_timelines.log.)
+      const int gmode = p.g_res == nullptr ? 0 : (gres3 ? 1 : (p.nc == 16 ? 2 : 3));  // 3: no room, load late
+      auto gres_ptr_of = [&](int pix) -> const __nv_bfloat16* {
+        if (p.g_res == nullptr || pix >= p.num_pixels) return nullptr;
+        if (p.gres_mode == 1) return p.g_res + static_cast<size_t>(pix) * p.nc;
+        const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+        if (((w | h) & 1) != 0) return nullptr;
+        return p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
+      };
+      // one 16-channel chunk of a tile: raw loads, then their use.  (Processing the current tile between the two, so
+      // that the next tile's load latency hides under it, needs 24 live registers more than the 128 that keep the side
+      // branches co-resident: the spills made the 32x32 layers 1 us slower, profiles/r02_layer_timelines.log.)
+      struct RawChunk { uint4 a0, a1, y0, y1, g0, g1; };
+      auto issue_chunk = [&](int tile, int c0, RawChunk& rc) {
+        const int pix = tile * 128 + m;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        rc.a0 = rc.a1 = rc.y0 = rc.y1 = rc.g0 = rc.g1 = z;
+        if (pix < p.num_pixels) {
+          const size_t base = static_cast<size_t>(pix) * p.nc + c0;
+          const uint4* qa = reinterpret_cast<const uint4*>(p.act_in + base);
+          const uint4* qy = reinterpret_cast<const uint4*>(p.y_in + base);
+          rc.a0 = __ldg(qa); rc.a1 = __ldg(qa + 1);
+          rc.y0 = __ldg(qy); rc.y1 = __ldg(qy + 1);
+        }
+        if (gmode == 1 || gmode == 2) {
+          const __nv_bfloat16* gp = gres_ptr_of(pix);
+          if (gp != nullptr) {
+            const uint4* qg = reinterpret_cast<const uint4*>(gp + c0);
+            rc.g0 = __ldg(qg); rc.g1 = __ldg(qg + 1);
+          }
+        }
+      };
+      auto consume_chunk = [&](int as_, int c0, const RawChunk& rc, unsigned long long& mask, uint4& g0, uint4& g1) {
+        float a[16], yv[16];
+        unpack16_bf16(rc.a0, rc.a1, a);
+        unpack16_bf16(rc.y0, rc.y1, yv);
+        unsigned bits = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          bits |= (a[i] > 0.f ? 1u : 0u) << i;                      // rows beyond the last pixel loaded zeros: mask 0
+          yv[i] = (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i];        // x-hat (garbage in masked rows is never used: gz = 0)
+        }
+        mask |= static_cast<unsigned long long>(bits) << c0;
+        tmem_st16(tmem_base + lane_base + stash_col + as_ * p.nc + c0, yv);
+        if (gmode == 1) {
+          float r[16];
+          unpack16_bf16(rc.g0, rc.g1, r);
+          tmem_st16(tmem_base + lane_base + gres_col + as_ * p.nc + c0, r);
+        } else if (gmode == 2) {
+          g0 = rc.g0;
+          g1 = rc.g1;
+        }
+      };
+      auto stage_tile = [&](int tile, int as_, unsigned long long& mask, uint4& g0, uint4& g1) {
+        mask = 0ull;
+        for (int c0 = 0; c0 < p.nc; c0 += 16) {
+          RawChunk rc;
+          issue_chunk(tile, c0, rc);
+          consume_chunk(as_, c0, rc, mask, g0, g1);
+        }
+      };
+      unsigned long long mask_cur = 0ull, mask_nxt = 0ull;
+      uint4 gc0 = make_uint4(0u, 0u, 0u, 0u), gc1 = gc0, gn0 = gc0, gn1 = gc0;
+      int tile = blockIdx.x;
+      if (tile < p.num_tiles) stage_tile(tile, 0, mask_cur, gc0, gc1);
+      for (; tile < p.num_tiles; tile += gridDim.x, ++as) {
+        const int nt = tile + static_cast<int>(gridDim.x);
+        if (nt < p.num_tiles) stage_tile(nt, as + 1, mask_nxt, gn0, gn1);
+        mbar_wait(&accfull[as], 0);
+        tc_fence_after();
+        if (tid128 == 0 && as == 0) WACIL_STAMP(6);  // first accumulator complete
+        for (int c0 = 0; c0 < p.nc; c0 += 16) {
+          float v[16], xh[16], s2[16];
+          tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
+          tmem_ld16(tmem_base + lane_base + stash_col + as * p.nc + c0, xh);
+          if (gmode == 1) {
+            float r[16];
+            tmem_ld16(tmem_base + lane_base + gres_col + as * p.nc + c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          } else if (gmode == 2) {
+            float r[16];
+            unpack16_bf16(gc0, gc1, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          } else if (gmode == 3) {
+            const __nv_bfloat16* gp = gres_ptr_of(tile * 128 + m);
+            if (gp != nullptr) {
+              float r[16];
+              load16_bf16(gp + c0, r);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += r[i];
+            }
+          }
+          const unsigned bits = static_cast<unsigned>(mask_cur >> c0) & 0xffffu;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;  // gz (masked gradient; rows beyond the last pixel have mask 0)
+            s2[i] = v[i] * xh[i];
+          }
+          tmem_st16(tmem_base + lane_base + as * p.nc + c0, v);  // phase 2 reads gz here, x-hat from the stash
+          const float t1 = warp_colsum16(v, lane);
+          const float t2 = warp_colsum16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int c = c0 + warp_colsum16_col(lane);
+            s_part[(ew * 2 + 0) * 64 + c] += t1;
+            s_part[(ew * 2 + 1) * 64 + c] += t2;
+          }
+        }
+        mask_cur = mask_nxt;
+        gc0 = gn0;
+        gc1 = gn1;
+      }
+    }
+    for (int tile = blockIdx.x; epi == EPI_BN_TRAIN && tile < p.num_tiles; tile += gridDim.x, ++as) {
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
-      const __nv_bfloat16* gres_ptr = nullptr;
       const __nv_bfloat16* res_ptr = nullptr;
-      if (p.epi == EPI_BNBWD && p.g_res != nullptr && valid) {
-        if (p.gres_mode == 1) {
-          gres_ptr = p.g_res + base;
-        } else {
-          const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
-          if (((w | h) & 1) == 0) {
-            gres_ptr = p.g_res + ((static_cast<size_t>(n) * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.nc);
-          }
-        }
-      }
-      if (p.epi == EPI_BN_TRAIN && p.res != nullptr && valid) {
+      if (p.res != nullptr && valid) {
         if (p.res_stride == 1) {
           res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
         } else {
@@ -563,7 +682,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           res_ptr = p.res + ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.res_c;
         }
       }
-      if (p.epi == EPI_BN_TRAIN && stash) {
+      if (stash) {
         // the shortcut does not depend on this tile's accumulator: fetch it while the MMAs of the tile are in flight
         for (int c0 = 0; c0 < p.nc; c0 += 16) {
           float r[16];
@@ -579,7 +698,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16], s2[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (p.epi == EPI_BN_TRAIN) {
+        {
           uint4 oa, ob;
           pack16_bf16(v, oa, ob);  // y as stored (bf16); the statistics are taken over the rounded values
           if (valid) {
@@ -592,30 +711,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
           unpack16_bf16(oa, ob, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) s2[i] = v[i] * v[i];
-        } else {
-          float a[16], yv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { a[i] = 0.f; yv[i] = 0.f; }
-          if (valid) {
-            load16_bf16(p.act_in + base + c0, a);
-            load16_bf16(p.y_in + base + c0, yv);
-            if (gres_ptr != nullptr) {
-              float r[16];
-              load16_bf16(gres_ptr + c0, r);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += r[i];
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = (valid && a[i] > 0.f) ? v[i] : 0.f;                             // gz (masked gradient)
-            yv[i] = valid ? (yv[i] - s_mean[c0 + i]) * s_rstd[c0 + i] : 0.f;       // x-hat
-          }
-          // phase 2 reads both back from TMEM: gz replaces the accumulator, x-hat goes to the stash region
-          tmem_st16(tmem_base + lane_base + as * p.nc + c0, v);
-          tmem_st16(tmem_base + lane_base + stash_col + as * p.nc + c0, yv);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s2[i] = v[i] * yv[i];
         }
         const float t1 = warp_colsum16(v, lane);
         const float t2 = warp_colsum16(s2, lane);
@@ -657,9 +752,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
     // threads: one channel per thread)
     const int myc = tid128 < p.nc ? tid128 : 0;
     const float gam = p.gamma[myc % ncr];
-    const float bet = p.epi == EPI_BN_TRAIN ? p.beta[myc % ncr] : 0.f;
+    const float bet = epi == EPI_BN_TRAIN ? p.beta[myc % ncr] : 0.f;
     float rmean = 0.f, rvar = 0.f;
-    if (p.epi == EPI_BN_TRAIN && blockIdx.x == 0 && tid128 < ncr) {
+    if (epi == EPI_BN_TRAIN && blockIdx.x == 0 && tid128 < ncr) {
       rmean = p.running_mean[tid128];
       rvar = p.running_var[tid128];
     }
@@ -688,7 +783,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         t0 += s_scr[sl * V + c];
         t1 += s_scr[sl * V + p.nc + c];
       }
-      if (p.epi == EPI_BN_TRAIN) {
+      if (epi == EPI_BN_TRAIN) {
         const float mean = t0 / cnt;
         float var = t1 / cnt - mean * mean;
         var = fmaxf(var, 0.f);
@@ -721,14 +816,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       const bool valid = pix < p.num_pixels;
       const size_t base = static_cast<size_t>(valid ? pix : 0) * p.nc;
       size_t up_base = 0;
-      if (p.epi == EPI_BNBWD && p.gy_up != nullptr) {
+      if (epi == EPI_BNBWD && p.gy_up != nullptr) {
         const int w = pix % p.Wo, h = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
         up_base = ((static_cast<size_t>(n) * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.nc;
       }
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + lane_base + as * p.nc + c0, v);
-        if (p.epi == EPI_BN_TRAIN) {
+        if (epi == EPI_BN_TRAIN) {
           {
             uint4 ya, yb;
             pack16_bf16(v, ya, yb);  // the stored (rounded) conv output is what gets normalised
@@ -788,7 +883,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       const int pix = tile * 128 + m;
       const bool valid = pix < p.num_pixels;
       const __nv_bfloat16* res_ptr = nullptr;
-      if (p.epi == EPI_INFER && p.res != nullptr && valid) {
+      if (epi == EPI_INFER && p.res != nullptr && valid) {
         if (p.res_stride == 1) {
           res_ptr = p.res + static_cast<size_t>(pix) * p.res_c;
         } else {
@@ -801,7 +896,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
       for (int c0 = 0; c0 < p.nc; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * p.nc + c0, v);
-        if (p.epi == EPI_INFER) {
+        if (epi == EPI_INFER) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
           if (res_ptr != nullptr && c0 < p.res_c) {
@@ -822,7 +917,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         } else {
           oa = ob = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (p.epi == EPI_STATS) {
+        if (epi == EPI_STATS) {
           float s1[16], s2[16];
           unpack16_bf16(oa, ob, s1);
 #pragma unroll
@@ -844,7 +939,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
         aphase ^= 1;
       }
     }
-    if (p.epi == EPI_STATS) {
+    if (epi == EPI_STATS) {
       // the four epilogue warps only: named barrier 1, 128 threads
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;
@@ -866,10 +961,26 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   if (threadIdx.x == 0) WACIL_STAMP(10);  // teardown done
 }
 
+// Three entry points over one body.  (At most 128 registers: above that the side branches of the step graph no longer
+// share an SM with these kernels, profiles/r02_chain_experiments.md.)
 __global__ void __maxnreg__(128)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                     const ConvGemmParams p) {
-  conv_gemm_body(mapA, mapW, p);
+                     const ConvGemmParams p) {  // RAW / STATS / INFER
+  conv_gemm_body<-1>(mapA, mapW, p);
+}
+__global__ void __maxnreg__(128)
+    conv_gemm_kernel_bn_fwd(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                            const ConvGemmParams p) {  // conv + batch statistics + BatchNorm + shortcut + ReLU
+  conv_gemm_body<EPI_BN_TRAIN>(mapA, mapW, p);
+}
+__global__ void __maxnreg__(128)
+    conv_gemm_kernel_bn_bwd(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                            const ConvGemmParams p) {  // data gradient + ReLU mask + BatchNorm backward
+  conv_gemm_body<EPI_BNBWD>(mapA, mapW, p);
+}
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvGemmParams);
+inline ConvKernelFn conv_kernel_for(int epi) {
+  return epi == EPI_BN_TRAIN ? conv_gemm_kernel_bn_fwd : (epi == EPI_BNBWD ? conv_gemm_kernel_bn_bwd : conv_gemm_kernel);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -154,11 +154,11 @@ static int run_conv(const Case& c) {
   if (fused) p.acc_stages = (p.num_tiles + 147) / 148;  // upper bound for the shared-memory size
   const size_t smem = conv_smem_bytes(p);
   const int nthreads = kConvThreads;
-  CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute((const void*)conv_kernel_for(p.epi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute((const void*)conv_kernel_for(p.epi), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)conv_kernel_for(p.epi), kConvThreads, smem));
     if (g_timing) printf("   occupancy %d CTAs/SM at %zu B smem\n", occ, smem);
     if (grid > occ * 148) grid = occ * 148;
     if (fused) { p.acc_stages = (p.num_tiles + grid - 1) / grid; }
@@ -166,7 +166,7 @@ static int run_conv(const Case& c) {
   auto launch = [&]() {
     if (fused) {
       void* args[] = {&mapA, &mapW, &p};
-      CK(cudaLaunchCooperativeKernel((void*)conv_gemm_kernel, dim3(grid), dim3(nthreads), args, smem, 0));
+      CK(cudaLaunchCooperativeKernel((void*)conv_kernel_for(p.epi), dim3(grid), dim3(nthreads), args, smem, 0));
     } else {
       conv_gemm_kernel<<<grid, kConvThreads, smem>>>(mapA, mapW, p);
     }

@@ -311,11 +311,14 @@ constexpr size_t kChainSmemMax = 227 * 1024;
 int conv_attrs() {
   static bool set = false;
   if (set) return 0;
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kConvSmemWide));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+  cudaError_t e = cudaSuccess;
+  for (int epi : {static_cast<int>(EPI_RAW), static_cast<int>(EPI_BN_TRAIN), static_cast<int>(EPI_BNBWD)}) {
+    const void* k = reinterpret_cast<const void*>(conv_kernel_for(epi));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kConvSmemWide));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kConvSmemMax));
@@ -340,7 +343,7 @@ int conv_attrs() {
 int conv_max_resident(size_t smem) {
   int occ = 0;
   if (conv_attrs()) return num_sms();
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel, kConvThreads, smem) != cudaSuccess || occ < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gemm_kernel_bn_fwd, kConvThreads, smem) != cudaSuccess || occ < 1)
     occ = 1;
   if (occ > 2) occ = 2;
   return occ * num_sms();
@@ -368,7 +371,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, c.mapA, c.mapW, c.p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(c.p.epi), c.mapA, c.mapW, c.p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm_kernel");
   return 0;
 }
@@ -1000,8 +1003,9 @@ int wacil_net_run_chain(wacil_net_t* n, int backward, int index, long long* dbg,
   cudaError_t ce = backward ? cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st)
                             : cudaMemsetAsync(n->ws + n->off.sync_f, 0, n->off.sync_f_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
-  if (n->engine == ENGINE_LAYER) {  // one conv_gemm_kernel launch (no stamps)
+  if (n->engine == ENGINE_LAYER) {  // one conv_gemm_kernel launch; dbg: [grid][16] clock64 stamps (WACIL_STAMP slots)
     ConvLaunch c = backward ? n->dgrad[static_cast<int>(n->L.size()) - 1 - v[index].first] : n->fprop[v[index].first];
+    c.p.dbg = dbg;
     c.p.pdl = 0;
     c.p.w_early = 0;
     return launch_conv(c, st);

@@ -1,0 +1,3 @@
+timeout 200 python tools/layer_timeline.py 2>&1 | grep -A2 "^backward"
+timeout 120 python tools/step_parts.py 2>&1 | tail -6
+timeout 500 python -m pytest tests/test_gpu_engine.py -x -q -m gpu 2>&1 | tail -3
