@@ -293,8 +293,8 @@ def kernel_rooflines(w, pk):
     us = 1e3 * e0.elapsed_time(e1) / reps
     bytes_alg = 4 * BATCH * 32 * 32 * 16 * 2 + 9 * 16 * 16 * 2 + 4 * 16 * 4  # x + shortcut in, y + a out (bf16), weights, stats
     flops = 2 * BATCH * 32 * 32 * 16 * 16 * 9
-    out["conv"] = {"kernel": "conv_gemm_kernel EPI_BN_TRAIN (fused stage-1 layer 128x32x32x16->16: conv + batch stats + "
-                             "BN + shortcut + ReLU; includes its 128-byte stats memset)", "us": us,
+    out["conv"] = {"kernel": "conv_gemm_kernel_bn_fwd (fused stage-1 layer 128x32x32x16->16: conv + batch stats + "
+                             "exchange of the per-CTA sums + BN + shortcut + ReLU, one launch)", "us": us,
                    "gbs": bytes_alg / us / 1e3, "tflops": flops / us / 1e6, "bytes": bytes_alg}
     del rs, acts
     del xs, ys
@@ -540,10 +540,10 @@ def run_ours(args, rank, local_rank, world):
         c = roof["conv"]
         line["roofline"] = {"bound": "hbm", "achieved": c["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": c["gbs"] / pk["hbm_gbs"],
-                            "traffic": ncu_traffic("r02_ncu_full_fused_stage1.csv", "conv_gemm_kernel"),
+                            "traffic": ncu_traffic("r02_ncu_full_bn_fwd_stage1.csv", "conv_gemm_kernel_bn_fwd"),
                             "kernel": c["kernel"], "us": c["us"],
                             "traffic_note": "dram__bytes_read+write of one launch, parsed from the committed ncu --set full export "
-                                            "profiles/r02_ncu_full_fused_stage1.csv (same entry point): outputs stay in the 126 MB L2 "
+                                            "profiles/r02_ncu_full_bn_fwd_stage1.csv (same entry point): outputs stay in the 126 MB L2 "
                                             "(write-back), inputs are read once from DRAM",
                             "algorithmic_bytes": c["bytes"], "tflops": c["tflops"], "peak_src": pk["src"]}
         line["kd_kernel"] = roof["kd"]
