@@ -961,19 +961,31 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& mapA, const CU
   if (threadIdx.x == 0) WACIL_STAMP(10);  // teardown done
 }
 
-// Three entry points over one body.  (At most 128 registers: above that the side branches of the step graph no longer
-// share an SM with these kernels, profiles/r02_chain_experiments.md.)
-__global__ void __maxnreg__(128)
+// Three entry points over one body.  Register caps measured on the step graph (profiles/r02_register_caps_ab.log): an
+// SM holds the CTA of the running layer, the CTA of the NEXT layer (programmatic dependent launch: its prologue runs
+// under this one's tail) and a CTA of the side branch (teacher / weight gradient), 192 threads each.  Above 128 the
+// branches stop overlapping; the fused backward at 120 (a few spilled words) is 13 us per step faster than at 128;
+// the forward at 112 / 120 is slower than at 128; the run-time flavour needs 106.
+#ifndef WACIL_FWD_REGS
+#define WACIL_FWD_REGS 128
+#endif
+#ifndef WACIL_BWD_REGS
+#define WACIL_BWD_REGS 120
+#endif
+#ifndef WACIL_GEN_REGS
+#define WACIL_GEN_REGS 128
+#endif
+__global__ void __maxnreg__(WACIL_GEN_REGS)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const ConvGemmParams p) {  // RAW / STATS / INFER
   conv_gemm_body<-1>(mapA, mapW, p);
 }
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(WACIL_FWD_REGS)
     conv_gemm_kernel_bn_fwd(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                             const ConvGemmParams p) {  // conv + batch statistics + BatchNorm + shortcut + ReLU
   conv_gemm_body<EPI_BN_TRAIN>(mapA, mapW, p);
 }
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(WACIL_BWD_REGS)
     conv_gemm_kernel_bn_bwd(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                             const ConvGemmParams p) {  // data gradient + ReLU mask + BatchNorm backward
   conv_gemm_body<EPI_BNBWD>(mapA, mapW, p);
