@@ -672,7 +672,6 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
   const bool pdl = pdl_enabled();
   n->engine = engine_kind();
   const bool per_layer = n->engine == ENGINE_LAYER;
-  const bool wide_ok = !per_layer || env_int("WACIL_WIDE", 1, 0, 1) != 0;
   const int fwd_len = per_layer ? 1 : chain_fwd_len(), bwd_len = per_layer ? 1 : chain_bwd_len();
   ce = cudaMemset(n->ws + n->off.gbar, 0, 64 + 16 * nl);
   // the published statistics rows: a zero word = "not written" (a recycled workspace may hold an older plan's rows)
@@ -691,7 +690,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     c.smem = conv_smem_bytes(c.p);
     // a launch on at most half of the SMs (the 8x8 layers: 64 tiles) does not share its SMs with the side branches'
     // CTAs, so the half-SM footprint rule (kConvSmemMax) does not bind it
-    const size_t cap = wide_ok && grid * 2 <= num_sms() ? kConvSmemWide : kConvSmemMax;
+    const size_t cap = grid * 2 <= num_sms() ? kConvSmemWide : kConvSmemMax;
     while (c.smem > cap && c.p.stages > 2) {  // the ring was sized for the chain kernel's slightly larger budget
       --c.p.stages;
       c.smem = conv_smem_bytes(c.p);
@@ -725,7 +724,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
     for (int l = first; l < first + count; ++l) w_max = std::max(w_max, w_tile_bytes(n->L[l].cin_pad, n->L[l].cout));
     int group_tiles = 0;
     for (int l = first; l < first + count; ++l) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[l].H_out));
-    const size_t ring = chain_ring_bytes(w_max, fwd_ew, wide_ok && group_tiles * 2 <= num_sms());
+    const size_t ring = chain_ring_bytes(w_max, fwd_ew, group_tiles * 2 <= num_sms());
     int max_tiles = 0;
     for (int l = first; l < first + count; ++l) {
       const LayerDesc& d = n->L[l];
@@ -856,7 +855,7 @@ int wacil_net_create(wacil_net_t** out, int depth, int batch, int max_classes, i
       }
       int group_tiles = 0;
       for (int el = first; el < first + count; ++el) group_tiles = std::max(group_tiles, tiles_of(batch, n->L[layer_of(el)].H_in));
-      const size_t ring = chain_ring_bytes(w_max, ew_fused, wide_ok && group_tiles * 2 <= num_sms());
+      const size_t ring = chain_ring_bytes(w_max, ew_fused, group_tiles * 2 <= num_sms());
       int max_tiles = 0;
       for (int el = first; el < first + count; ++el) {
         const int l = layer_of(el), pl = l - 1;

@@ -1,5 +1,5 @@
 """The dominant kernel of the step in isolation, for ncu: the fused stage-1 layer (wacil_conv3x3_bn_relu: 3x3 conv 16->16
-over 128x32x32 + batch statistics + grid barrier + BatchNorm + shortcut + ReLU) and the weight gradient of the same layer
+over 128x32x32 + batch statistics + exchange of the partial sums + BatchNorm + shortcut + ReLU) and the weight gradient of the same layer
 (wacil_conv3x3_wgrad), five launches each over rotating buffers."""
 import os
 import sys
