@@ -1,6 +1,7 @@
 """world_size-2 CPU (gloo) test of the multi-rank host logic: shard arithmetic, the flat-arena gradient exchange
 (sum + 1/world in the optimiser = DDP's mean, template.py:243-244), per-epoch statistic reduction, rank-identical
-model construction.  The kernels themselves are covered by the -m gpu tests."""
+model construction, the rank-0 BatchNorm-statistics broadcast of the task boundary.  The kernels themselves are covered
+by the -m gpu tests."""
 import os
 import sys
 
@@ -57,7 +58,18 @@ def _worker(rank, world, port, q):
     ev_cover = (torch.cat(ev_all).unique().numel(), torch.cat(ev_all).numel())  # 101 samples, 102 with the padding duplicate
     meter = torch.tensor([51.0, 2.0, 1.0 + rank, 40.0 + rank, 50.0, 0, 0, 0], dtype=torch.float64)
     acc1, acc5, loss = w.train._finish_meter(meter, log=None)
-    q.put((rank, same_init, covered, mean_ok, abs(scale - 1.0 / world) < 1e-12, stats, ev_cover, (acc1, acc5, loss)))
+    # DDP's buffer broadcast at the task boundary (template.py:243-244): ranks that trained on different shards hold
+    # different running statistics; afterwards every rank holds rank 0's, and plans built on the old ones are stale
+    with torch.no_grad():
+        model.bn_running.add_(0.25 * (rank + 1))
+    mine_bn = model.bn_running.clone()
+    version = model._param_version
+    w.train.broadcast_buffers(model, world)
+    rank0_bn = mine_bn.clone()
+    dist.broadcast(rank0_bn, src=0)
+    bn_ok = torch.equal(model.bn_running, rank0_bn) and (rank == 0 or not torch.equal(mine_bn, rank0_bn)) \
+        and model._param_version != version
+    q.put((rank, same_init, covered, mean_ok, abs(scale - 1.0 / world) < 1e-12, stats, ev_cover, (acc1, acc5, loss), bn_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,8 +86,8 @@ def test_two_rank_gloo_host_logic():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, same_init, covered, mean_ok, scale_ok, stats, ev_cover, ev in results:
-        assert same_init and covered == 7000 and mean_ok and scale_ok
+    for rank, same_init, covered, mean_ok, scale_ok, stats, ev_cover, ev, bn_ok in results:
+        assert same_init and covered == 7000 and mean_ok and scale_ok and bn_ok
         assert abs(stats["ce"] - (1.0 + 2.0) / 4) < 1e-9 and abs(stats["acc1"] - 100 * 61 / 200) < 1e-9
         assert ev_cover == (101, 102)
         # every rank ends with the same global averages: 81 top-1 hits of 102 samples, loss 3 / 4 batches
