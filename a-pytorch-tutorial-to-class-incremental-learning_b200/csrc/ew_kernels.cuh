@@ -3,8 +3,8 @@
 //   cast_weights      fp32 master weights [9][cin][cout] -> bf16 fprop ([9][cout][cin]) and dgrad
 //                     ([9 flipped][cin][cout]) operand copies, all layers in one launch
 //   fold_bn           eval-mode BatchNorm folded into bf16 weights + fp32 bias (teacher / feature extraction)
-//   bn_bwd_reduce / bn_bwd_apply   stand-alone ReLU mask + BatchNorm backward (last layer; the other layers' BN forward
-//                     and backward are fused into conv_gemm_kernel, tc_conv.cuh)
+//   (BatchNorm forward / backward are fused into the conv kernels, tc_conv.cuh; the last layer's backward together with
+//    the classifier's data gradient is head_kernels.cuh)
 //   pool_fc_fwd / fc_bwd           8x8 average pool + classifier heads                      (resnet.py:114-115,
 //                                                                                          template.py:99-101)
 //   sgd_step          momentum SGD with weight decay on the flat arena                      (template.py:246-247,271)
@@ -94,235 +94,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ params, const float* __
   }
 }
 
-// ------------------------------------------------------------------------------------------------ BN backward
-struct BnBwdParams {
-  const __nv_bfloat16* g_main;  // gradient wrt this layer's post-ReLU output [pix][C], or nullptr
-  const float* g_pool;          // or: gradient wrt the pooled features [N][C] (last layer), scaled by inv_hw
-  float inv_hw;
-  const __nv_bfloat16* g_res;   // shortcut gradient from the following block, or nullptr
-  int gres_mode;                // 1: same shape; 2: source is [N][Ho/2][Wo/2][2C], lands on even pixels, channels < C
-  const __nv_bfloat16* act;     // post-ReLU output of this layer (mask)
-  const __nv_bfloat16* y;       // raw conv output
-  const float* saved;           // mean, rstd
-  const float* gamma;
-  float* dgamma;                // grads arena (written by block 0 of the apply kernel)
-  float* dbeta;
-  float* part;                  // [nparts][2*C] per-block partial sums of the reduce kernel (plain stores, fixed order)
-  int nparts;                   // blocks of the reduce kernel
-  __nv_bfloat16* gy;            // out: gradient wrt the conv output [pix][C]
-  __nv_bfloat16* gy_up;         // optional: same, scattered to even pixels of [N][2Ho][2Wo][C] (stride-2 dgrad input)
-  __nv_bfloat16* gz;            // optional: masked gradient (before BN backward) for the previous block's shortcut
-  int C, Ho, Wo;
-  long long num_pixels;
-};
-
-// Raw 16-byte loads of everything one output vector needs, issued together; decode happens later.
-struct BnBwdRaw {
-  uint4 g, r, a, y;
-  float gp[8];
-  bool has_r;
-};
-
-__device__ __forceinline__ void bn_bwd_issue_loads(const BnBwdParams& p, long long pix, int c0, long long v,
-                                                   BnBwdRaw& raw) {
-  raw.has_r = false;
-  if (p.g_main) {
-    raw.g = __ldg(reinterpret_cast<const uint4*>(p.g_main) + v);
-  } else {
-    const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-    const float4* gp = reinterpret_cast<const float4*>(p.g_pool + n * p.C + c0);
-    const float4 a = __ldg(gp), b = __ldg(gp + 1);
-    raw.gp[0] = a.x; raw.gp[1] = a.y; raw.gp[2] = a.z; raw.gp[3] = a.w;
-    raw.gp[4] = b.x; raw.gp[5] = b.y; raw.gp[6] = b.z; raw.gp[7] = b.w;
-  }
-  if (p.g_res) {
-    if (p.gres_mode == 1) {
-      raw.r = __ldg(reinterpret_cast<const uint4*>(p.g_res) + v);
-      raw.has_r = true;
-    } else {
-      const int w = static_cast<int>(pix % p.Wo);
-      const int h = static_cast<int>((pix / p.Wo) % p.Ho);
-      if (((w | h) & 1) == 0) {
-        const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-        const long long rp = ((n * (p.Ho / 2) + h / 2) * (p.Wo / 2) + w / 2) * (2 * p.C) + c0;
-        raw.r = __ldg(reinterpret_cast<const uint4*>(p.g_res + rp));
-        raw.has_r = true;
-      }
-    }
-  }
-  raw.a = __ldg(reinterpret_cast<const uint4*>(p.act) + v);
-  raw.y = __ldg(reinterpret_cast<const uint4*>(p.y) + v);
-}
-
-// masked gradient gz (fp32) and raw conv output y (fp32) of one vector
-__device__ __forceinline__ void bn_bwd_decode(const BnBwdParams& p, const BnBwdRaw& raw, float (&g)[8],
-                                              float (&yv)[8]) {
-  if (p.g_main) {
-    bf16x8_to_float(raw.g, g);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = raw.gp[i] * p.inv_hw;
-  }
-  if (raw.has_r) {
-    float r[8];
-    bf16x8_to_float(raw.r, r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] += r[i];
-  }
-  float a[8];
-  bf16x8_to_float(raw.a, a);
-  bf16x8_to_float(raw.y, yv);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] = (a[i] > 0.f) ? g[i] : 0.f;
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  __shared__ float s_acc[8][128];  // per-warp sums, combined in warp order (no atomics: bit-reproducible)
-  for (int i = threadIdx.x; i < 8 * 128; i += blockDim.x) (&s_acc[0][0])[i] = 0.f;
-  __syncthreads();
-  constexpr int kU = 2;
-  const int cv = p.C / 8;                 // channel vectors per pixel (2 / 4 / 8)
-  const int lanes = blockDim.x / cv;      // pixels per block pass
-  const int myc = threadIdx.x % cv;
-  const int c0 = myc * 8;
-  float mean[8], rstd[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    mean[i] = p.saved[c0 + i];
-    rstd[i] = p.saved[p.C + c0 + i];
-  }
-  float sg[8], sx[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
-  const long long pstride = static_cast<long long>(gridDim.x) * lanes;
-  for (long long pb = blockIdx.x * static_cast<long long>(lanes) + threadIdx.x / cv; pb < p.num_pixels;
-       pb += pstride * kU) {
-    BnBwdRaw raw[kU];
-    bool ok[kU];
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      const long long pix = pb + j * pstride;
-      ok[j] = pix < p.num_pixels;
-      if (ok[j]) bn_bwd_issue_loads(p, pix, c0, pix * cv + myc, raw[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      if (!ok[j]) continue;
-      float g[8], yv[8];
-      bn_bwd_decode(p, raw[j], g, yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sg[i] += g[i];
-        sx[i] += g[i] * (yv[i] - mean[i]) * rstd[i];
-      }
-    }
-  }
-  // combine the threads of a warp that own the same channel vector (lane ids congruent mod cv)
-  for (int o = 16; o >= cv; o >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sg[i] += __shfl_xor_sync(0xffffffffu, sg[i], o);
-      sx[i] += __shfl_xor_sync(0xffffffffu, sx[i], o);
-    }
-  }
-  if ((threadIdx.x & 31) < cv) {  // lanes 0..cv-1 of every warp own distinct channel vectors
-    float* mine = s_acc[threadIdx.x >> 5];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      mine[c0 + i] = sg[i];
-      mine[p.C + c0 + i] = sx[i];
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
-    float t = 0.f;
-#pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += s_acc[wv][i];
-    p.part[static_cast<long long>(blockIdx.x) * 2 * p.C + i] = t;
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
-  __shared__ float s_k[64], s_a[64], s_b[64], s_mean[64], s_rstd[64], s_sum[2][128];
-  const float inv_m = 1.f / static_cast<float>(p.num_pixels);
-  {
-    // every block adds the reduce kernel's per-block partial rows in the same fixed order (two interleaved halves)
-    const int V = 2 * p.C, half = threadIdx.x / 128, v = threadIdx.x % 128;
-    float t = 0.f;
-    if (v < V)
-      for (int r0 = half; r0 < p.nparts; r0 += 2 * 16) {  // sixteen independent loads in flight, added in row order
-        float q[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = r0 + 2 * j;
-          q[j] = r < p.nparts ? __ldcg(p.part + static_cast<long long>(r) * V + v) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) t += q[j];
-      }
-    s_sum[half][v] = t;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float rstd = p.saved[p.C + c];
-    const float db = s_sum[0][c] + s_sum[1][c], dg = s_sum[0][p.C + c] + s_sum[1][p.C + c];
-    s_mean[c] = p.saved[c];
-    s_rstd[c] = rstd;
-    s_k[c] = p.gamma[c] * rstd;          // dL/dy = k * (gz - a - xhat * b)
-    s_a[c] = db * inv_m;
-    s_b[c] = dg * inv_m;
-    if (blockIdx.x == 0) {  // the parameter gradients of this BatchNorm
-      p.dbeta[c] = db;
-      p.dgamma[c] = dg;
-    }
-  }
-  __syncthreads();
-  constexpr int kU = 2;
-  const int cv = p.C / 8;
-  const long long total = p.num_pixels * cv;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const int c0 = static_cast<int>(v0 % cv) * 8;
-  float kk[8], aa[8], bb[8], mm[8], rr[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    kk[i] = s_k[c0 + i]; aa[i] = s_a[c0 + i]; bb[i] = s_b[c0 + i]; mm[i] = s_mean[c0 + i]; rr[i] = s_rstd[c0 + i];
-  }
-  for (long long vb = v0; vb < total; vb += stride * kU) {
-    BnBwdRaw raw[kU];
-    bool ok[kU];
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      const long long v = vb + j * stride;
-      ok[j] = v < total;
-      if (ok[j]) bn_bwd_issue_loads(p, v / cv, c0, v, raw[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < kU; ++j) {
-      if (!ok[j]) continue;
-      const long long v = vb + j * stride;
-      float g[8], yv[8], o[8];
-      bn_bwd_decode(p, raw[j], g, yv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xhat = (yv[i] - mm[i]) * rr[i];
-        o[i] = kk[i] * (g[i] - aa[i] - xhat * bb[i]);
-      }
-      const uint4 q = float_to_bf16x8(o);
-      reinterpret_cast<uint4*>(p.gy)[v] = q;
-      if (p.gy_up) {
-        const long long pix = v / cv;
-        const int w = static_cast<int>(pix % p.Wo);
-        const int h = static_cast<int>((pix / p.Wo) % p.Ho);
-        const long long n = pix / (static_cast<long long>(p.Wo) * p.Ho);
-        const long long up = ((n * (2 * p.Ho) + 2 * h) * (2 * p.Wo) + 2 * w) * p.C + c0;
-        *reinterpret_cast<uint4*>(p.gy_up + up) = q;
-      }
-      if (p.gz) reinterpret_cast<uint4*>(p.gz)[v] = float_to_bf16x8(g);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ pool + FC
 // One CTA (64 threads) per image: feats = mean over the 8x8 map; logits = feats . W^T + b over C_seen rows.
 __global__ void __launch_bounds__(64) pool_fc_fwd_kernel(const __nv_bfloat16* __restrict__ act, int HW, int D,
@@ -351,39 +122,28 @@ __global__ void __launch_bounds__(64) pool_fc_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-// blocks [0, C_seen): dW[j][:] and db[j];  blocks [C_seen, C_seen + B): dfeats[b][:].  256 threads = 4 groups of 64
-// (one per feature column) that split the reduction 4 ways; fixed-order combine, no atomics.
+// One block per class row j: dW[j][:] = sum_n dlogits[n][j] feats[n][:] and db[j] = sum_n dlogits[n][j].  256 threads =
+// 4 groups of 64 (one per feature column) that split the batch 4 ways; fixed-order combine, no atomics.  (The data
+// gradient dfeats = dlogits . W is computed by head_bwd_kernel, head_kernels.cuh.)
 __global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ feats,
-                                                     const float* __restrict__ W, int B, int C_seen, int D,
-                                                     float* __restrict__ dW, float* __restrict__ db,
-                                                     float* __restrict__ dfeats) {
+                                                     int B, int C_seen, int D, float* __restrict__ dW,
+                                                     float* __restrict__ db) {
   __shared__ float s_acc[4][64], s_accb[4];
   const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  if (static_cast<int>(blockIdx.x) < C_seen) {
-    const int j = blockIdx.x;
-    float acc = 0.f, accb = 0.f;
+  const int j = blockIdx.x;
+  float acc = 0.f, accb = 0.f;
 #pragma unroll 8
-    for (int n = grp; n < B; n += 4) {
-      const float g = __ldg(dlogits + static_cast<long long>(n) * C_seen + j);
-      acc = fmaf(g, __ldg(feats + static_cast<long long>(n) * D + c), acc);
-      accb += g;
-    }
-    s_acc[grp][c] = acc;
-    if (c == 0) s_accb[grp] = accb;
-    __syncthreads();
-    if (grp == 0) {
-      dW[static_cast<long long>(j) * D + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
-      if (c == 0) db[j] = (s_accb[0] + s_accb[1]) + (s_accb[2] + s_accb[3]);
-    }
-  } else {
-    const int n = blockIdx.x - C_seen;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int j = grp; j < C_seen; j += 4)
-      acc = fmaf(__ldg(dlogits + static_cast<long long>(n) * C_seen + j), __ldg(W + static_cast<long long>(j) * D + c), acc);
-    s_acc[grp][c] = acc;
-    __syncthreads();
-    if (grp == 0) dfeats[static_cast<long long>(n) * D + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
+  for (int n = grp; n < B; n += 4) {
+    const float g = __ldg(dlogits + static_cast<long long>(n) * C_seen + j);
+    acc = fmaf(g, __ldg(feats + static_cast<long long>(n) * D + c), acc);
+    accb += g;
+  }
+  s_acc[grp][c] = acc;
+  if (c == 0) s_accb[grp] = accb;
+  __syncthreads();
+  if (grp == 0) {
+    dW[static_cast<long long>(j) * D + c] = (s_acc[0][c] + s_acc[1][c]) + (s_acc[2][c] + s_acc[3][c]);
+    if (c == 0) db[j] = (s_accb[0] + s_accb[1]) + (s_accb[2] + s_accb[3]);
   }
 }
 

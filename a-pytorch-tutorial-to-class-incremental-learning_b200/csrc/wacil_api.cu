@@ -13,6 +13,7 @@
 #include "tc_conv.cuh"
 #include "tc_chain.cuh"
 #include "tc_fc.cuh"
+#include "head_kernels.cuh"
 
 using namespace wacil;
 
@@ -1114,11 +1115,6 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
   if (n->engine == ENGINE_CHAIN) ce = cudaMemsetAsync(n->ws + n->off.sync_b, 0, n->off.sync_b_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "sync clear");
   float* dfeats = n->at<float>(n->off.dfeats);
-  fc_bwd_kernel<<<C_seen + n->batch, 256, 0, st>>>(dlogits, n->last_feats, n->params + n->lay.fc_weight_off, n->batch,
-                                                  C_seen, kFeatDim, n->grads + n->lay.fc_weight_off,
-                                                  n->grads + n->lay.fc_bias_off, dfeats);
-  WACIL_LAUNCH_CHECK("fc_bwd_kernel");
-  ++launches;
   const float* saved = n->at<float>(n->off.saved);
   std::vector<size_t> soff(nl);
   {
@@ -1126,35 +1122,45 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     for (int l = 0; l < nl; ++l) { soff[l] = o; o += 2 * n->L[l].cout; }
   }
   {
-    // the last layer's gradient comes from the pooled features: stand-alone ReLU-mask + BatchNorm backward
+    // The last layer's gradient comes from the pooled features: ONE cooperative launch computes the classifier's data
+    // gradient, the ReLU mask and the BatchNorm backward of that layer (head_kernels.cuh); the classifier's weight
+    // gradient runs on the weight-gradient branch (below).
     const int l = nl - 1;
     const LayerDesc& d = n->L[l];
-    BnBwdParams bp{};
-    bp.g_pool = dfeats;
-    bp.inv_hw = 1.f / static_cast<float>(d.H_out * d.H_out);
-    bp.act = n->at<__nv_bfloat16>(n->off.a[l]);
-    bp.y = n->at<__nv_bfloat16>(n->off.y[l]);
-    bp.saved = saved + soff[l];
-    bp.gamma = n->params + d.gamma_off;
-    bp.dgamma = n->grads + d.gamma_off;
-    bp.dbeta = n->grads + d.beta_off;
-    bp.gy = n->at<__nv_bfloat16>(n->off.gy[l]);
-    bp.gy_up = d.stride == 2 ? n->at<__nv_bfloat16>(n->off.gyup[l]) : nullptr;
-    bp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
-    bp.C = d.cout;
-    bp.Ho = d.H_out;
-    bp.Wo = d.H_out;
-    bp.num_pixels = static_cast<long long>(n->batch) * d.H_out * d.H_out;
-    const int lanes = 256 / (d.cout / 8);
-    int rgrid = static_cast<int>((bp.num_pixels + lanes - 1) / lanes);
-    if (rgrid > num_sms()) rgrid = num_sms();
-    bp.part = n->at<float>(n->off.bstats) + 2 * soff[l] * num_sms();  // this layer's [SMs][2*cout] rows (no chain element uses them)
-    bp.nparts = rgrid;
-    bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(bp);
-    WACIL_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-    bn_bwd_apply_kernel<<<ew_grid(bp.num_pixels * d.cout / 8 / 2), 256, 0, st>>>(bp);
-    WACIL_LAUNCH_CHECK("bn_bwd_apply_kernel");
-    launches += 2;
+    HeadBwdParams hp{};
+    hp.dlogits = dlogits;
+    hp.W = n->params + n->lay.fc_weight_off;
+    hp.B = n->batch;
+    hp.C_seen = C_seen;
+    hp.HW = d.H_out * d.H_out;
+    hp.act = n->at<__nv_bfloat16>(n->off.a[l]);
+    hp.y = n->at<__nv_bfloat16>(n->off.y[l]);
+    hp.saved = saved + soff[l];
+    hp.gamma = n->params + d.gamma_off;
+    hp.dgamma = n->grads + d.gamma_off;
+    hp.dbeta = n->grads + d.beta_off;
+    hp.dfeats = dfeats;
+    hp.gy = n->at<__nv_bfloat16>(n->off.gy[l]);
+    hp.gz = (l >= 2 && l % 2 == 0) ? n->at<__nv_bfloat16>(n->off.gz[((l - 2) / 2) % 2]) : nullptr;
+    hp.table = reinterpret_cast<unsigned*>(n->at<float>(n->off.bstats) + 2 * soff[l] * num_sms());  // this layer's rows
+    hp.counter = n->at<unsigned>(n->off.gbar) + 4 * nl;  // past the per-launch counters of the fused conv launches
+    hp.num_pixels = static_cast<long long>(n->batch) * hp.HW;
+    const int grid = std::min(n->batch, num_sms());
+    hp.pix_per_cta = static_cast<int>((hp.num_pixels + grid - 1) / grid);
+    if (d.cout != kFeatDim || d.stride != 1 || (hp.pix_per_cta + hp.HW - 1) / hp.HW + 1 > kHeadMaxImgs)
+      return fail(WACIL_E_SHAPE, "head backward: cout %d stride %d batch %d", d.cout, d.stride, n->batch);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kHeadThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;  // the CTAs wait for each other's partial sums: all must be resident
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, head_bwd_kernel, hp);
+    if (le != cudaSuccess) return cuda_fail(le, "head_bwd_kernel");
+    ++launches;
   }
   // GY_{nl-1} is ready.  Every chain launch produces the gradients GY_{l-1} of its layers l; the weight gradient of
   // layer l needs (a_{l-1}, GY_l), so the weight gradients of a launch's OUTPUTS start when the launch ends and run
@@ -1228,6 +1234,12 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     WACIL_EV(cudaEventRecord(n->ev_chain[0], st), "event record");
     WACIL_EV(cudaStreamWaitEvent(ws, n->ev_chain[0], 0), "event wait");
   }
+  // the classifier's weight and bias gradients: first on the weight-gradient branch (head_bwd_kernel has done the data
+  // gradient)
+  fc_bwd_kernel<<<C_seen, 256, 0, ws>>>(dlogits, n->last_feats, n->batch, C_seen, kFeatDim,
+                                        n->grads + n->lay.fc_weight_off, n->grads + n->lay.fc_bias_off);
+  WACIL_LAUNCH_CHECK("fc_bwd_kernel");
+  ++launches;
   if ((e = wgrads(nl - 1, nl - 1))) return e;
   for (size_t ci = 0; ci < n->bchains.size(); ++ci) {
     const ChainPlan& c = n->bchains[ci];
