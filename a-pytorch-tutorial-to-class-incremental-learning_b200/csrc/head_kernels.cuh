@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(const HeadBwdPar
   const int img0 = static_cast<int>(pix0 / p.HW);
   const int nimg = pix1 > pix0 ? static_cast<int>((pix1 - 1) / p.HW) - img0 + 1 : 0;
   const float inv_hw = 1.f / static_cast<float>(p.HW);
+  // programmatic dependent launch: this grid may have been started under the tail of the loss kernel, and lets the
+  // first fused backward launch run its prologue (barriers, TMEM, weight TMA) under this one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- the classifier's data gradient of this CTA's images (4 groups of 64 threads take images round robin)
   for (int i = tid >> 6; i < nimg; i += 4) {
     const int c = tid & 63, n = img0 + i;

@@ -1153,11 +1153,13 @@ int wacil_net_backward(wacil_net_t* n, const float* dlogits, int C_seen, void* s
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kHeadThreads);
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeCooperative;  // the CTAs wait for each other's partial sums: all must be resident
     at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, head_bwd_kernel, hp);
     if (le != cudaSuccess) return cuda_fail(le, "head_bwd_kernel");
     ++launches;
