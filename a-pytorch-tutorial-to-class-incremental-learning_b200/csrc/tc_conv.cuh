@@ -26,9 +26,10 @@ enum ConvEpilogue : int {
   EPI_RAW = 0,    // bf16 store of the accumulator
   EPI_STATS = 1,  // bf16 store + per-channel sum / sum-of-squares of the stored (rounded) values
   EPI_INFER = 2,  // + bias[c] (+ residual) -> ReLU -> bf16 store   (BatchNorm folded into weights/bias)
-  // Fused modes: cooperative launch, every tile of the CTA keeps its accumulator in TMEM across a grid barrier.
-  EPI_BN_TRAIN = 3,  // fprop: store y, batch statistics -> grid barrier -> BatchNorm + shortcut + ReLU -> store a
-  EPI_BNBWD = 4,     // dgrad: gz = (acc + shortcut grad) * relu mask, d-gamma/d-beta -> grid barrier -> gy (BN backward)
+  // Fused modes: cooperative launch, every tile of the CTA keeps its accumulator in TMEM across the exchange of the
+  // per-CTA partial sums (published_row_sum4).
+  EPI_BN_TRAIN = 3,  // fprop: store y, batch statistics -> exchange -> BatchNorm + shortcut + ReLU -> store a
+  EPI_BNBWD = 4,     // dgrad: gz = (acc + shortcut grad) * relu mask, d-gamma/d-beta -> exchange -> gy (BN backward)
 };
 
 struct ConvGemmParams {
@@ -45,9 +46,10 @@ struct ConvGemmParams {
   int tps;        // taps per pipeline stage (one mbarrier round trip per stage)
   int epi;
   __nv_bfloat16* out;        // [num_pixels][nc]
-  float* stats;              // [2*nc] sum, sumsq (EPI_STATS; global atomics, zero before the launch).  Fused modes:
-                             // [gridDim.x][2*nc] per-CTA partial sums (BN_TRAIN: sum, sumsq; BNBWD: d-beta, d-gamma), plain
-                             // stores before the grid barrier, summed in CTA order by every CTA after it (deterministic)
+  float* stats;              // [2*nc] sum, sumsq (EPI_STATS, a single-op diagnostic mode: global atomics, zero before the
+                             // launch).  Fused modes: two buffers of [gridDim.x][2*nc] complemented words, the per-CTA
+                             // partial sums (BN_TRAIN: sum, sumsq; BNBWD: d-beta, d-gamma) that every CTA publishes, polls
+                             // and adds in CTA order (deterministic); zero before the first launch
   const float* bias;         // [nc] (EPI_INFER)
   const __nv_bfloat16* res;  // residual (EPI_INFER) or nullptr
   int res_stride;            // 1: same geometry as out; 2: residual is [N][2Ho][2Wo][res_c] sampled at even pixels

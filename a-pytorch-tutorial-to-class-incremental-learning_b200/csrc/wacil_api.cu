@@ -360,7 +360,7 @@ int launch_conv(const ConvLaunch& c, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
-  if (c.p.epi >= EPI_BN_TRAIN) {  // fused BatchNorm modes hold a grid barrier: all CTAs must be co-resident
+  if (c.p.epi >= EPI_BN_TRAIN) {  // fused BatchNorm modes wait for each other's partial sums: all CTAs must be co-resident
     attrs[na].id = cudaLaunchAttributeCooperative;
     attrs[na].val.cooperative = 1;
     ++na;

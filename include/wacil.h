@@ -250,13 +250,15 @@ int wacil_net_tensor(const wacil_net_t* net, int what, int layer, void** ptr, si
 /* Number of kernels the last forward / backward call launched (for bench.py's gpu_launches). */
 int wacil_net_last_launches(const wacil_net_t* net);
 
-/* The convolution layers of a plan run as a few persistent "chain" launches (several layers per cooperative launch,
- * csrc/tc_chain.cuh).  Introspection + profiling: number of chain launches of the forward (backward = 0) or of the
- * data-gradient pass (backward = 1); layout of one of them; and a stand-alone run of ONE chain launch on the plan's
- * own buffers (after a forward, and for backward chains after a backward, so that its inputs hold real data) —
- * bench.py times the dominant kernel this way.  dbg: NULL, or [grid][n_layers][48] int64 clock64 stamps
- * (epilogue: phase 1 done, grid barrier passed, phase 2 stored, published; producer: dependencies met, last load issued;
- * MMA warp: first operands landed, last MMA issued). */
+/* The convolution layers of a plan are a list of launch elements: one layer each in the default per-layer engine
+ * (conv_gemm_kernel*, csrc/tc_conv.cuh), several layers per persistent cooperative launch with WACIL_ENGINE=chain
+ * (csrc/tc_chain.cuh, kept under the parity tests; slower, profiles/r02_chain_experiments.md).  Introspection +
+ * profiling: number of elements of the forward (backward = 0) or of the data-gradient pass (backward = 1); layout of
+ * one of them; and a stand-alone run of ONE element on the plan's own buffers (after a forward, and for backward
+ * elements after a backward, so that its inputs hold real data) — tools/layer_timeline.py and the ncu drivers use it.
+ * dbg: NULL, or clock64 stamps: per-layer engine [grid][16] int64 (slots: 1 setup, 2 last load issued, 3 weights landed,
+ * 4 first operands landed, 5 last MMA issued, 7 phase 1 done, 8 all partial sums seen, 13 constants ready, 9 phase 2
+ * done, 10 exit); chain engine [grid][n_layers][48]. */
 int wacil_net_chain_count(const wacil_net_t* net, int backward);
 int wacil_net_chain_info(const wacil_net_t* net, int backward, int index, int* first_layer, int* n_layers, int* grid,
                          int* epilogue_warps, size_t* smem_bytes);
